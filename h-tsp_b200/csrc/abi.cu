@@ -1,0 +1,150 @@
+// extern "C" entry points of libhtsp_b200 that are not defined next to their kernels:
+// library bookkeeping, weight packing, encode and decode dispatch.  See include/htsp_b200.h.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+#include <atomic>
+#include <vector>
+#include "common.cuh"
+
+namespace htsp {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+}  // namespace htsp
+
+using namespace htsp;
+
+extern "C" int htsp_abi_version(void) { return HTSP_ABI_VERSION; }
+extern "C" const char* htsp_last_error(void) { return g_err; }
+extern "C" uint64_t htsp_launch_count(void) { return g_launches.load(); }
+
+extern "C" size_t htsp_weights_blob_bytes(int n_layers) {
+  if (n_layers < 0) return 0;
+  return dec_off(n_layers).end * sizeof(float);
+}
+extern "C" int htsp_n_weight_tensors(int n_layers) { return 2 + 17 * n_layers + 9; }
+
+extern "C" int htsp_pack_weights(const float* const* t, int n_tensors, int n_layers,
+                                 void* dev_blob, void* stream) {
+  HTSP_REQUIRE(t && dev_blob, "null pointer");
+  HTSP_REQUIRE(n_layers >= 0 && n_tensors == htsp_n_weight_tensors(n_layers), "tensor count");
+  for (int i = 0; i < n_tensors; ++i) HTSP_REQUIRE(t[i] != nullptr, "null tensor");
+  const DecOff d = dec_off(n_layers);
+  std::vector<float> blob(d.end);
+  float* o = blob.data();
+  int k = 0;
+  memcpy(o + kEncInitW, t[k++], sizeof(float) * H * 2);
+  memcpy(o + kEncInitB, t[k++], sizeof(float) * H);
+  auto fold_bn = [&](const float* w, const float* b, const float* rm, const float* rv, float* alpha,
+                     float* beta) {
+    for (int c = 0; c < H; ++c) {  // eval BatchNorm1d, eps 1e-5 (models.py:35,37)
+      const float invstd = 1.0f / sqrtf(rv[c] + 1e-5f);
+      alpha[c] = invstd * w[c];
+      beta[c] = b[c] - rm[c] * alpha[c];
+    }
+  };
+  for (int l = 0; l < n_layers; ++l) {
+    const EncLayerOff e = enc_layer_off(l);
+    memcpy(o + e.wqkv, t[k++], sizeof(float) * H * H);                  // Wq
+    memcpy(o + e.wqkv + (size_t)H * H, t[k++], sizeof(float) * H * H);  // Wk
+    memcpy(o + e.wqkv + (size_t)2 * H * H, t[k++], sizeof(float) * H * H);  // Wv
+    memcpy(o + e.wo, t[k++], sizeof(float) * H * H);
+    memcpy(o + e.bo, t[k++], sizeof(float) * H);
+    memcpy(o + e.w1, t[k++], sizeof(float) * FF * H);
+    memcpy(o + e.b1, t[k++], sizeof(float) * FF);
+    memcpy(o + e.w2, t[k++], sizeof(float) * H * FF);
+    memcpy(o + e.b2, t[k++], sizeof(float) * H);
+    fold_bn(t[k], t[k + 1], t[k + 2], t[k + 3], o + e.bn1a, o + e.bn1b); k += 4;
+    fold_bn(t[k], t[k + 1], t[k + 2], t[k + 3], o + e.bn2a, o + e.bn2b); k += 4;
+  }
+  const float* wq_graph = t[k++]; const float* wq_source = t[k++]; const float* wq_target = t[k++];
+  const float* wq_first = t[k++]; const float* wq_last = t[k++];
+  const float* wk = t[k++]; const float* wv = t[k++]; const float* wc = t[k++]; const float* bc = t[k++];
+  memcpy(o + d.wg, wq_graph, sizeof(float) * H * H);
+  memcpy(o + d.ws, wq_source, sizeof(float) * H * H);
+  memcpy(o + d.wt, wq_target, sizeof(float) * H * H);
+  memcpy(o + d.wproj + (size_t)0 * H * H, wk, sizeof(float) * H * H);
+  memcpy(o + d.wproj + (size_t)1 * H * H, wv, sizeof(float) * H * H);
+  memcpy(o + d.wproj + (size_t)2 * H * H, wq_last, sizeof(float) * H * H);
+  memcpy(o + d.wproj + (size_t)3 * H * H, wq_first, sizeof(float) * H * H);
+  for (int i = 0; i < H; ++i)
+    for (int c = 0; c < H; ++c) o[d.wproj + (size_t)4 * H * H + (size_t)i * H + c] = wc[(size_t)c * H + i];
+  memcpy(o + d.wc, wc, sizeof(float) * H * H);
+  memcpy(o + d.bc, bc, sizeof(float) * H);
+  // synchronous copy: the staging vector dies at return
+  HTSP_CHECK_CUDA(cudaMemcpyAsync(dev_blob, o, d.end * sizeof(float), cudaMemcpyHostToDevice,
+                                  (cudaStream_t)stream));
+  HTSP_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return HTSP_OK;
+}
+
+extern "C" size_t htsp_encode_workspace_bytes(int Bp, int N, int mode) {
+  (void)mode;
+  if (Bp <= 0 || N <= 0) return 0;
+  return encode_f32_ws_floats(Bp, N) * sizeof(float);
+}
+
+extern "C" int htsp_encode(const void* blob, int n_layers, const float* x, int Bp, int N, int mode,
+                           float* emb, void* workspace, size_t workspace_bytes, void* stream) {
+  HTSP_REQUIRE(blob && x && emb, "null pointer");
+  HTSP_REQUIRE(Bp >= 0 && N >= 1 && n_layers >= 0, "bad shape");
+  HTSP_REQUIRE(mode >= HTSP_MODE_FP32 && mode <= HTSP_MODE_TC_FAST, "bad mode");
+  if (Bp == 0) return HTSP_OK;
+  if (workspace == nullptr || workspace_bytes < htsp_encode_workspace_bytes(Bp, N, mode)) {
+    set_error("htsp_encode: workspace too small (%zu < %zu)", workspace_bytes,
+              htsp_encode_workspace_bytes(Bp, N, mode));
+    return HTSP_ERR_WORKSPACE;
+  }
+  return launch_encode_f32((const float*)blob, n_layers, x, Bp, N, emb, (float*)workspace,
+                           (cudaStream_t)stream);
+}
+
+static size_t dec_proj_bytes(int Bp, int N) { return align_up((size_t)Bp * N * PROJ * 4, 256); }
+static size_t dec_qfix_bytes(int Bp) { return align_up((size_t)Bp * H * 4, 256); }
+static size_t dec_c0_bytes(int Bp, int N) { return align_up((size_t)Bp * N * 4, 256); }
+
+extern "C" size_t htsp_decode_workspace_bytes(int Bp, int N, int G, int mode) {
+  (void)G;
+  if (Bp <= 0 || N <= 0) return 0;
+  size_t b = dec_proj_bytes(Bp, N) + dec_qfix_bytes(Bp) + dec_c0_bytes(Bp, N);
+  if (mode != HTSP_MODE_FP32) b += decode_mma_pack_bytes(Bp, N);
+  return b;
+}
+
+extern "C" int htsp_decode(const void* blob, int n_layers, const float* x, const float* emb,
+                           const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp,
+                           int N, int G, int mode, const int32_t* forced_pi, int32_t* pi,
+                           float* reward, float* logits_out, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  HTSP_REQUIRE(blob && x && emb && src && tgt && first && pi && reward, "null pointer");
+  HTSP_REQUIRE(Bp >= 0 && N >= 3 && G >= 1 && G <= N && n_layers >= 0, "bad shape");
+  HTSP_REQUIRE(mode >= HTSP_MODE_FP32 && mode <= HTSP_MODE_TC_FAST, "bad mode");
+  if (Bp == 0) return HTSP_OK;
+  if (workspace == nullptr || workspace_bytes < htsp_decode_workspace_bytes(Bp, N, G, mode)) {
+    set_error("htsp_decode: workspace too small (%zu < %zu)", workspace_bytes,
+              htsp_decode_workspace_bytes(Bp, N, G, mode));
+    return HTSP_ERR_WORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  char* w = (char*)workspace;
+  float* proj = (float*)w; w += dec_proj_bytes(Bp, N);
+  float* qfix = (float*)w; w += dec_qfix_bytes(Bp);
+  float* c0 = (float*)w;   w += dec_c0_bytes(Bp, N);
+  int rc = launch_decode_prep((const float*)blob, n_layers, emb, src, tgt, Bp, N, proj, qfix, c0, s);
+  if (rc) return rc;
+  if (mode == HTSP_MODE_FP32)
+    return launch_decode_f32((const float*)blob, n_layers, x, emb, proj, qfix, src, tgt, first, Bp,
+                             N, G, forced_pi, pi, reward, logits_out, s);
+  return launch_decode_mma(x, proj, qfix, c0, src, tgt, first, Bp, N, G, mode, forced_pi, pi, reward,
+                           logits_out, w, s);
+}

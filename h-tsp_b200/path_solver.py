@@ -1,0 +1,254 @@
+"""B200PathSolver: drop-in for the reference's rl4cop PathSolver *inference* interface
+(rl4cop/train_path_solver.py:170-311) -- same constructor-from-state_dict keys, `.device`,
+`.eval()/.train()/.training`, and the same `forward(batch, source_nodes, target_nodes,
+val_type, return_pi, group_size, greedy)` call -- with every tensor op replaced by the
+sm_100a kernels of libhtsp_b200.so (C ABI, include/htsp_b200.h).  torch is used for device
+memory, streams and the host RNG call the reference makes (`torch.randperm`, :256)."""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Dict, Optional
+
+import torch
+
+from . import _abi
+from .weights import EMBED_DIM, FF_DIM, expected_keys, n_layers_of
+
+
+class _EncLayerParams(torch.nn.Module):
+    """Parameter container with the reference's names (models.py:12-28); never called."""
+
+    def __init__(self, H: int, F: int):
+        super().__init__()
+        self.Wq = torch.nn.Linear(H, H, bias=False)
+        self.Wk = torch.nn.Linear(H, H, bias=False)
+        self.Wv = torch.nn.Linear(H, H, bias=False)
+        self.multi_head_combine = torch.nn.Linear(H, H)
+        self.feed_forward = torch.nn.Sequential(torch.nn.Linear(H, F), torch.nn.ReLU(),
+                                                torch.nn.Linear(F, H))
+        self.norm1 = torch.nn.BatchNorm1d(H)
+        self.norm2 = torch.nn.BatchNorm1d(H)
+
+
+class _EncParams(torch.nn.Module):
+    def __init__(self, n_layers: int, H: int, F: int):
+        super().__init__()
+        self.init_projection_layer = torch.nn.Linear(2, H)
+        self.attn_layers = torch.nn.ModuleList([_EncLayerParams(H, F) for _ in range(n_layers)])
+
+
+class _DecParams(torch.nn.Module):
+    def __init__(self, H: int):
+        super().__init__()
+        for name in ("Wq_graph", "Wq_source", "Wq_target", "Wq_first", "Wq_last", "Wk", "Wv"):
+            setattr(self, name, torch.nn.Linear(H, H, bias=False))
+        self.multi_head_combine = torch.nn.Linear(H, H)
+
+
+class _Workspace:
+    """Grow-only device scratch buffers keyed by name (the C ABI never allocates)."""
+
+    def __init__(self):
+        self._bufs: Dict[str, torch.Tensor] = {}
+
+    def get(self, name: str, nbytes: int, device) -> torch.Tensor:
+        buf = self._bufs.get(name)
+        if buf is None or buf.numel() < nbytes or buf.device != device:
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            self._bufs[name] = buf
+        return buf
+
+
+class B200PathSolver(torch.nn.Module):
+    """mode: "fp32" (CUDA-core parity anchor), "x3" (tensor cores, split-fp16, default once
+    available) or "fast" (tensor cores, single-fp16 glimpse scores)."""
+
+    def __init__(self, cfg=None, state_dict: Optional[Dict[str, torch.Tensor]] = None,
+                 n_layers: Optional[int] = None, graph_size: int = 200, mode: str = "fp32",
+                 device="cuda"):
+        super().__init__()
+        if cfg is None:
+            if n_layers is None:
+                n_layers = n_layers_of(state_dict) if state_dict is not None else 6
+            cfg = SimpleNamespace(node_dim=2, encoder_type="mha", n_layers=n_layers, n_heads=8,
+                                  embedding_dim=EMBED_DIM, add_init_projection=True,
+                                  tanh_clipping=10, n_decoding_neighbors=None,
+                                  graph_size=graph_size, group_size=graph_size, precision=32,
+                                  val_type="x8Aug_nTraj")
+        assert cfg.encoder_type == "mha" and cfg.embedding_dim == EMBED_DIM and cfg.n_heads == 8
+        assert cfg.node_dim == 2 and cfg.tanh_clipping == 10 and cfg.n_decoding_neighbors is None
+        self.cfg = cfg
+        self.mode = mode
+        self.encoder = _EncParams(cfg.n_layers, EMBED_DIM, FF_DIM)
+        self.decoder = _DecParams(EMBED_DIM)
+        self._blob: Optional[torch.Tensor] = None
+        self._ws = _Workspace()
+        self.first_action_override: Optional[torch.Tensor] = None
+        self.max_instances_per_launch = 8192
+        self.to(device)
+        if state_dict is not None:
+            self.load_state_dict(state_dict, strict=False)
+        self.eval()
+
+    # -- reference surface ---------------------------------------------------------------
+    @property
+    def device(self) -> torch.device:
+        return self.encoder.init_projection_layer.weight.device
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        out = super().load_state_dict(state_dict, strict=strict)
+        self._blob = None
+        return out
+
+    def _apply(self, fn, *a, **k):
+        self._blob = None
+        return super()._apply(fn, *a, **k)
+
+    # -- weights -------------------------------------------------------------------------
+    def _packed_weights(self) -> torch.Tensor:
+        if self._blob is None:
+            lib = _abi.lib()
+            L = self.cfg.n_layers
+            sd = super().state_dict()
+            keys = expected_keys(L)
+            host = [sd[k].detach().to("cpu", torch.float32).contiguous() for k in keys]
+            assert len(host) == lib.htsp_n_weight_tensors(L)
+            arr = (_abi.C.c_void_p * len(host))(*[t.data_ptr() for t in host])
+            blob = torch.empty(lib.htsp_weights_blob_bytes(L), dtype=torch.uint8, device=self.device)
+            with torch.cuda.device(self.device):
+                st = torch.cuda.current_stream().cuda_stream
+                _abi.check(lib.htsp_pack_weights(arr, len(host), L, blob.data_ptr(), st),
+                           "htsp_pack_weights")
+            self._blob = blob
+        return self._blob
+
+    # -- stages (also used directly by the tests) ----------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def encode(self, x: torch.Tensor) -> torch.Tensor:
+        """MHAEncoder.forward (models.py:55-60): [Bp,N,2] -> [Bp,N,128]."""
+        lib = _abi.lib()
+        x = x.to(self.device, torch.float32).contiguous()
+        Bp, N, _ = x.shape
+        mode = _abi.MODES[self.mode]
+        emb = torch.empty(Bp, N, EMBED_DIM, dtype=torch.float32, device=self.device)
+        nbytes = lib.htsp_encode_workspace_bytes(Bp, N, mode)
+        ws = self._ws.get("enc", nbytes, self.device)
+        with torch.cuda.device(self.device):
+            _abi.check(lib.htsp_encode(self._packed_weights().data_ptr(), self.cfg.n_layers,
+                                       x.data_ptr(), Bp, N, mode, emb.data_ptr(), ws.data_ptr(),
+                                       ws.numel(), self._stream()), "htsp_encode")
+        return emb
+
+    def rollout(self, x: torch.Tensor, emb: torch.Tensor, src: torch.Tensor, tgt: torch.Tensor,
+                first: torch.Tensor, forced_pi: Optional[torch.Tensor] = None,
+                want_logits: bool = False):
+        """Greedy POMO rollout -> (pi [Bp,G,N] i32, reward [Bp,G] f32, logits or None)."""
+        lib = _abi.lib()
+        Bp, N, _ = x.shape
+        G = first.numel()
+        dev = self.device
+        mode = _abi.MODES[self.mode]
+        src = src.reshape(-1).to(dev, torch.int32).contiguous()
+        tgt = tgt.reshape(-1).to(dev, torch.int32).contiguous()
+        first = first.reshape(-1).to(dev, torch.int32).contiguous()
+        assert src.numel() == Bp and tgt.numel() == Bp
+        if forced_pi is not None:
+            forced_pi = forced_pi.to(dev, torch.int32).contiguous()
+            assert forced_pi.shape == (Bp, G, N)
+        pi = torch.empty(Bp, G, N, dtype=torch.int32, device=dev)
+        reward = torch.empty(Bp, G, dtype=torch.float32, device=dev)
+        logits = (torch.empty(Bp, G, N - 2, N, dtype=torch.float32, device=dev)
+                  if want_logits else None)
+        nbytes = lib.htsp_decode_workspace_bytes(Bp, N, G, mode)
+        ws = self._ws.get("dec", nbytes, dev)
+        with torch.cuda.device(dev):
+            _abi.check(lib.htsp_decode(self._packed_weights().data_ptr(), self.cfg.n_layers,
+                                       x.data_ptr(), emb.data_ptr(), src.data_ptr(),
+                                       tgt.data_ptr(), first.data_ptr(), Bp, N, G, mode,
+                                       _abi.ptr(forced_pi), pi.data_ptr(), reward.data_ptr(),
+                                       _abi.ptr(logits), ws.data_ptr(), ws.numel(),
+                                       self._stream()), "htsp_decode")
+        return pi, reward, logits
+
+    def select_best(self, reward: torch.Tensor, pi: torch.Tensor, n_aug: int):
+        """train_path_solver.py:293-306 -> (best_len [B] f32, best_pi [B,N] i64, best_row [B])."""
+        lib = _abi.lib()
+        Bp, G, N = pi.shape
+        B = Bp // n_aug
+        dev = self.device
+        best_len = torch.empty(B, dtype=torch.float32, device=dev)
+        best_row = torch.empty(B, dtype=torch.int32, device=dev)
+        best_pi = torch.empty(B, N, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            _abi.check(lib.htsp_select_best(reward.data_ptr(), pi.data_ptr(), n_aug, B, G, N,
+                                            best_len.data_ptr(), best_row.data_ptr(),
+                                            best_pi.data_ptr(), self._stream()), "htsp_select_best")
+        return best_len, best_pi, best_row
+
+    def draw_first_action(self, N: int, G: int) -> torch.Tensor:
+        """The reference's `torch.randperm(N, device=self.device)[None, :G]` (:256): same call,
+        same generator, so a seeded caller sees the same POMO starts on both sides."""
+        if self.first_action_override is not None:
+            fa = self.first_action_override.reshape(-1)
+            assert fa.numel() == G
+            return fa
+        return torch.randperm(N, device=self.device)[:G]
+
+    # -- PathSolver.forward (train_path_solver.py:224-311) ---------------------------------
+    @torch.no_grad()
+    def forward(self, batch, source_nodes, target_nodes, val_type="x8Aug_2Traj", return_pi=False,
+                group_size=2, greedy=True):
+        if not greedy:
+            raise NotImplementedError("sampling rollouts (greedy=False) are outside the B200 hot "
+                                      "path (SURVEY.md section 8f rank 4); use the reference module")
+        lib = _abi.lib()
+        val_type = val_type or self.cfg.val_type
+        dev = self.device
+        batch = batch.to(dev, torch.float32).contiguous()
+        B0, N, C = batch.shape
+        assert C == 2
+        G = int(group_size)
+        assert G <= self.cfg.graph_size
+        n_aug = 8 if "x8Aug" in val_type else 1
+        src = source_nodes.reshape(-1).to(dev)
+        tgt = target_nodes.reshape(-1).to(dev)
+        if n_aug == 8:
+            x = torch.empty(8 * B0, N, 2, dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                _abi.check(lib.htsp_augment8(batch.data_ptr(), B0, N, x.data_ptr(), self._stream()),
+                           "htsp_augment8")
+            # the reference repeat_interleaves the endpoints although the coordinates are
+            # block-major (:236-238); reproduced as is
+            src = torch.repeat_interleave(src, 8, dim=0)
+            tgt = torch.repeat_interleave(tgt, 8, dim=0)
+        else:
+            x = batch
+        first = self.draw_first_action(N, G)
+        pi, reward = self._rollout_chunked(x, src, tgt, first, n_aug)
+        if val_type == "noAug_1Traj":
+            max_reward, best_pi = reward, pi.to(torch.int64)
+        else:
+            best_len, best_pi, _ = self.select_best(reward, pi, n_aug)
+            max_reward = -best_len
+            best_pi = best_pi.reshape(B0, 1, N) if n_aug == 1 else best_pi.reshape(1, B0, 1, N)
+        if return_pi:
+            return -max_reward, best_pi.squeeze()
+        return -max_reward
+
+    def _rollout_chunked(self, x, src, tgt, first, n_aug):
+        Bp = x.shape[0]
+        cap = self.max_instances_per_launch
+        if Bp <= cap:
+            emb = self.encode(x)
+            pi, reward, _ = self.rollout(x, emb, src, tgt, first)
+            return pi, reward
+        pis, rs = [], []
+        for s in range(0, Bp, cap):
+            xs = x[s:s + cap]
+            emb = self.encode(xs)
+            p, r, _ = self.rollout(xs, emb, src[s:s + cap], tgt[s:s + cap], first)
+            pis.append(p)
+            rs.append(r)
+        return torch.cat(pis), torch.cat(rs)

@@ -1,0 +1,115 @@
+/*
+ * htsp_b200 -- C ABI of the B200-native (sm_100a) H-TSP lower-level path-solver hot path.
+ *
+ * The reference (Learning4Optimization-HUST/H-TSP) is pure Python/PyTorch and has no FFI:
+ * its boundary for this path is two duck-typed Python interfaces, RLSolver.solve
+ * (h_tsp.py:165-228) and PathSolver.forward (rl4cop/train_path_solver.py:224-311).  The
+ * entry points below are what a ctypes binding on the reference side calls instead of the
+ * eager ATen op sequences cited on each function (INTEGRATION.md shows the stub).
+ *
+ * Conventions: plain pointers and sizes only (no torch types); every pointer that is not
+ * explicitly "host" is a DEVICE pointer; all work is enqueued on `stream` (a cudaStream_t
+ * passed as void*) and nothing synchronises; no hidden allocation -- scratch memory is a
+ * caller-provided workspace sized by the matching *_workspace_bytes query; the return
+ * value is 0 on success and a negative htsp_status otherwise (htsp_last_error() has text).
+ * Shapes: B subproblems, A = 1 or 8 augmentations, Bp = A*B instances, N nodes per
+ * instance, G POMO starts (rows) per instance, H = 128, 8 heads x 16, FF 512.
+ */
+#ifndef HTSP_B200_H_
+#define HTSP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HTSP_ABI_VERSION 1
+#define HTSP_EMBED_DIM 128
+#define HTSP_N_HEADS 8
+#define HTSP_FF_DIM 512
+
+typedef enum {
+  HTSP_OK = 0,
+  HTSP_ERR_INVALID_ARG = -1,
+  HTSP_ERR_WORKSPACE = -2,
+  HTSP_ERR_CUDA = -3,
+  HTSP_ERR_UNSUPPORTED = -4
+} htsp_status;
+
+/* arithmetic of the decode/encode kernels */
+typedef enum {
+  HTSP_MODE_FP32 = 0,   /* fp32 FMA on CUDA cores, reference op order (parity anchor)        */
+  HTSP_MODE_TC_X3 = 1,  /* tensor cores, split-fp16 operands (hi+lo, 3 MMAs), fp32 accumulate */
+  HTSP_MODE_TC_FAST = 2 /* as X3 but glimpse QK^T with single fp16 operands                   */
+} htsp_mode;
+
+int htsp_abi_version(void);
+const char* htsp_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+uint64_t htsp_launch_count(void);
+
+/* ---- weights ------------------------------------------------------------------------
+ * Replaces PathSolver.load_state_dict + the per-call nn.Linear / BatchNorm1d parameter reads
+ * (rl4cop/models/models.py:12-60, 331-358).  `host_tensors` is a HOST array of HOST fp32
+ * pointers in the canonical order of htsp_b200.weights.expected_keys(n_layers).  Eval-mode
+ * BatchNorm (models.py:35,37, eps 1e-5) is folded to per-channel alpha/beta; Wq/Wk/Wv and
+ * the decoder projections are concatenated; multi_head_combine is also stored transposed.
+ * The packed blob (htsp_weights_blob_bytes) is written to device memory `dev_blob`.     */
+size_t htsp_weights_blob_bytes(int n_layers);
+int htsp_n_weight_tensors(int n_layers);
+int htsp_pack_weights(const float* const* host_tensors, int n_tensors, int n_layers,
+                      void* dev_blob, void* stream);
+
+/* ---- K1: subproblem extraction ------------------------------------------------------
+ * RLSolver.solve gather + min/max normalisation into [0.05,0.95]^2 (h_tsp.py:176-191) and
+ * utils.augment_xy_data_by_8_fold (rl4cop/utils/utils.py:37-56, block-major).
+ * data [B,Ntot,2] f32, fragment [B,N] i64 -> x_new [B,N,2], scale [B] (= s),
+ * x_aug [n_aug*B,N,2] (n_aug 1 or 8; may be NULL).                                       */
+int htsp_extract_normalize(const float* data, const int64_t* fragment, int B, int Ntot, int N,
+                           int n_aug, float* x_new, float* scale, float* x_aug, void* stream);
+int htsp_augment8(const float* x, int B, int N, float* x_aug, void* stream);
+
+/* ---- K2: encoder --------------------------------------------------------------------
+ * MHAEncoder.forward, eval mode (models.py:30-60; utils.py:12-34): x [Bp,N,2] -> emb [Bp,N,128]. */
+size_t htsp_encode_workspace_bytes(int Bp, int N, int mode);
+int htsp_encode(const void* blob, int n_layers, const float* x, int Bp, int N, int mode,
+                float* emb, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K3: POMO rollout ---------------------------------------------------------------
+ * PathDecoder.reset/forward (models.py:360-446), GroupState/Env (train_path_solver.py:23-149)
+ * and the decode loop + pi extraction (train_path_solver.py:252-288), greedy.
+ * src,tgt [Bp] i32; first [G] i32 (the reference's randperm(N)[:G], :256, drawn by the host);
+ * forced_pi [Bp,G,N] i32 or NULL (teacher forcing); outputs pi [Bp,G,N] i32 (cycle order
+ * from first[g]) and reward [Bp,G] f32 (= -(cycle length - |x[src]-x[tgt]|));
+ * logits_out [Bp,G,N-2,N] f32 or NULL receives the masked 10*tanh logits of every step.  */
+size_t htsp_decode_workspace_bytes(int Bp, int N, int G, int mode);
+int htsp_decode(const void* blob, int n_layers, const float* x, const float* emb, const int32_t* src,
+                const int32_t* tgt, const int32_t* first, int Bp, int N, int G, int mode,
+                const int32_t* forced_pi, int32_t* pi, float* reward, float* logits_out,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K4: best-of selection and path orientation ---------------------------------------
+ * train_path_solver.py:290-306 (max over G, then over the 8 augmentation blocks; first max
+ * wins) -> best_len [B] (= -max reward), best_pi [B,N] i64, best_row [B] i32 (a*G+g).
+ * htsp_finalize_paths: h_tsp.py:206-226 -- lengths / s, rotate to start at local 0, flip if
+ * it does not end at N-1, map through fragment to global ids; status[b] != 0 flags a row
+ * that violates the reference's asserts (h_tsp.py:218-224).                              */
+int htsp_select_best(const float* reward, const int32_t* pi, int n_aug, int B, int G, int N,
+                     float* best_len, int32_t* best_row, int64_t* best_pi, void* stream);
+int htsp_finalize_paths(const int64_t* best_pi, const int64_t* fragment, const float* best_len,
+                        const float* scale, int B, int N, int64_t* out_paths, float* out_len,
+                        int32_t* status, void* stream);
+
+/* ---- K5: tour length ----------------------------------------------------------------
+ * rl_utils.get_tour_distance over dist_matrix = fp32(cdist_fp64(1000 x)) (rl_utils.py:87-102,
+ * h_tsp.py:449-453,586-589) without the N x N matrix: closed-tour length of each of E tours.
+ * coords [E,Ntot,2] f32; tours [E,Tmax] i64; tour_len [E] i32 -> out [E] f32 (already / 1000). */
+int htsp_tour_length(const float* coords, const int64_t* tours, const int32_t* tour_len, int E,
+                     int Ntot, int Tmax, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HTSP_B200_H_ */

@@ -1,0 +1,62 @@
+"""CPU tests of the host-side logic that does not need the GPU."""
+import numpy as np
+import pytest
+import torch
+
+from htsp_b200.weights import expected_keys, n_layers_of, synthetic_state_dict
+from oracle import ref_loader
+
+
+def test_synthetic_weights_have_reference_keys_and_are_deterministic():
+    sd = synthetic_state_dict(1234, 6)
+    assert list(sd) == expected_keys(6) and n_layers_of(sd) == 6
+    sd2 = synthetic_state_dict(1234, 6)
+    assert all(torch.equal(sd[k], sd2[k]) for k in sd)
+    assert sum(v.numel() for k, v in sd.items() if "running" not in k) == 1318912
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not mounted")
+def test_reference_model_accepts_the_key_layout():
+    sd = synthetic_state_dict(1, 2)
+    m = ref_loader.build_reference_path_solver(sd, n_layers=2)
+    got = {k for k in m.state_dict() if not k.endswith("num_batches_tracked")}
+    assert got == set(expected_keys(2))
+
+
+def test_fragment_buffer_ring_semantics():
+    from htsp_b200.rl_solver import FragmentBuffer
+    fb = FragmentBuffer(5, 3, 2)
+    a = torch.arange(4 * 3 * 2, dtype=torch.float32).reshape(4, 3, 2)
+    fb.update_buffer(a)
+    assert fb.next_idx == 4 and fb.now_len == 4 and not fb.if_full
+    b = a + 100
+    fb.update_buffer(b[:3])          # wraps: 1 goes to the tail, 2 to the head
+    assert fb.if_full and fb.now_len == 5 and fb.next_idx == 2
+    assert torch.equal(fb.frag_buffer[4], b[0]) and torch.equal(fb.frag_buffer[0:2], b[1:3])
+    if ref_loader.available():
+        ref_loader.load_h_tsp_module()
+        import rl_utils
+        rb = rl_utils.FragmengBuffer(5, 3, 2)
+        rb.update_buffer(a)
+        rb.update_buffer(b[:3])
+        assert torch.equal(rb.frag_buffer, fb.frag_buffer) and rb.next_idx == fb.next_idx
+
+
+def test_product_package_does_not_import_the_oracle():
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "h-tsp_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
+
+
+def test_solver_refuses_without_the_cuda_library(monkeypatch, tmp_path):
+    from htsp_b200 import _abi
+    monkeypatch.setattr(_abi, "_lib", None)
+    monkeypatch.setattr(_abi, "LIB_PATH", str(tmp_path / "missing.so"))
+    with pytest.raises(_abi.HtspError):
+        _abi.lib()
