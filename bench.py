@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the H-TSP lower-level path-solver hot path on B200.
+
+Metric (BASELINE.json): 200-node subpath solves/s.  Workload at N=1 = BASELINE config 2:
+"rl4cop path solver POMO (200 starts), batch 4096 subproblems on 1 B200": coordinates
+torch.rand(B,200,2) (seed 1234), src=0, tgt=199, G=200 starts, noAug_nTraj, 6-layer encoder,
+random-init weights (htsp_b200.weights.synthetic_state_dict(1234, 6)).  One "step" = one pass of
+the hot path over one batch: encoder -> POMO rollout (198 decode steps x 200 rows) -> path
+length -> best-of-G selection.  Multi-GPU (torchrun, one rank per GPU): weak scaling, every rank
+solves its own 4096 subproblems and the selected tours are all-gathered over NCCL each step.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--mode fp32|x3|fast]
+
+`--impl reference` times the reference's algorithm on the host CPU (the oracle port of the pure
+Python reference -- /root/reference itself cannot travel to the GPU box) on a bounded sample.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "200-node subpath solves/sec (rl4cop path solver, POMO 200 starts, greedy)"
+UNIT = "solves/s"
+H, FF = 128, 512
+
+
+def algorithmic_flops(N: int, G: int, L: int):
+    """FLOPs (2*MAC) per instance, hoisted count."""
+    enc = L * (24 * N * H * H + 4 * N * N * H) + 4 * N * H
+    reset = 2 * (3 * N * H * H + (G + 3) * H * H)
+    dec = (N - 2) * G * (6 * N * H + 2 * H * H)
+    return enc, reset, dec
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            d = json.load(open(p))
+            return float(d["bf16_tflops_sustained"]), float(d["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_inputs(B, N, seed, device=None, pin=False):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(B, N, 2, generator=g)
+    if pin:
+        x = x.pin_memory()
+    if device is not None:
+        x = x.to(device)
+    return x
+
+
+def cpu_oracle_throughput(N, G, L, sample_B, threads=None, repeats=1):
+    """The reference algorithm (oracle port, plain torch fp32) on the host cores."""
+    import torch
+    from htsp_b200.weights import synthetic_state_dict
+    from oracle import path_solver_oracle as po
+    if threads:
+        torch.set_num_threads(threads)
+    sd = synthetic_state_dict(1234, L)
+    x = make_inputs(sample_B, N, 4321)
+    src = torch.zeros(sample_B, 1, dtype=torch.long)
+    tgt = torch.full((sample_B, 1), N - 1, dtype=torch.long)
+    first = torch.randperm(N, generator=torch.Generator().manual_seed(7))[:G]
+    best = None
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            po.path_solver_forward(sd, x, src, tgt, first, val_type="noAug_nTraj", return_pi=True)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return sample_B / best, torch.get_num_threads(), best
+
+
+def run_reference(args):
+    """--impl reference: rank 0 only; each step = one bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from htsp_b200.weights import synthetic_state_dict
+    from oracle import path_solver_oracle as po
+    N, G, L = args.nodes, args.group, args.layers
+    sB = args.ref_sample
+    sd = synthetic_state_dict(1234, L)
+    src = torch.zeros(sB, 1, dtype=torch.long)
+    tgt = torch.full((sB, 1), N - 1, dtype=torch.long)
+    first = torch.randperm(N, generator=torch.Generator().manual_seed(7))[:G]
+    xs = [make_inputs(sB, N, 1234 + i) for i in range(args.warmup + args.steps)]
+    with torch.no_grad():
+        for i in range(args.warmup):
+            po.path_solver_forward(sd, xs[i], src, tgt, first, val_type="noAug_nTraj", return_pi=True)
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            po.path_solver_forward(sd, xs[args.warmup + i], src, tgt, first, val_type="noAug_nTraj",
+                                   return_pi=True)
+        dt = time.perf_counter() - t0
+    value = sB * args.steps / dt
+    cores = torch.get_num_threads()
+    sample = (f"{sB} of the {args.batch} subproblems per step (N={N}, G={G}, noAug_nTraj, L={L}), "
+              f"oracle port of the pure-Python reference, torch {torch.__version__} CPU fp32")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic uniform coords, random-init weights (seed 1234)",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample, "host_cpus": os.cpu_count()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_config(args):
+    return {"workload": f"BASELINE config 2: rl4cop path solver, POMO {args.group} starts, batch "
+                        f"{args.batch} subproblems of {args.nodes} nodes per GPU, noAug_nTraj, greedy",
+            "batch_per_gpu": args.batch, "nodes": args.nodes, "pomo_starts": args.group,
+            "encoder_layers": args.layers, "val_type": "noAug_nTraj", "arith": args.mode,
+            "l2": "per-step working set (embeddings + decoder tables, >2 GB) exceeds the 126 MB L2; "
+                  "a different input batch is used every step"}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import htsp_b200  # noqa: F401
+    from htsp_b200 import B200PathSolver, _abi
+    from htsp_b200.sharding import gather_tours
+    from htsp_b200.weights import synthetic_state_dict
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _abi.lib()
+    N, G, L, B = args.nodes, args.group, args.layers, args.batch
+    model = B200PathSolver(state_dict=synthetic_state_dict(1234, L), mode=args.mode, device=dev)
+    model.first_action_override = torch.randperm(N, generator=torch.Generator().manual_seed(7))[:G]
+    src = torch.zeros(B, 1, dtype=torch.long, device=dev)
+    tgt = torch.full((B, 1), N - 1, dtype=torch.long, device=dev)
+    n_in = min(args.warmup + args.steps, 4)
+    xs_dev = [make_inputs(B, N, 1234 + 97 * rank + i, device=dev) for i in range(n_in)]
+    xs_pin = [make_inputs(B, N, 1234 + 97 * rank + i, pin=True) for i in range(n_in)]
+    total = B * world
+
+    def step(i, timer=None):
+        if timer is not None:
+            lib.htsp_set_kernel_timer(timer[0].cuda_event, timer[1].cuda_event)
+        length, pi = model(xs_dev[i % n_in], src, tgt, val_type="noAug_nTraj", return_pi=True,
+                           group_size=G)
+        if world > 1:
+            pi, length = gather_tours(pi, length, total)
+        return length, pi
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (value) ------------------------------------------------
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    timers = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+              for _ in range(args.steps)]
+    for a, b in timers:       # materialise the cudaEvent_t handles; the library re-records them
+        a.record(); b.record()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.htsp_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        length, pi = step(args.warmup + i, timers[i])
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = lib.htsp_launch_count() - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    kern_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in timers) / args.steps], device=dev)
+    nl = torch.tensor([launches], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(nl, op=dist.ReduceOp.SUM)
+    total_ms = float(ms)
+    value = total * args.steps / (total_ms / 1e3)
+
+    # ---- end to end through the public API with HOST buffers --------------------------------
+    src_h, tgt_h = src.cpu(), tgt.cpu()
+    out_len = torch.empty(B, dtype=torch.float32).pin_memory()
+    out_pi = torch.empty(B, N, dtype=torch.int64).pin_memory()
+
+    def e2e_step(i):
+        length, pi = model(xs_pin[i % n_in], src_h, tgt_h, val_type="noAug_nTraj", return_pi=True,
+                           group_size=G)          # forward() does the H2D of this step's inputs
+        if world > 1:
+            pi, length = gather_tours(pi, length, total)
+            pi, length = pi[rank * B:(rank + 1) * B], length[rank * B:(rank + 1) * B]
+        out_len.copy_(length, non_blocking=True)
+        out_pi.copy_(pi, non_blocking=True)
+        torch.cuda.synchronize()                  # the caller consumes the tours on the host
+
+    e2e_steps = max(1, min(args.steps, 3))
+    e2e_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i + 1)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = total * e2e_steps / float(e2e_s)
+    h2d = B * N * 2 * 4 + 2 * B * 8
+    d2h = B * N * 8 + B * 4
+
+    if rank == 0:
+        tc_peak, hbm_peak, peak_src = load_peaks()
+        enc_f, reset_f, dec_f = algorithmic_flops(N, G, L)
+        kms = float(kern_ms)
+        achieved = dec_f * B / (kms / 1e3) / 1e12
+        cpu_val, cores, cpu_dt = cpu_oracle_throughput(N, G, L, args.cpu_sample)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "f32", "x3": "f16x3 (split-fp32 on fp16 tensor cores, f32 accumulate)",
+                      "fast": "f16x3/f16"}[args.mode],
+            "data": "synthetic uniform coords, random-init weights (seed 1234)",
+            "config": workload_config(args),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "api": "B200PathSolver.forward(host pinned batch) -> host tours"},
+            "gpu_launches": int(nl),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "rollout (decode) kernel",
+                         "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
+                         "frac": achieved / tc_peak, "traffic": None,
+                         "peak_source": f"bf16_tflops_sustained, {peak_src}",
+                         "kernel_ms": kms, "kernel_share_of_step": kms / (total_ms / args.steps),
+                         "algorithmic_flops_per_launch": dec_f * B},
+            "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{args.cpu_sample} subproblems (N={N}, G={G}, noAug_nTraj, "
+                                       f"L={L}) in {cpu_dt:.1f} s, oracle port, torch CPU fp32",
+                             "host_cpus": os.cpu_count()},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default=os.environ.get("HTSP_MODE", "fp32"), choices=["fp32", "x3", "fast"])
+    ap.add_argument("--batch", type=int, default=4096, help="subproblems per GPU per step")
+    ap.add_argument("--nodes", type=int, default=200)
+    ap.add_argument("--group", type=int, default=200)
+    ap.add_argument("--layers", type=int, default=6)
+    ap.add_argument("--cpu-sample", type=int, default=64, help="subproblems in the cpu_baseline sample")
+    ap.add_argument("--ref-sample", type=int, default=16, help="subproblems per step of --impl reference")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -18,6 +18,7 @@ SIGNATURES = {
     "htsp_abi_version": (_i, []),
     "htsp_last_error": (C.c_char_p, []),
     "htsp_launch_count": (C.c_uint64, []),
+    "htsp_set_kernel_timer": (_i, [_vp, _vp]),
     "htsp_weights_blob_bytes": (_sz, [_i]),
     "htsp_n_weight_tensors": (_i, [_i]),
     "htsp_pack_weights": (_i, [C.POINTER(_vp), _i, _i, _vp, _vp]),

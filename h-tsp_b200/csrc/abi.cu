@@ -18,6 +18,14 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static thread_local cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
+void kernel_timer_begin(cudaStream_t s) {
+  if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_start, s);
+}
+void kernel_timer_end(cudaStream_t s) {
+  if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_stop, s);
+  g_ev_start = g_ev_stop = nullptr;
+}
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 }  // namespace htsp
@@ -27,6 +35,12 @@ using namespace htsp;
 extern "C" int htsp_abi_version(void) { return HTSP_ABI_VERSION; }
 extern "C" const char* htsp_last_error(void) { return g_err; }
 extern "C" uint64_t htsp_launch_count(void) { return g_launches.load(); }
+
+extern "C" int htsp_set_kernel_timer(void* start_event, void* stop_event) {
+  g_ev_start = (cudaEvent_t)start_event;
+  g_ev_stop = (cudaEvent_t)stop_event;
+  return HTSP_OK;
+}
 
 extern "C" size_t htsp_weights_blob_bytes(int n_layers) {
   if (n_layers < 0) return 0;

@@ -59,6 +59,8 @@ __host__ __device__ inline DecOff dec_off(int n_layers) {
 // ---- error plumbing -------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+void kernel_timer_begin(cudaStream_t s);  // records the armed start event, if any
+void kernel_timer_end(cudaStream_t s);    // records the armed stop event and disarms
 
 #define HTSP_CHECK_CUDA(expr)                                                        \
   do {                                                                               \

@@ -234,9 +234,11 @@ static int launch_rb(const float* blob, int n_layers, const float* x, const floa
   HTSP_CHECK_CUDA(cudaFuncSetAttribute(decode_f32_kernel<RB>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((G + RB - 1) / RB, Bp);
+  kernel_timer_begin(s);
   decode_f32_kernel<RB><<<grid, DF_THREADS, smem, s>>>(
       x, emb, proj, qfix, blob + d.wproj + (size_t)4 * H * H, blob + d.bc, src, tgt, first, N, G,
       forced_pi, pi, reward, logits_out);
+  kernel_timer_end(s);
   HTSP_CHECK_LAUNCH();
   return HTSP_OK;
 }

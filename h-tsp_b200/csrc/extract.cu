@@ -67,8 +67,9 @@ extract_normalize_kernel(const float2* __restrict__ data, const long long* __res
     mnx = fminf(mnx, red[0][w]); mny = fminf(mny, red[1][w]);
     mxx = fmaxf(mxx, red[2][w]); mxy = fmaxf(mxy, red[3][w]);
   }
-  // s = 0.9 / max(dx, dy); x' = s*(x - min) + 0.05 with separate roundings (h_tsp.py:188-191)
-  const float s = __fdiv_rn(0.9f, fmaxf(__fsub_rn(mxx, mnx), __fsub_rn(mxy, mny)));
+  // s = 0.9 / max(dx, dy): torch evaluates `scalar / tensor` as reciprocal(tensor) * scalar (two
+  // roundings); x' = s*(x - min) + 0.05 as separate ops, no FMA contraction (h_tsp.py:188-191)
+  const float s = __fmul_rn(__frcp_rn(fmaxf(__fsub_rn(mxx, mnx), __fsub_rn(mxy, mny))), 0.9f);
   if (tid == 0) scale[b] = s;
 #pragma unroll
   for (int i = 0; i < kExtractPerThread; ++i) {

@@ -50,6 +50,12 @@ const char* htsp_last_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 uint64_t htsp_launch_count(void);
 
+/* Measurement hook: when both are non-NULL cudaEvent_t handles, the NEXT launch of the dominant
+ * kernel (the rollout kernel inside htsp_decode) is bracketed by cudaEventRecord(start) /
+ * cudaEventRecord(stop) on its stream; the pair is consumed by that launch.  bench.py uses
+ * this for the live roofline number.                                                       */
+int htsp_set_kernel_timer(void* start_event, void* stop_event);
+
 /* ---- weights ------------------------------------------------------------------------
  * Replaces PathSolver.load_state_dict + the per-call nn.Linear / BatchNorm1d parameter reads
  * (rl4cop/models/models.py:12-60, 331-358).  `host_tensors` is a HOST array of HOST fp32
