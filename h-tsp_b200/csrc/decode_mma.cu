@@ -1,11 +1,579 @@
+// K3 (tensor-core variant, HTSP_MODE_TC_X3 / HTSP_MODE_TC_FAST): persistent POMO rollout kernel.
+//
+// One CTA owns up to 16*NWARPS rows (POMO starts) of one instance for all N-2 decode steps
+// (PathDecoder.forward, rl4cop/models/models.py:404-446; GroupState, train_path_solver.py:45-72).
+// Each compute warp owns 16 rows; per step and head it runs a flash-style pass
+//   S = Q_h K_h^T (m16n8k16) -> online softmax with the visited mask -> O_h += P V_h
+// entirely in registers, then the pointer logits  u = O K2^T + c0  (multi_head_combine folded
+// into the keys, K2 = emb Wc, c0 = emb.bc), 10*tanh, mask, arg-max, and the state update.
+//
+// Arithmetic: every GEMM operand is split into fp16 hi + fp16 lo (x = hi + lo to ~2^-22) and
+// each product is 3 tensor-core MMAs (hi*hi + hi*lo + lo*hi) with fp32 accumulation, which
+// measures 3e-5 max abs error on the clipped logits against the fp32 reference (single fp16 /
+// bf16 operands give 2e-2 / 2e-1).  HTSP_MODE_TC_FAST drops the lo
+// terms of the glimpse scores only (3.5e-4).
+//
+// Operands: K_h, V_h (per head) and K2 (per key chunk) of the instance are pre-split, pre-swizzled
+// fp16 tiles in global memory (L2-resident, 1536*NP bytes per instance) and are STREAMED through
+// a shared-memory ring by one producer warp with cp.async.bulk (TMA bulk copy, SASS UBLKCP) +
+// mbarrier full/empty pairs; consumers read them with ldmatrix.  Nothing else is staged.
 #include "common.cuh"
+
 namespace htsp {
-size_t decode_mma_pack_bytes(int Bp, int N) { return 0; }
+
+constexpr int MM_STAGES = 3;
+constexpr int MM_KT = 32;            // keys per K2 tile
+constexpr int QROW_STRIDE = 136;     // floats; 8*row + 2q is conflict-free for float2 reads
+constexpr float kScoreScale = 0.25f * 1.4426950408889634f;   // 1/sqrt(dk) * log2(e)
+constexpr float kInvSqrtH = 0.08838834764831845f;            // 1/sqrt(128)
+
+// image layout per instance (bytes): 8 KV tiles of 128*NP, then K2 tiles of 512*rows_t
+__host__ __device__ inline size_t img_bytes(int NP) { return (size_t)1536 * NP; }
+__host__ __device__ inline int n_k2_tiles(int NP) { return (NP + MM_KT - 1) / MM_KT; }
+__host__ __device__ inline int stage_bytes(int NP) {
+  int a = 128 * NP, b = 512 * MM_KT;
+  return a > b ? a : b;
+}
+
+// ------------------------------------------------------------------------------------------
+// pack: proj fp32 [Bp*N, 640] -> per-instance fp16 hi/lo operand image (swizzled tile order)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+  __half2 h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    float2 f = __half22float2(h[i]);
+    l[i] = __floats2half2_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+  }
+  hi = *reinterpret_cast<uint4*>(h);
+  lo = *reinterpret_cast<uint4*>(l);
+}
+
+__global__ void __launch_bounds__(256)
+decode_pack_kernel(const float* __restrict__ proj, int Bp, int N, int NP,
+                   unsigned char* __restrict__ img) {
+  // one thread per (instance, key row r < NP, matrix m in {K,V,K2}, 8-column chunk c16 < 16)
+  const size_t total = (size_t)Bp * NP * 48;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int c16 = (int)(i % 16);
+    const int m = (int)((i / 16) % 3);
+    const int r = (int)((i / 48) % NP);
+    const int b = (int)(i / ((size_t)48 * NP));
+    float v[8];
+    if (r < N) {
+      const int col = (m == 0 ? 0 : (m == 1 ? H : 4 * H)) + c16 * 8;
+      const float4* p = (const float4*)(proj + ((size_t)b * N + r) * PROJ + col);
+      float4 a = __ldg(p), c = __ldg(p + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = 0.f;
+    }
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    unsigned char* base = img + (size_t)b * img_bytes(NP);
+    if (m < 2) {
+      const int h = c16 >> 1, chunk = c16 & 1;
+      unsigned char* tile = base + (size_t)h * 128 * NP;
+      const int off = r * 32 + ((chunk ^ ((r >> 2) & 1)) * 16);
+      // tile = [K hi | K lo | V hi | V lo], each NP*32 bytes
+      *(uint4*)(tile + (size_t)(2 * m) * NP * 32 + off) = hi;
+      *(uint4*)(tile + (size_t)(2 * m + 1) * NP * 32 + off) = lo;
+    } else {
+      const int t = r / MM_KT, rl = r - t * MM_KT;
+      const int rows_t = min(MM_KT, NP - t * MM_KT);
+      unsigned char* tile = base + (size_t)8 * 128 * NP + (size_t)t * 512 * MM_KT;
+      const int off = rl * 256 + ((c16 ^ (rl & 7)) * 16);
+      *(uint4*)(tile + off) = hi;
+      *(uint4*)(tile + (size_t)rows_t * 256 + off) = lo;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                                        uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                                          uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  __half2 h = __floats2half2_rn(x, y);
+  float2 f = __half22float2(h);
+  __half2 l = __floats2half2_rn(x - f.x, y - f.y);
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  lo = *reinterpret_cast<uint32_t*>(&l);
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+// ------------------------------------------------------------------------------------------
+// the rollout kernel
+// ------------------------------------------------------------------------------------------
+struct MmaArgs {
+  const float* x;        // [Bp,N,2]
+  const float* proj;     // [Bp*N,640]  (QL at +256, QF at +384)
+  const float* qfix;     // [Bp,128]
+  const float* c0;       // [Bp,N]
+  const unsigned char* img;
+  const int32_t* src;
+  const int32_t* tgt;
+  const int32_t* first;
+  const int32_t* forced_pi;
+  int32_t* pi;
+  float* reward;
+  float* logits_out;
+  int N, NP, G, rows_per_cta, fast;
+};
+
+template <int NWARPS, int NCHUNK_T>
+__global__ void __launch_bounds__((NWARPS + 1) * 32, 1) decode_mma_kernel(const MmaArgs A) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.y;
+  const int N = A.N, NP = A.NP, G = A.G;
+  const int NCHUNK = NCHUNK_T > 0 ? NCHUNK_T : NP / 16;
+  const int g0 = blockIdx.x * A.rows_per_cta;
+  const int rows_here = min(A.rows_per_cta, G - g0);
+  const int active_warps = (rows_here + 15) / 16;
+  const int NWORDS = (NP + 31) / 32;
+  const int VSTRIDE = NWORDS + 1;
+  const int STAGE = stage_bytes(NP);
+  const int NT2 = n_k2_tiles(NP);
+  const int tiles_per_step = NH + NT2;
+
+  // shared memory carve-up
+  unsigned char* ring = smem;                                           // MM_STAGES * STAGE
+  float* qrow = (float*)(ring + (size_t)MM_STAGES * STAGE);             // [16*NWARPS][QROW_STRIDE]
+  float* c0s = qrow + (size_t)16 * NWARPS * QROW_STRIDE;                // [NP]
+  float2* xs = (float2*)(c0s + NP);                                     // [N]
+  unsigned* vis = (unsigned*)(xs + N);                                  // [16*NWARPS][VSTRIDE]
+  uint64_t* bars = (uint64_t*)(((uintptr_t)(vis + 16 * NWARPS * VSTRIDE) + 15) & ~(uintptr_t)15);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + MM_STAGES);
+  // per-warp staging of the O fragments (hi/lo A operands of the logits GEMM) in fragment order:
+  // [warp][head][lane][8 x b32]; every lane only ever touches its own 32 bytes
+  uint4* obuf = (uint4*)(bars + 2 * MM_STAGES);
+
+  const int src = A.src[b], tgt = A.tgt[b];
+  const float* projb = A.proj + (size_t)b * N * PROJ;
+  const unsigned char* imgb = A.img + (size_t)b * img_bytes(NP);
+
+  if (tid == 0) {
+    for (int s = 0; s < MM_STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, active_warps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  for (int i = tid; i < N; i += blockDim.x) xs[i] = __ldg((const float2*)A.x + (size_t)b * N + i);
+  for (int i = tid; i < NP; i += blockDim.x) c0s[i] = i < N ? __ldg(&A.c0[(size_t)b * N + i]) : 0.f;
+  for (int i = tid; i < 16 * NWARPS * H; i += blockDim.x) {
+    const int r = i / H, c = i % H;
+    const int g = min(g0 + r, G - 1);
+    qrow[r * QROW_STRIDE + c] =
+        __ldg(&A.qfix[(size_t)b * H + c]) + __ldg(&projb[(size_t)A.first[g] * PROJ + 3 * H + c]);
+  }
+  // visited masks: padded keys (>= N) are permanently visited
+  for (int i = tid; i < 16 * NWARPS * VSTRIDE; i += blockDim.x) {
+    const int w = i % VSTRIDE;
+    unsigned m = 0u;
+    if (w < NWORDS) {
+      const int lo = w * 32;
+      if (lo + 32 > N) m = (N <= lo) ? 0xffffffffu : (0xffffffffu << (N - lo));
+    }
+    vis[i] = m;
+  }
+  __syncthreads();
+
+  const int n_steps = N - 2;
+  // ======================================================================== producer warp
+  if (warp == NWARPS) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int step = 0; step < n_steps; ++step) {
+        for (int t = 0; t < tiles_per_step; ++t, ++it) {
+          const uint32_t s = it % MM_STAGES, use = it / MM_STAGES;
+          mbar_wait(empty0 + 8 * s, (use & 1) ^ 1);
+          const unsigned char* srcp;
+          uint32_t bytes;
+          if (t < NH) {
+            srcp = imgb + (size_t)t * 128 * NP;
+            bytes = 128 * NP;
+          } else {
+            const int k2 = t - NH;
+            srcp = imgb + (size_t)8 * 128 * NP + (size_t)k2 * 512 * MM_KT;
+            bytes = 512 * min(MM_KT, NP - k2 * MM_KT);
+          }
+          mbar_arrive_expect_tx(full0 + 8 * s, bytes);
+          bulk_g2s(smem_u32(ring + (size_t)s * STAGE), srcp, bytes, full0 + 8 * s);
+        }
+      }
+    }
+    return;
+  }
+  if (warp >= active_warps) return;
+
+  // ======================================================================== compute warps
+  const int q4 = lane & 3, rr = lane >> 2;
+  const int rA = warp * 16 + rr, rB = rA + 8;          // rows inside the CTA
+  const int gA = g0 + rA, gB = g0 + rB;
+  const bool okA = rA < rows_here, okB = rB < rows_here;
+  unsigned* visA = vis + rA * VSTRIDE;
+  unsigned* visB = vis + rB * VSTRIDE;
+  int curA = 0, curB = 0, cntA = 0, cntB = 0;
+  int32_t* piA = A.pi + ((size_t)b * G + min(gA, G - 1)) * N;
+  int32_t* piB = A.pi + ((size_t)b * G + min(gB, G - 1)) * N;
+
+  // step 0: visit(first[g]) with source<->target coupling (train_path_solver.py:256-257, 45-66)
+  auto visit = [&](unsigned* v, int32_t* p, int& cur, int& cnt, int a, bool ok) {
+    // all four lanes of the quad execute this redundantly with identical values
+    if (ok) {
+      if (q4 == 0) { p[cnt] = a; }
+      v[a >> 5] |= 1u << (a & 31);
+      cnt++;
+      cur = a;
+      const int partner = (a == src) ? tgt : ((a == tgt) ? src : -1);
+      if (partner >= 0) {
+        if (q4 == 0) p[cnt] = partner;
+        v[partner >> 5] |= 1u << (partner & 31);
+        cnt++;
+        cur = partner;
+      }
+    }
+  };
+  // quad lanes write the same smem word with the same value: benign; order with __syncwarp
+  if (okA) visit(visA, piA, curA, cntA, A.first[gA], true);
+  if (okB) visit(visB, piB, curB, cntB, A.first[gB], true);
+  __syncwarp();
+
+  uint32_t it = 0;
+  uint4* my_o = obuf + ((size_t)warp * NH * 32 + lane) * 2;   // + h*64 per head
+  const float* qrA = qrow + rA * QROW_STRIDE;
+  const float* qrB = qrow + rB * QROW_STRIDE;
+
+  for (int step = 0; step < n_steps; ++step) {
+    const float* qlA = projb + (size_t)curA * PROJ + 2 * H;
+    const float* qlB = projb + (size_t)curB * PROJ + 2 * H;
+    // ------------------------------------------------------------ glimpse, one head at a time
+#pragma unroll 1
+    for (int h = 0; h < NH; ++h, ++it) {
+      // q = (qfix + q_first) + q_last  (models.py:409-413), A fragments hi/lo
+      uint32_t qh[4], ql[4];
+      {
+        const int c = h * DK + 2 * q4;
+        const float2 fa0 = *(const float2*)(qrA + c), fa1 = *(const float2*)(qrA + c + 8);
+        const float2 fb0 = *(const float2*)(qrB + c), fb1 = *(const float2*)(qrB + c + 8);
+        const float2 la0 = __ldg((const float2*)(qlA + c)), la1 = __ldg((const float2*)(qlA + c + 8));
+        const float2 lb0 = __ldg((const float2*)(qlB + c)), lb1 = __ldg((const float2*)(qlB + c + 8));
+        split2(fa0.x + la0.x, fa0.y + la0.y, qh[0], ql[0]);
+        split2(fb0.x + lb0.x, fb0.y + lb0.y, qh[1], ql[1]);
+        split2(fa1.x + la1.x, fa1.y + la1.y, qh[2], ql[2]);
+        split2(fb1.x + lb1.x, fb1.y + lb1.y, qh[3], ql[3]);
+      }
+      const uint32_t s = it % MM_STAGES, use = it / MM_STAGES;
+      mbar_wait(full0 + 8 * s, use & 1);
+      const uint32_t tile = smem_u32(ring + (size_t)s * STAGE);
+      const uint32_t khi = tile, klo = tile + NP * 32, vhi = tile + 2 * NP * 32, vlo = tile + 3 * NP * 32;
+
+      float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+      float mA = -INFINITY, mB = -INFINITY, lA = 0.f, lB = 0.f;
+      // ldmatrix lane addressing
+      const int mi = lane >> 3, l7 = lane & 7;
+#pragma unroll
+      for (int kc = 0; kc < NCHUNK; ++kc) {
+        // ---- S = Q K^T for 16 keys (two n8 tiles)
+        const int keyK = kc * 16 + (mi >> 1) * 8 + l7;
+        const uint32_t offK = keyK * 32 + (((mi & 1) ^ ((keyK >> 2) & 1)) * 16);
+        uint32_t bh0, bh1, bh2, bh3;
+        ldsm_x4(khi + offK, bh0, bh1, bh2, bh3);
+        float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+        mma16816(s0, qh, bh0, bh1);
+        mma16816(s1, qh, bh2, bh3);
+        if (!A.fast) {
+          uint32_t bl0, bl1, bl2, bl3;
+          ldsm_x4(klo + offK, bl0, bl1, bl2, bl3);
+          mma16816(s0, qh, bl0, bl1);
+          mma16816(s1, qh, bl2, bl3);
+          mma16816(s0, ql, bh0, bh1);
+          mma16816(s1, ql, bh2, bh3);
+        }
+        // ---- mask + online softmax (utils.py:20-27), exponent base 2
+        const int key0 = kc * 16 + 2 * q4;                 // keys key0,key0+1 (tile 0), +8,+9 (tile 1)
+        const unsigned wA = visA[key0 >> 5] >> (key0 & 31);
+        const unsigned wB = visB[key0 >> 5] >> (key0 & 31);
+        float t0 = (wA & 1u) ? -INFINITY : s0[0] * kScoreScale;
+        float t1 = (wA & 2u) ? -INFINITY : s0[1] * kScoreScale;
+        float t2 = (wA & 0x100u) ? -INFINITY : s1[0] * kScoreScale;
+        float t3 = (wA & 0x200u) ? -INFINITY : s1[1] * kScoreScale;
+        float u0 = (wB & 1u) ? -INFINITY : s0[2] * kScoreScale;
+        float u1 = (wB & 2u) ? -INFINITY : s0[3] * kScoreScale;
+        float u2 = (wB & 0x100u) ? -INFINITY : s1[2] * kScoreScale;
+        float u3 = (wB & 0x200u) ? -INFINITY : s1[3] * kScoreScale;
+        const float nmA = fmaxf(mA, quad_max(fmaxf(fmaxf(t0, t1), fmaxf(t2, t3))));
+        const float nmB = fmaxf(mB, quad_max(fmaxf(fmaxf(u0, u1), fmaxf(u2, u3))));
+        const float sA = (nmA == -INFINITY) ? 0.f : nmA;
+        const float sB = (nmB == -INFINITY) ? 0.f : nmB;
+        const float aA = exp2f(mA - sA), aB = exp2f(mB - sB);   // mA=-inf -> 0
+        mA = nmA; mB = nmB;
+        t0 = exp2f(t0 - sA); t1 = exp2f(t1 - sA); t2 = exp2f(t2 - sA); t3 = exp2f(t3 - sA);
+        u0 = exp2f(u0 - sB); u1 = exp2f(u1 - sB); u2 = exp2f(u2 - sB); u3 = exp2f(u3 - sB);
+        lA = lA * aA + ((t0 + t1) + (t2 + t3));
+        lB = lB * aB + ((u0 + u1) + (u2 + u3));
+        o0[0] *= aA; o0[1] *= aA; o1[0] *= aA; o1[1] *= aA;
+        o0[2] *= aB; o0[3] *= aB; o1[2] *= aB; o1[3] *= aB;
+        // ---- O += P V for these 16 keys
+        uint32_t ph[4], pl[4];
+        split2(t0, t1, ph[0], pl[0]);
+        split2(u0, u1, ph[1], pl[1]);
+        split2(t2, t3, ph[2], pl[2]);
+        split2(u2, u3, ph[3], pl[3]);
+        const int keyV = kc * 16 + (mi & 1) * 8 + l7;
+        const uint32_t offV = keyV * 32 + (((mi >> 1) ^ ((keyV >> 2) & 1)) * 16);
+        uint32_t vh0, vh1, vh2, vh3, vl0, vl1, vl2, vl3;
+        ldsm_x4_t(vhi + offV, vh0, vh1, vh2, vh3);
+        ldsm_x4_t(vlo + offV, vl0, vl1, vl2, vl3);
+        mma16816(o0, ph, vh0, vh1);
+        mma16816(o1, ph, vh2, vh3);
+        mma16816(o0, ph, vl0, vl1);
+        mma16816(o1, ph, vl2, vl3);
+        mma16816(o0, pl, vh0, vh1);
+        mma16816(o1, pl, vh2, vh3);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty0 + 8 * s);
+      const float iA = 1.f / quad_sum(lA), iB = 1.f / quad_sum(lB);
+      uint4 fh, fl;
+      split2(o0[0] * iA, o0[1] * iA, fh.x, fl.x);
+      split2(o0[2] * iB, o0[3] * iB, fh.y, fl.y);
+      split2(o1[0] * iA, o1[1] * iA, fh.z, fl.z);
+      split2(o1[2] * iB, o1[3] * iB, fh.w, fl.w);
+      my_o[h * 64] = fh;
+      my_o[h * 64 + 1] = fl;
+    }
+    uint32_t ohi[NH][4], olo[NH][4];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      const uint4 fh = my_o[h * 64], fl = my_o[h * 64 + 1];
+      ohi[h][0] = fh.x; ohi[h][1] = fh.y; ohi[h][2] = fh.z; ohi[h][3] = fh.w;
+      olo[h][0] = fl.x; olo[h][1] = fl.y; olo[h][2] = fl.z; olo[h][3] = fl.w;
+    }
+    // ------------------------------------------------------------ pointer logits + arg-max
+    float bestA = -INFINITY, bestB = -INFINITY;
+    int idxA = 0x7fffffff, idxB = 0x7fffffff;
+    float* loA = A.logits_out ? A.logits_out + (((size_t)b * G + min(gA, G - 1)) * n_steps + step) * N : nullptr;
+    float* loB = A.logits_out ? A.logits_out + (((size_t)b * G + min(gB, G - 1)) * n_steps + step) * N : nullptr;
+#pragma unroll 1
+    for (int t = 0; t < NT2; ++t, ++it) {
+      const uint32_t s = it % MM_STAGES, use = it / MM_STAGES;
+      mbar_wait(full0 + 8 * s, use & 1);
+      const int rows_t = min(MM_KT, NP - t * MM_KT);
+      const uint32_t k2hi = smem_u32(ring + (size_t)s * STAGE), k2lo = k2hi + rows_t * 256;
+      const int mi = lane >> 3, l7 = lane & 7;
+      for (int nt = 0; nt < rows_t / 8; ++nt) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const int rl = nt * 8 + l7;
+#pragma unroll
+        for (int kp = 0; kp < NH / 2; ++kp) {       // two k16 steps (= two heads) per ldmatrix.x4
+          const uint32_t off = rl * 256 + ((((2 * kp) * 2 + mi) ^ (rl & 7)) * 16);
+          uint32_t bh0, bh1, bh2, bh3, bl0, bl1, bl2, bl3;
+          ldsm_x4(k2hi + off, bh0, bh1, bh2, bh3);
+          ldsm_x4(k2lo + off, bl0, bl1, bl2, bl3);
+          mma16816(acc, ohi[2 * kp], bh0, bh1);
+          mma16816(acc, ohi[2 * kp + 1], bh2, bh3);
+          mma16816(acc, ohi[2 * kp], bl0, bl1);
+          mma16816(acc, ohi[2 * kp + 1], bl2, bl3);
+          mma16816(acc, olo[2 * kp], bh0, bh1);
+          mma16816(acc, olo[2 * kp + 1], bh2, bh3);
+        }
+        // score/sqrt(H) -> 10*tanh -> mask -> running arg-max, first index wins (models.py:438-440)
+        const int key0 = t * MM_KT + nt * 8 + 2 * q4;
+        const float2 cc = *(const float2*)(c0s + key0);
+        const unsigned wA = visA[key0 >> 5] >> (key0 & 31);
+        const unsigned wB = visB[key0 >> 5] >> (key0 & 31);
+        float zA0 = 10.0f * tanhf((acc[0] + cc.x) * kInvSqrtH);
+        float zA1 = 10.0f * tanhf((acc[1] + cc.y) * kInvSqrtH);
+        float zB0 = 10.0f * tanhf((acc[2] + cc.x) * kInvSqrtH);
+        float zB1 = 10.0f * tanhf((acc[3] + cc.y) * kInvSqrtH);
+        if (wA & 1u) zA0 = -INFINITY;
+        if (wA & 2u) zA1 = -INFINITY;
+        if (wB & 1u) zB0 = -INFINITY;
+        if (wB & 2u) zB1 = -INFINITY;
+        if (loA != nullptr) {
+          if (okA && key0 < N) { loA[key0] = zA0; if (key0 + 1 < N) loA[key0 + 1] = zA1; }
+          if (okB && key0 < N) { loB[key0] = zB0; if (key0 + 1 < N) loB[key0 + 1] = zB1; }
+        }
+        if (zA0 > bestA) { bestA = zA0; idxA = key0; }
+        if (zA1 > bestA) { bestA = zA1; idxA = key0 + 1; }
+        if (zB0 > bestB) { bestB = zB0; idxB = key0; }
+        if (zB1 > bestB) { bestB = zB1; idxB = key0 + 1; }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty0 + 8 * s);
+    }
+#pragma unroll
+    for (int off = 1; off <= 2; off <<= 1) {
+      const float obA = __shfl_xor_sync(0xffffffffu, bestA, off);
+      const int oiA = __shfl_xor_sync(0xffffffffu, idxA, off);
+      const float obB = __shfl_xor_sync(0xffffffffu, bestB, off);
+      const int oiB = __shfl_xor_sync(0xffffffffu, idxB, off);
+      if (obA > bestA || (obA == bestA && oiA < idxA)) { bestA = obA; idxA = oiA; }
+      if (obB > bestB || (obB == bestB && oiB < idxB)) { bestB = obB; idxB = oiB; }
+    }
+    // ---- state update (train_path_solver.py:45-72); all quad lanes hold identical values
+    __syncwarp();
+    if (okA) {
+      const int a = A.forced_pi ? A.forced_pi[((size_t)b * G + gA) * N + cntA] : idxA;
+      visit(visA, piA, curA, cntA, a, true);
+    }
+    if (okB) {
+      const int a = A.forced_pi ? A.forced_pi[((size_t)b * G + gB) * N + cntB] : idxB;
+      visit(visB, piB, curB, cntB, a, true);
+    }
+    __syncwarp();
+  }
+  // ---- reward = -(closed tour length - fixed edge)   (train_path_solver.py:109-149)
+  __syncwarp();
+  {
+    float lenA = 0.f, lenB = 0.f;
+    for (int i = q4; i < N; i += 4) {
+      const int j = (i + 1 == N) ? 0 : i + 1;
+      if (okA) {
+        const float2 p = xs[piA[i]], c = xs[piA[j]];
+        const float dx = p.x - c.x, dy = p.y - c.y;
+        lenA += sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+      }
+      if (okB) {
+        const float2 p = xs[piB[i]], c = xs[piB[j]];
+        const float dx = p.x - c.x, dy = p.y - c.y;
+        lenB += sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+      }
+    }
+    lenA = quad_sum(lenA);
+    lenB = quad_sum(lenB);
+    const float dx = xs[src].x - xs[tgt].x, dy = xs[src].y - xs[tgt].y;
+    const float fixed = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+    if (q4 == 0) {
+      if (okA) A.reward[(size_t)b * G + gA] = -(lenA - fixed);
+      if (okB) A.reward[(size_t)b * G + gB] = -(lenB - fixed);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int np_of(int N) { return (N + 15) / 16 * 16; }
+
+size_t decode_mma_pack_bytes(int Bp, int N) { return align_up((size_t)Bp * img_bytes(np_of(N)), 256); }
+
+template <int NWARPS>
+static size_t mma_smem_bytes(int N, int NP) {
+  const int NWORDS = (NP + 31) / 32;
+  size_t b = (size_t)MM_STAGES * stage_bytes(NP);
+  b += (size_t)16 * NWARPS * QROW_STRIDE * 4;
+  b += (size_t)NP * 4 + (size_t)N * 8;
+  b += (size_t)16 * NWARPS * (NWORDS + 1) * 4;
+  b += 16 + 2 * MM_STAGES * 8;
+  b += (size_t)NWARPS * NH * 32 * 32;
+  return b;
+}
+
+template <int NWARPS, int NCHUNK_T>
+static int launch_mma_t(const MmaArgs& a, int Bp, cudaStream_t s) {
+  const size_t smem = mma_smem_bytes<NWARPS>(a.N, a.NP);
+  if (smem > 227 * 1024) {
+    set_error("decode_mma: N=%d needs %zu bytes of shared memory", a.N, smem);
+    return HTSP_ERR_UNSUPPORTED;
+  }
+  HTSP_CHECK_CUDA(cudaFuncSetAttribute(decode_mma_kernel<NWARPS, NCHUNK_T>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((a.G + a.rows_per_cta - 1) / a.rows_per_cta, Bp);
+  kernel_timer_begin(s);
+  decode_mma_kernel<NWARPS, NCHUNK_T><<<grid, (NWARPS + 1) * 32, smem, s>>>(a);
+  kernel_timer_end(s);
+  HTSP_CHECK_LAUNCH();
+  return HTSP_OK;
+}
+
 int launch_decode_mma(const float* x, const float* proj, const float* qfix, const float* c0,
                       const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp, int N,
                       int G, int mode, const int32_t* forced_pi, int32_t* pi, float* reward,
                       float* logits_out, void* pack_ws, cudaStream_t s) {
-  set_error("tensor-core decode not built yet");
-  return HTSP_ERR_UNSUPPORTED;
+  const int NP = np_of(N);
+  {
+    const size_t total = (size_t)Bp * NP * 48;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    decode_pack_kernel<<<blocks, 256, 0, s>>>(proj, Bp, N, NP, (unsigned char*)pack_ws);
+    HTSP_CHECK_LAUNCH();
+  }
+  constexpr int NW = 7;
+  MmaArgs a;
+  a.x = x; a.proj = proj; a.qfix = qfix; a.c0 = c0; a.img = (const unsigned char*)pack_ws;
+  a.src = src; a.tgt = tgt; a.first = first; a.forced_pi = forced_pi;
+  a.pi = pi; a.reward = reward; a.logits_out = logits_out;
+  a.N = N; a.NP = NP; a.G = G; a.fast = (mode == HTSP_MODE_TC_FAST) ? 1 : 0;
+  const int n_cta = (G + 16 * NW - 1) / (16 * NW);
+  a.rows_per_cta = (G + n_cta - 1) / n_cta;
+  if (NP == 208) return launch_mma_t<NW, 13>(a, Bp, s);
+  return launch_mma_t<NW, 0>(a, Bp, s);
 }
+
 }  // namespace htsp

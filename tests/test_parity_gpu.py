@@ -10,7 +10,7 @@ from oracle import path_solver_oracle as po
 
 pytestmark = pytest.mark.gpu
 
-MODES = ["fp32"]
+MODES = ["fp32", "x3", "fast"]
 
 
 def T(a):
@@ -188,9 +188,25 @@ def test_forward_matches_golden(solvers, golden, sd6, mode, tag, vt):
     pi, length = pi.cpu().numpy(), length.cpu().numpy()
     if np.array_equal(pi, want_pi):
         np.testing.assert_allclose(length, want_len, rtol=1e-5)
-    else:   # a near-tie flipped a decision somewhere: the selected length must still be as good
-        np.testing.assert_allclose(length, want_len, rtol=2e-3)
-        print(f"[{mode}/{vt}] tours differ from golden in {(pi != want_pi).any(-1).sum()} rows")
+        return
+    # A near-tie flipped a decision somewhere, so another (equally greedy) tour was selected.
+    # Prove it: every decision of every rollout is an oracle arg-max within the mode's tolerance,
+    # and the returned result is exactly the reference's selection rule applied to those rollouts.
+    print(f"[{mode}/{vt}] tours differ from golden in {(pi != want_pi).any(-1).sum()} rows")
+    first = T(golden[f"fwd_{tag}_first"]).long()
+    xa = po.augment_8fold(x) if "x8Aug" in vt else x
+    sa = torch.zeros(xa.shape[0], dtype=torch.long)
+    ta = torch.full((xa.shape[0],), N - 1)
+    xc = xa.cuda()
+    r_pi, r_rew, _ = s.rollout(xc, s.encode(xc), sa, ta, first)
+    with torch.no_grad():
+        tie_aware_check(sd6, xa, sa, ta, first, r_pi.cpu().long(), 2 * LOGIT_TOL[mode])
+    sel_r, sel_pi = po.select_best(r_rew.cpu(), r_pi.cpu().long(), vt)
+    np.testing.assert_allclose(length, -sel_r.numpy(), rtol=1e-6)
+    assert np.array_equal(pi, sel_pi.squeeze().numpy())
+    same = (pi == want_pi).reshape(-1, N).all(-1) if pi.ndim > 1 else np.array([False])
+    if vt == "noAug_1Traj" and same.any():   # untouched rows still agree to 1e-5
+        np.testing.assert_allclose(length.reshape(-1)[same], want_len.reshape(-1)[same], rtol=1e-5)
 
 
 def test_forward_seeded_randperm_alignment(solvers, sd6):
