@@ -329,7 +329,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("HTSP_MODE", "fp32"), choices=["fp32", "x3", "fast"])
+    ap.add_argument("--mode", default=os.environ.get("HTSP_MODE", "x3"), choices=["fp32", "x3", "fast"])
     ap.add_argument("--batch", type=int, default=4096, help="subproblems per GPU per step")
     ap.add_argument("--nodes", type=int, default=200)
     ap.add_argument("--group", type=int, default=200)

@@ -21,10 +21,19 @@
 
 namespace htsp {
 
-constexpr int MM_STAGES = 3;
-constexpr int MM_KT = 32;            // keys per K2 tile
-constexpr int QROW_STRIDE = 136;     // floats; 8*row + 2q is conflict-free for float2 reads
+#ifndef HTSP_MMA_NWARPS
+#define HTSP_MMA_NWARPS 13
+#endif
+#ifndef HTSP_MMA_SPLIT_ACC
+#define HTSP_MMA_SPLIT_ACC 0
+#endif
+#ifndef HTSP_MMA_STAGES
+#define HTSP_MMA_STAGES 3
+#endif
+constexpr int MM_STAGES = HTSP_MMA_STAGES;
+constexpr int MM_KT = 48;            // keys per K2 tile (multiple of 16)
 constexpr float kScoreScale = 0.25f * 1.4426950408889634f;   // 1/sqrt(dk) * log2(e)
+constexpr float kLazy = 6.0f;                                 // lazy-rescale threshold (log2 units)
 constexpr float kInvSqrtH = 0.08838834764831845f;            // 1/sqrt(128)
 
 // image layout per instance (bytes): 8 KV tiles of 128*NP, then K2 tiles of 512*rows_t
@@ -154,6 +163,18 @@ __device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t&
   hi = *reinterpret_cast<uint32_t*>(&h);
   lo = *reinterpret_cast<uint32_t*>(&l);
 }
+__device__ __forceinline__ float ex2_approx(float x) {   // 2^x, rel. error 2^-22, -inf -> +0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 10*tanh(u) = 10 - 20/(2^(2u*log2e)+1): MUFU.EX2 + MUFU.RCP, abs. error < 4e-6 on the logit
+__device__ __forceinline__ float clip_tanh10(float u) {
+  const float e = ex2_approx(u * 2.8853900817779268f);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  return fmaf(-20.0f, r, 10.0f);
+}
 __device__ __forceinline__ float quad_max(float v) {
   v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
   return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
@@ -193,22 +214,20 @@ __global__ void __launch_bounds__((NWARPS + 1) * 32, 1) decode_mma_kernel(const 
   const int rows_here = min(A.rows_per_cta, G - g0);
   const int active_warps = (rows_here + 15) / 16;
   const int NWORDS = (NP + 31) / 32;
-  const int VSTRIDE = NWORDS + 1;
+  const int VSTRIDE = NWORDS | 1;       // odd stride: the 8 rows of a warp quarter hit distinct banks
   const int STAGE = stage_bytes(NP);
   const int NT2 = n_k2_tiles(NP);
   const int tiles_per_step = NH + NT2;
 
   // shared memory carve-up
   unsigned char* ring = smem;                                           // MM_STAGES * STAGE
-  float* qrow = (float*)(ring + (size_t)MM_STAGES * STAGE);             // [16*NWARPS][QROW_STRIDE]
-  float* c0s = qrow + (size_t)16 * NWARPS * QROW_STRIDE;                // [NP]
+  uint4* obuf = (uint4*)(ring + (size_t)MM_STAGES * STAGE);             // [NWARPS][NH][32][2]
+  float* qfs = (float*)(obuf + (size_t)NWARPS * NH * 64);               // [H]   qfix
+  float* c0s = qfs + H;                                                 // [NP]
   float2* xs = (float2*)(c0s + NP);                                     // [N]
   unsigned* vis = (unsigned*)(xs + N);                                  // [16*NWARPS][VSTRIDE]
   uint64_t* bars = (uint64_t*)(((uintptr_t)(vis + 16 * NWARPS * VSTRIDE) + 15) & ~(uintptr_t)15);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + MM_STAGES);
-  // per-warp staging of the O fragments (hi/lo A operands of the logits GEMM) in fragment order:
-  // [warp][head][lane][8 x b32]; every lane only ever touches its own 32 bytes
-  uint4* obuf = (uint4*)(bars + 2 * MM_STAGES);
 
   const int src = A.src[b], tgt = A.tgt[b];
   const float* projb = A.proj + (size_t)b * N * PROJ;
@@ -224,12 +243,7 @@ __global__ void __launch_bounds__((NWARPS + 1) * 32, 1) decode_mma_kernel(const 
   }
   for (int i = tid; i < N; i += blockDim.x) xs[i] = __ldg((const float2*)A.x + (size_t)b * N + i);
   for (int i = tid; i < NP; i += blockDim.x) c0s[i] = i < N ? __ldg(&A.c0[(size_t)b * N + i]) : 0.f;
-  for (int i = tid; i < 16 * NWARPS * H; i += blockDim.x) {
-    const int r = i / H, c = i % H;
-    const int g = min(g0 + r, G - 1);
-    qrow[r * QROW_STRIDE + c] =
-        __ldg(&A.qfix[(size_t)b * H + c]) + __ldg(&projb[(size_t)A.first[g] * PROJ + 3 * H + c]);
-  }
+  for (int i = tid; i < H; i += blockDim.x) qfs[i] = __ldg(&A.qfix[(size_t)b * H + i]);
   // visited masks: padded keys (>= N) are permanently visited
   for (int i = tid; i < 16 * NWARPS * VSTRIDE; i += blockDim.x) {
     const int w = i % VSTRIDE;
@@ -281,61 +295,72 @@ __global__ void __launch_bounds__((NWARPS + 1) * 32, 1) decode_mma_kernel(const 
   int32_t* piA = A.pi + ((size_t)b * G + min(gA, G - 1)) * N;
   int32_t* piB = A.pi + ((size_t)b * G + min(gB, G - 1)) * N;
 
-  // step 0: visit(first[g]) with source<->target coupling (train_path_solver.py:256-257, 45-66)
-  auto visit = [&](unsigned* v, int32_t* p, int& cur, int& cnt, int a, bool ok) {
-    // all four lanes of the quad execute this redundantly with identical values
-    if (ok) {
-      if (q4 == 0) { p[cnt] = a; }
-      v[a >> 5] |= 1u << (a & 31);
+  // visit(a) with source<->target coupling (train_path_solver.py:45-66); all four lanes of a quad
+  // execute it redundantly with identical values (same-value smem writes are benign)
+  auto visit = [&](unsigned* v, int32_t* p, int& cur, int& cnt, int a) {
+    if (q4 == 0) p[cnt] = a;
+    v[a >> 5] |= 1u << (a & 31);
+    cnt++;
+    cur = a;
+    const int partner = (a == src) ? tgt : ((a == tgt) ? src : -1);
+    if (partner >= 0) {
+      if (q4 == 0) p[cnt] = partner;
+      v[partner >> 5] |= 1u << (partner & 31);
       cnt++;
-      cur = a;
-      const int partner = (a == src) ? tgt : ((a == tgt) ? src : -1);
-      if (partner >= 0) {
-        if (q4 == 0) p[cnt] = partner;
-        v[partner >> 5] |= 1u << (partner & 31);
-        cnt++;
-        cur = partner;
-      }
+      cur = partner;
     }
   };
-  // quad lanes write the same smem word with the same value: benign; order with __syncwarp
-  if (okA) visit(visA, piA, curA, cntA, A.first[gA], true);
-  if (okB) visit(visB, piB, curB, cntB, A.first[gB], true);
+  // step 0: no decoder call (train_path_solver.py:256-257)
+  const int fA = A.first[min(gA, G - 1)], fB = A.first[min(gB, G - 1)];
+  if (okA) visit(visA, piA, curA, cntA, fA);
+  if (okB) visit(visB, piB, curB, cntB, fB);
   __syncwarp();
 
   uint32_t it = 0;
-  uint4* my_o = obuf + ((size_t)warp * NH * 32 + lane) * 2;   // + h*64 per head
-  const float* qrA = qrow + rA * QROW_STRIDE;
-  const float* qrB = qrow + rB * QROW_STRIDE;
+  uint4* my_o = obuf + (size_t)warp * NH * 64 + lane;         // hi at [h*64], lo at [h*64+32]: 16B lane stride
+  const float* qfA = projb + (size_t)fA * PROJ + 3 * H + 2 * q4;   // Wq_first emb[first]  (models.py:393-397)
+  const float* qfB = projb + (size_t)fB * PROJ + 3 * H + 2 * q4;
+  const int mi = lane >> 3, l7 = lane & 7;                    // ldmatrix lane addressing
 
   for (int step = 0; step < n_steps; ++step) {
-    const float* qlA = projb + (size_t)curA * PROJ + 2 * H;
-    const float* qlB = projb + (size_t)curB * PROJ + 2 * H;
+    const float* qlA = projb + (size_t)curA * PROJ + 2 * H + 2 * q4;   // Wq_last emb[cur] (models.py:409-411)
+    const float* qlB = projb + (size_t)curB * PROJ + 2 * H + 2 * q4;
+    // software prefetch of the per-head query pieces (L2-resident tables), one head ahead
+    float2 pf[8];
+    auto fetch_q = [&](int h) {
+      const int c = h * DK;
+      pf[0] = __ldg((const float2*)(qfA + c)); pf[1] = __ldg((const float2*)(qfA + c + 8));
+      pf[2] = __ldg((const float2*)(qfB + c)); pf[3] = __ldg((const float2*)(qfB + c + 8));
+      pf[4] = __ldg((const float2*)(qlA + c)); pf[5] = __ldg((const float2*)(qlA + c + 8));
+      pf[6] = __ldg((const float2*)(qlB + c)); pf[7] = __ldg((const float2*)(qlB + c + 8));
+    };
+    fetch_q(0);
     // ------------------------------------------------------------ glimpse, one head at a time
 #pragma unroll 1
     for (int h = 0; h < NH; ++h, ++it) {
-      // q = (qfix + q_first) + q_last  (models.py:409-413), A fragments hi/lo
+      // q = ((q_graph+q_source+q_target) + q_first) + q_last  (models.py:413); 1/sqrt(dk)*log2(e) is
+      // folded in so the MMA result is the base-2 exponent directly.  A fragments hi/lo.
       uint32_t qh[4], ql[4];
       {
-        const int c = h * DK + 2 * q4;
-        const float2 fa0 = *(const float2*)(qrA + c), fa1 = *(const float2*)(qrA + c + 8);
-        const float2 fb0 = *(const float2*)(qrB + c), fb1 = *(const float2*)(qrB + c + 8);
-        const float2 la0 = __ldg((const float2*)(qlA + c)), la1 = __ldg((const float2*)(qlA + c + 8));
-        const float2 lb0 = __ldg((const float2*)(qlB + c)), lb1 = __ldg((const float2*)(qlB + c + 8));
-        split2(fa0.x + la0.x, fa0.y + la0.y, qh[0], ql[0]);
-        split2(fb0.x + lb0.x, fb0.y + lb0.y, qh[1], ql[1]);
-        split2(fa1.x + la1.x, fa1.y + la1.y, qh[2], ql[2]);
-        split2(fb1.x + lb1.x, fb1.y + lb1.y, qh[3], ql[3]);
+        const float2 x0 = *(const float2*)(qfs + h * DK + 2 * q4);
+        const float2 x1 = *(const float2*)(qfs + h * DK + 2 * q4 + 8);
+        split2(((x0.x + pf[0].x) + pf[4].x) * kScoreScale, ((x0.y + pf[0].y) + pf[4].y) * kScoreScale, qh[0], ql[0]);
+        split2(((x0.x + pf[2].x) + pf[6].x) * kScoreScale, ((x0.y + pf[2].y) + pf[6].y) * kScoreScale, qh[1], ql[1]);
+        split2(((x1.x + pf[1].x) + pf[5].x) * kScoreScale, ((x1.y + pf[1].y) + pf[5].y) * kScoreScale, qh[2], ql[2]);
+        split2(((x1.x + pf[3].x) + pf[7].x) * kScoreScale, ((x1.y + pf[3].y) + pf[7].y) * kScoreScale, qh[3], ql[3]);
       }
+      if (h + 1 < NH) fetch_q(h + 1);
       const uint32_t s = it % MM_STAGES, use = it / MM_STAGES;
       mbar_wait(full0 + 8 * s, use & 1);
       const uint32_t tile = smem_u32(ring + (size_t)s * STAGE);
       const uint32_t khi = tile, klo = tile + NP * 32, vhi = tile + 2 * NP * 32, vlo = tile + 3 * NP * 32;
 
-      float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
-      float mA = -INFINITY, mB = -INFINITY, lA = 0.f, lB = 0.f;
-      // ldmatrix lane addressing
-      const int mi = lane >> 3, l7 = lane & 7;
+      // hi*hi and (hi*lo + lo*hi) are accumulated separately: independent MMA chains (ILP) and the
+      // small cross terms do not get absorbed into the large sum
+      float o0h[4] = {0.f, 0.f, 0.f, 0.f}, o1h[4] = {0.f, 0.f, 0.f, 0.f};
+      float o0l[4] = {0.f, 0.f, 0.f, 0.f}, o1l[4] = {0.f, 0.f, 0.f, 0.f};
+      // shift starts at a finite floor so (-inf) - m never produces NaN; any real score lifts it
+      float mA = -1e30f, mB = -1e30f, lA = 0.f, lB = 0.f;
 #pragma unroll
       for (int kc = 0; kc < NCHUNK; ++kc) {
         // ---- S = Q K^T for 16 keys (two n8 tiles)
@@ -349,35 +374,55 @@ __global__ void __launch_bounds__((NWARPS + 1) * 32, 1) decode_mma_kernel(const 
         if (!A.fast) {
           uint32_t bl0, bl1, bl2, bl3;
           ldsm_x4(klo + offK, bl0, bl1, bl2, bl3);
+#if HTSP_MMA_SPLIT_ACC
+          float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+          mma16816(c0, qh, bl0, bl1);
+          mma16816(c1, qh, bl2, bl3);
+          mma16816(c0, ql, bh0, bh1);
+          mma16816(c1, ql, bh2, bh3);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { s0[e] += c0[e]; s1[e] += c1[e]; }
+#else
           mma16816(s0, qh, bl0, bl1);
           mma16816(s1, qh, bl2, bl3);
           mma16816(s0, ql, bh0, bh1);
           mma16816(s1, ql, bh2, bh3);
+#endif
         }
         // ---- mask + online softmax (utils.py:20-27), exponent base 2
         const int key0 = kc * 16 + 2 * q4;                 // keys key0,key0+1 (tile 0), +8,+9 (tile 1)
         const unsigned wA = visA[key0 >> 5] >> (key0 & 31);
         const unsigned wB = visB[key0 >> 5] >> (key0 & 31);
-        float t0 = (wA & 1u) ? -INFINITY : s0[0] * kScoreScale;
-        float t1 = (wA & 2u) ? -INFINITY : s0[1] * kScoreScale;
-        float t2 = (wA & 0x100u) ? -INFINITY : s1[0] * kScoreScale;
-        float t3 = (wA & 0x200u) ? -INFINITY : s1[1] * kScoreScale;
-        float u0 = (wB & 1u) ? -INFINITY : s0[2] * kScoreScale;
-        float u1 = (wB & 2u) ? -INFINITY : s0[3] * kScoreScale;
-        float u2 = (wB & 0x100u) ? -INFINITY : s1[2] * kScoreScale;
-        float u3 = (wB & 0x200u) ? -INFINITY : s1[3] * kScoreScale;
-        const float nmA = fmaxf(mA, quad_max(fmaxf(fmaxf(t0, t1), fmaxf(t2, t3))));
-        const float nmB = fmaxf(mB, quad_max(fmaxf(fmaxf(u0, u1), fmaxf(u2, u3))));
-        const float sA = (nmA == -INFINITY) ? 0.f : nmA;
-        const float sB = (nmB == -INFINITY) ? 0.f : nmB;
-        const float aA = exp2f(mA - sA), aB = exp2f(mB - sB);   // mA=-inf -> 0
-        mA = nmA; mB = nmB;
-        t0 = exp2f(t0 - sA); t1 = exp2f(t1 - sA); t2 = exp2f(t2 - sA); t3 = exp2f(t3 - sA);
-        u0 = exp2f(u0 - sB); u1 = exp2f(u1 - sB); u2 = exp2f(u2 - sB); u3 = exp2f(u3 - sB);
-        lA = lA * aA + ((t0 + t1) + (t2 + t3));
-        lB = lB * aB + ((u0 + u1) + (u2 + u3));
-        o0[0] *= aA; o0[1] *= aA; o1[0] *= aA; o1[1] *= aA;
-        o0[2] *= aB; o0[3] *= aB; o1[2] *= aB; o1[3] *= aB;
+        float t0 = (wA & 1u) ? -INFINITY : s0[0];
+        float t1 = (wA & 2u) ? -INFINITY : s0[1];
+        float t2 = (wA & 0x100u) ? -INFINITY : s1[0];
+        float t3 = (wA & 0x200u) ? -INFINITY : s1[1];
+        float u0 = (wB & 1u) ? -INFINITY : s0[2];
+        float u1 = (wB & 2u) ? -INFINITY : s0[3];
+        float u2 = (wB & 0x100u) ? -INFINITY : s1[2];
+        float u3 = (wB & 0x200u) ? -INFINITY : s1[3];
+        // lazy online softmax: the running shift m only moves when some row of the warp sees a
+        // score more than kLazy above it (p stays <= 2^kLazy, well inside fp16), so most chunks
+        // skip the max reduction and the O/l rescale entirely
+        const float cA = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
+        const float cB = fmaxf(fmaxf(u0, u1), fmaxf(u2, u3));
+        if (__any_sync(0xffffffffu, (cA > mA + kLazy) || (cB > mB + kLazy))) {
+          const float nmA = fmaxf(mA, quad_max(cA));
+          const float nmB = fmaxf(mB, quad_max(cB));
+          const float aA = ex2_approx(mA - nmA), aB = ex2_approx(mB - nmB);
+          mA = nmA; mB = nmB;
+          lA *= aA; lB *= aB;
+          o0h[0] *= aA; o0h[1] *= aA; o1h[0] *= aA; o1h[1] *= aA;
+          o0h[2] *= aB; o0h[3] *= aB; o1h[2] *= aB; o1h[3] *= aB;
+#if HTSP_MMA_SPLIT_ACC
+          o0l[0] *= aA; o0l[1] *= aA; o1l[0] *= aA; o1l[1] *= aA;
+          o0l[2] *= aB; o0l[3] *= aB; o1l[2] *= aB; o1l[3] *= aB;
+#endif
+        }
+        t0 = ex2_approx(t0 - mA); t1 = ex2_approx(t1 - mA); t2 = ex2_approx(t2 - mA); t3 = ex2_approx(t3 - mA);
+        u0 = ex2_approx(u0 - mB); u1 = ex2_approx(u1 - mB); u2 = ex2_approx(u2 - mB); u3 = ex2_approx(u3 - mB);
+        lA += (t0 + t1) + (t2 + t3);
+        lB += (u0 + u1) + (u2 + u3);
         // ---- O += P V for these 16 keys
         uint32_t ph[4], pl[4];
         split2(t0, t1, ph[0], pl[0]);
@@ -389,28 +434,37 @@ __global__ void __launch_bounds__((NWARPS + 1) * 32, 1) decode_mma_kernel(const 
         uint32_t vh0, vh1, vh2, vh3, vl0, vl1, vl2, vl3;
         ldsm_x4_t(vhi + offV, vh0, vh1, vh2, vh3);
         ldsm_x4_t(vlo + offV, vl0, vl1, vl2, vl3);
-        mma16816(o0, ph, vh0, vh1);
-        mma16816(o1, ph, vh2, vh3);
-        mma16816(o0, ph, vl0, vl1);
-        mma16816(o1, ph, vl2, vl3);
-        mma16816(o0, pl, vh0, vh1);
-        mma16816(o1, pl, vh2, vh3);
+#if HTSP_MMA_SPLIT_ACC
+        mma16816(o0h, ph, vh0, vh1);
+        mma16816(o1h, ph, vh2, vh3);
+        mma16816(o0l, ph, vl0, vl1);
+        mma16816(o1l, ph, vl2, vl3);
+        mma16816(o0l, pl, vh0, vh1);
+        mma16816(o1l, pl, vh2, vh3);
+#else
+        mma16816(o0h, ph, vh0, vh1);
+        mma16816(o1h, ph, vh2, vh3);
+        mma16816(o0h, ph, vl0, vl1);
+        mma16816(o1h, ph, vl2, vl3);
+        mma16816(o0h, pl, vh0, vh1);
+        mma16816(o1h, pl, vh2, vh3);
+#endif
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty0 + 8 * s);
       const float iA = 1.f / quad_sum(lA), iB = 1.f / quad_sum(lB);
       uint4 fh, fl;
-      split2(o0[0] * iA, o0[1] * iA, fh.x, fl.x);
-      split2(o0[2] * iB, o0[3] * iB, fh.y, fl.y);
-      split2(o1[0] * iA, o1[1] * iA, fh.z, fl.z);
-      split2(o1[2] * iB, o1[3] * iB, fh.w, fl.w);
+      split2((o0h[0] + o0l[0]) * iA, (o0h[1] + o0l[1]) * iA, fh.x, fl.x);
+      split2((o0h[2] + o0l[2]) * iB, (o0h[3] + o0l[3]) * iB, fh.y, fl.y);
+      split2((o1h[0] + o1l[0]) * iA, (o1h[1] + o1l[1]) * iA, fh.z, fl.z);
+      split2((o1h[2] + o1l[2]) * iB, (o1h[3] + o1l[3]) * iB, fh.w, fl.w);
       my_o[h * 64] = fh;
-      my_o[h * 64 + 1] = fl;
+      my_o[h * 64 + 32] = fl;
     }
     uint32_t ohi[NH][4], olo[NH][4];
 #pragma unroll
     for (int h = 0; h < NH; ++h) {
-      const uint4 fh = my_o[h * 64], fl = my_o[h * 64 + 1];
+      const uint4 fh = my_o[h * 64], fl = my_o[h * 64 + 32];
       ohi[h][0] = fh.x; ohi[h][1] = fh.y; ohi[h][2] = fh.z; ohi[h][3] = fh.w;
       olo[h][0] = fl.x; olo[h][1] = fl.y; olo[h][2] = fl.z; olo[h][3] = fl.w;
     }
@@ -425,44 +479,69 @@ __global__ void __launch_bounds__((NWARPS + 1) * 32, 1) decode_mma_kernel(const 
       mbar_wait(full0 + 8 * s, use & 1);
       const int rows_t = min(MM_KT, NP - t * MM_KT);
       const uint32_t k2hi = smem_u32(ring + (size_t)s * STAGE), k2lo = k2hi + rows_t * 256;
-      const int mi = lane >> 3, l7 = lane & 7;
-      for (int nt = 0; nt < rows_t / 8; ++nt) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        const int rl = nt * 8 + l7;
+      // two n8 tiles (16 keys) per iteration, hi*hi and cross terms in separate accumulators:
+      // four independent MMA chains
+#pragma unroll 1
+      for (int np = 0; np < rows_t / 16; ++np) {
+        float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+        float x0[4] = {0.f, 0.f, 0.f, 0.f}, x1[4] = {0.f, 0.f, 0.f, 0.f};
+        const int r0 = np * 16 + l7, r1 = r0 + 8;
 #pragma unroll
         for (int kp = 0; kp < NH / 2; ++kp) {       // two k16 steps (= two heads) per ldmatrix.x4
-          const uint32_t off = rl * 256 + ((((2 * kp) * 2 + mi) ^ (rl & 7)) * 16);
+          const uint32_t off0 = r0 * 256 + (((4 * kp + mi) ^ (r0 & 7)) * 16);
+          const uint32_t off1 = r1 * 256 + (((4 * kp + mi) ^ (r1 & 7)) * 16);
           uint32_t bh0, bh1, bh2, bh3, bl0, bl1, bl2, bl3;
-          ldsm_x4(k2hi + off, bh0, bh1, bh2, bh3);
-          ldsm_x4(k2lo + off, bl0, bl1, bl2, bl3);
-          mma16816(acc, ohi[2 * kp], bh0, bh1);
-          mma16816(acc, ohi[2 * kp + 1], bh2, bh3);
-          mma16816(acc, ohi[2 * kp], bl0, bl1);
-          mma16816(acc, ohi[2 * kp + 1], bl2, bl3);
-          mma16816(acc, olo[2 * kp], bh0, bh1);
-          mma16816(acc, olo[2 * kp + 1], bh2, bh3);
+          uint32_t dh0, dh1, dh2, dh3, dl0, dl1, dl2, dl3;
+          ldsm_x4(k2hi + off0, bh0, bh1, bh2, bh3);
+          ldsm_x4(k2hi + off1, dh0, dh1, dh2, dh3);
+          ldsm_x4(k2lo + off0, bl0, bl1, bl2, bl3);
+          ldsm_x4(k2lo + off1, dl0, dl1, dl2, dl3);
+#if HTSP_MMA_SPLIT_ACC
+#define XACC0 x0
+#define XACC1 x1
+#else
+#define XACC0 a0
+#define XACC1 a1
+#endif
+          mma16816(a0, ohi[2 * kp], bh0, bh1);
+          mma16816(a1, ohi[2 * kp], dh0, dh1);
+          mma16816(XACC0, ohi[2 * kp], bl0, bl1);
+          mma16816(XACC1, ohi[2 * kp], dl0, dl1);
+          mma16816(a0, ohi[2 * kp + 1], bh2, bh3);
+          mma16816(a1, ohi[2 * kp + 1], dh2, dh3);
+          mma16816(XACC0, olo[2 * kp], bh0, bh1);
+          mma16816(XACC1, olo[2 * kp], dh0, dh1);
+          mma16816(XACC0, ohi[2 * kp + 1], bl2, bl3);
+          mma16816(XACC1, ohi[2 * kp + 1], dl2, dl3);
+          mma16816(XACC0, olo[2 * kp + 1], bh2, bh3);
+          mma16816(XACC1, olo[2 * kp + 1], dh2, dh3);
         }
         // score/sqrt(H) -> 10*tanh -> mask -> running arg-max, first index wins (models.py:438-440)
-        const int key0 = t * MM_KT + nt * 8 + 2 * q4;
-        const float2 cc = *(const float2*)(c0s + key0);
-        const unsigned wA = visA[key0 >> 5] >> (key0 & 31);
-        const unsigned wB = visB[key0 >> 5] >> (key0 & 31);
-        float zA0 = 10.0f * tanhf((acc[0] + cc.x) * kInvSqrtH);
-        float zA1 = 10.0f * tanhf((acc[1] + cc.y) * kInvSqrtH);
-        float zB0 = 10.0f * tanhf((acc[2] + cc.x) * kInvSqrtH);
-        float zB1 = 10.0f * tanhf((acc[3] + cc.y) * kInvSqrtH);
-        if (wA & 1u) zA0 = -INFINITY;
-        if (wA & 2u) zA1 = -INFINITY;
-        if (wB & 1u) zB0 = -INFINITY;
-        if (wB & 2u) zB1 = -INFINITY;
-        if (loA != nullptr) {
-          if (okA && key0 < N) { loA[key0] = zA0; if (key0 + 1 < N) loA[key0 + 1] = zA1; }
-          if (okB && key0 < N) { loB[key0] = zB0; if (key0 + 1 < N) loB[key0 + 1] = zB1; }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const float* acc = half ? a1 : a0;
+          const float* crs = half ? x1 : x0;
+          const int key0 = t * MM_KT + np * 16 + half * 8 + 2 * q4;
+          const float2 cc = *(const float2*)(c0s + key0);
+          const unsigned wA = visA[key0 >> 5] >> (key0 & 31);
+          const unsigned wB = visB[key0 >> 5] >> (key0 & 31);
+          float zA0 = clip_tanh10(((acc[0] + crs[0]) + cc.x) * kInvSqrtH);
+          float zA1 = clip_tanh10(((acc[1] + crs[1]) + cc.y) * kInvSqrtH);
+          float zB0 = clip_tanh10(((acc[2] + crs[2]) + cc.x) * kInvSqrtH);
+          float zB1 = clip_tanh10(((acc[3] + crs[3]) + cc.y) * kInvSqrtH);
+          if (wA & 1u) zA0 = -INFINITY;
+          if (wA & 2u) zA1 = -INFINITY;
+          if (wB & 1u) zB0 = -INFINITY;
+          if (wB & 2u) zB1 = -INFINITY;
+          if (loA != nullptr) {
+            if (okA && key0 < N) { loA[key0] = zA0; if (key0 + 1 < N) loA[key0 + 1] = zA1; }
+            if (okB && key0 < N) { loB[key0] = zB0; if (key0 + 1 < N) loB[key0 + 1] = zB1; }
+          }
+          if (zA0 > bestA) { bestA = zA0; idxA = key0; }
+          if (zA1 > bestA) { bestA = zA1; idxA = key0 + 1; }
+          if (zB0 > bestB) { bestB = zB0; idxB = key0; }
+          if (zB1 > bestB) { bestB = zB1; idxB = key0 + 1; }
         }
-        if (zA0 > bestA) { bestA = zA0; idxA = key0; }
-        if (zA1 > bestA) { bestA = zA1; idxA = key0 + 1; }
-        if (zB0 > bestB) { bestB = zB0; idxB = key0; }
-        if (zB1 > bestB) { bestB = zB1; idxB = key0 + 1; }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty0 + 8 * s);
@@ -478,14 +557,8 @@ __global__ void __launch_bounds__((NWARPS + 1) * 32, 1) decode_mma_kernel(const 
     }
     // ---- state update (train_path_solver.py:45-72); all quad lanes hold identical values
     __syncwarp();
-    if (okA) {
-      const int a = A.forced_pi ? A.forced_pi[((size_t)b * G + gA) * N + cntA] : idxA;
-      visit(visA, piA, curA, cntA, a, true);
-    }
-    if (okB) {
-      const int a = A.forced_pi ? A.forced_pi[((size_t)b * G + gB) * N + cntB] : idxB;
-      visit(visB, piB, curB, cntB, a, true);
-    }
+    if (okA) visit(visA, piA, curA, cntA, A.forced_pi ? A.forced_pi[((size_t)b * G + gA) * N + cntA] : idxA);
+    if (okB) visit(visB, piB, curB, cntB, A.forced_pi ? A.forced_pi[((size_t)b * G + gB) * N + cntB] : idxB);
     __syncwarp();
   }
   // ---- reward = -(closed tour length - fixed edge)   (train_path_solver.py:109-149)
@@ -527,9 +600,8 @@ template <int NWARPS>
 static size_t mma_smem_bytes(int N, int NP) {
   const int NWORDS = (NP + 31) / 32;
   size_t b = (size_t)MM_STAGES * stage_bytes(NP);
-  b += (size_t)16 * NWARPS * QROW_STRIDE * 4;
-  b += (size_t)NP * 4 + (size_t)N * 8;
-  b += (size_t)16 * NWARPS * (NWORDS + 1) * 4;
+  b += (size_t)H * 4 + (size_t)NP * 4 + (size_t)N * 8;
+  b += (size_t)16 * NWARPS * (NWORDS | 1) * 4;
   b += 16 + 2 * MM_STAGES * 8;
   b += (size_t)NWARPS * NH * 32 * 32;
   return b;
@@ -564,7 +636,7 @@ int launch_decode_mma(const float* x, const float* proj, const float* qfix, cons
     decode_pack_kernel<<<blocks, 256, 0, s>>>(proj, Bp, N, NP, (unsigned char*)pack_ws);
     HTSP_CHECK_LAUNCH();
   }
-  constexpr int NW = 7;
+  constexpr int NW = HTSP_MMA_NWARPS;
   MmaArgs a;
   a.x = x; a.proj = proj; a.qfix = qfix; a.c0 = c0; a.img = (const unsigned char*)pack_ws;
   a.src = src; a.tgt = tgt; a.first = first; a.forced_pi = forced_pi;

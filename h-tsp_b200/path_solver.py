@@ -64,7 +64,7 @@ class B200PathSolver(torch.nn.Module):
     available) or "fast" (tensor cores, single-fp16 glimpse scores)."""
 
     def __init__(self, cfg=None, state_dict: Optional[Dict[str, torch.Tensor]] = None,
-                 n_layers: Optional[int] = None, graph_size: int = 200, mode: str = "fp32",
+                 n_layers: Optional[int] = None, graph_size: int = 200, mode: str = "x3",
                  device="cuda"):
         super().__init__()
         if cfg is None:
