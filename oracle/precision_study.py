@@ -1,5 +1,9 @@
-import sys, math, time
-sys.path.insert(0, '/root/repo')
+"""TEST INFRASTRUCTURE ONLY -- CPU emulation of candidate tensor-core arithmetics for the path
+solver (operand rounding to bf16/fp16/tf32 and hi+lo splits, fp32 accumulate), teacher-forced
+against the fp32 oracle: prints max/rms error of the 10*tanh logits per stage.  The table in
+DESIGN.md section 4 comes from `python oracle/precision_study.py 6`."""
+import math, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.nn.functional as F
 from oracle import path_solver_oracle as po
 import htsp_b200
@@ -16,6 +20,9 @@ def mm(a, b, mode):
     if mode == 'fp16x3':
         ah, bh = rh(a), rh(b); al, bl = rh(a-ah), rh(b-bh)
         return ah@bh + (ah@bl + al@bh)
+    if mode == 'fp16x2b':   # only b split
+        ah = rh(a); bh = rh(b); bl = rh(b-bh)
+        return ah@bh + ah@bl
     if mode == 'fp16x2a':
         ah = rh(a); al = rh(a-ah); bh = rh(b)
         return ah@bh + al@bh
@@ -116,21 +123,25 @@ if __name__ == '__main__':
         res = po.rollout(sd, x, src, tgt, first, capture_logits=True)
         base = dict(enc_gemm='fp32', enc_attn='fp32', reset='fp32', qk='fp32', pv='fp32', comb='fp32', logit='fp32')
         cfgs = {
-          'all fp16': {k:'fp16' for k in base},
-          'all fp16x3': {k:'fp16x3' for k in base},
-          'all fp16x3 fold': dict({k:'fp16x3' for k in base}, fold=True),
-          'all bf16x3 fold': dict({k:'bf16x3' for k in base}, fold=True),
-          'dec fp16x3 fold, enc fp32': dict(base, reset='fp16x3', qk='fp16x3', pv='fp16x3', logit='fp16x3', fold=True),
-          'dec fp16x3 fold, qk fp16, enc fp32': dict(base, reset='fp16x3', qk='fp16', pv='fp16x3', logit='fp16x3', fold=True),
+          'all fp32 (hoisted order)': base,
+          'all fp32 folded': dict(base, fold=True),
+          'all bf16': {k: 'bf16' for k in base},
+          'all fp16': {k: 'fp16' for k in base},
+          'enc tf32 only': dict(base, enc_gemm='tf32', enc_attn='tf32'),
+          'logit tf32 only': dict(base, logit='tf32'),
+          'all bf16x3 fold': dict({k: 'bf16x3' for k in base}, fold=True),
+          'all fp16x3 fold (mode x3)': dict({k: 'fp16x3' for k in base}, fold=True),
+          'fp16x3 fold, qk fp16 (mode fast)': dict({k: 'fp16x3' for k in base}, qk='fp16', fold=True),
+          'enc fp16x3 only': dict(base, enc_gemm='fp16x3', enc_attn='fp16x3'),
+          'enc gemm fp16x3, attn fp16': dict(base, enc_gemm='fp16x3', enc_attn='fp16'),
           'qk fp16 only': dict(base, qk='fp16'),
           'pv fp16 only': dict(base, pv='fp16'),
-          'pv fp16x2a only': dict(base, pv='fp16x2a'),
+          'pv fp16x2a (P split only)': dict(base, pv='fp16x2a'),
+          'pv fp16x2b (V split only)': dict(base, pv='fp16x2b'),
           'logit fp16 only fold': dict(base, logit='fp16', fold=True),
-          'enc fp16 only': dict(base, enc_gemm='fp16', enc_attn='fp16'),
-          'enc fp16x3 only': dict(base, enc_gemm='fp16x3', enc_attn='fp16x3'),
-          'enc gemm fp16x3 attn fp16': dict(base, enc_gemm='fp16x3', enc_attn='fp16'),
+          'comb bf16 only': dict(base, comb='bf16'),
+          'reset bf16 only': dict(base, reset='bf16'),
         }
         for name, cfg in cfgs.items():
-            t=time.time()
             mx, rms, fl = run(sd, x, src, tgt, first, res.pi, cfg, res.logits)
             print(f"{name:40s} max|dz|={mx:.2e} rms={rms:.2e} argmax-flip={fl:.4f}", flush=True)
