@@ -44,7 +44,7 @@ extern "C" int htsp_set_kernel_timer(void* start_event, void* stop_event) {
 
 extern "C" size_t htsp_weights_blob_bytes(int n_layers) {
   if (n_layers < 0) return 0;
-  return dec_off(n_layers).end * sizeof(float);
+  return half_section_byte_off(n_layers) + half_section_halfs(n_layers) * sizeof(__half);
 }
 extern "C" int htsp_n_weight_tensors(int n_layers) { return 2 + 17 * n_layers + 9; }
 
@@ -54,7 +54,8 @@ extern "C" int htsp_pack_weights(const float* const* t, int n_tensors, int n_lay
   HTSP_REQUIRE(n_layers >= 0 && n_tensors == htsp_n_weight_tensors(n_layers), "tensor count");
   for (int i = 0; i < n_tensors; ++i) HTSP_REQUIRE(t[i] != nullptr, "null tensor");
   const DecOff d = dec_off(n_layers);
-  std::vector<float> blob(d.end);
+  const size_t total_bytes = htsp_weights_blob_bytes(n_layers);
+  std::vector<float> blob((total_bytes + 3) / 4, 0.f);
   float* o = blob.data();
   int k = 0;
   memcpy(o + kEncInitW, t[k++], sizeof(float) * H * 2);
@@ -95,16 +96,36 @@ extern "C" int htsp_pack_weights(const float* const* t, int n_tensors, int n_lay
     for (int c = 0; c < H; ++c) o[d.wproj + (size_t)4 * H * H + (size_t)i * H + c] = wc[(size_t)c * H + i];
   memcpy(o + d.wc, wc, sizeof(float) * H * H);
   memcpy(o + d.bc, bc, sizeof(float) * H);
+  // fp16 hi/lo copies of the GEMM weights for the tensor-core layers (w = hi + lo)
+  {
+    __half* hs = (__half*)((char*)o + half_section_byte_off(n_layers));
+    auto split = [&](const float* w, size_t n, size_t hi_off, size_t lo_off) {
+      for (size_t i = 0; i < n; ++i) {
+        const __half h = __float2half_rn(w[i]);
+        hs[hi_off + i] = h;
+        hs[lo_off + i] = __float2half_rn(w[i] - __half2float(h));
+      }
+    };
+    for (int l = 0; l < n_layers; ++l) {
+      const EncLayerOff e = enc_layer_off(l);
+      const EncLayerOffH eh = enc_layer_off_h(l);
+      split(o + e.wqkv, (size_t)3 * H * H, eh.wqkv_hi, eh.wqkv_lo);
+      split(o + e.wo, (size_t)H * H, eh.wo_hi, eh.wo_lo);
+      split(o + e.w1, (size_t)FF * H, eh.w1_hi, eh.w1_lo);
+      split(o + e.w2, (size_t)H * FF, eh.w2_hi, eh.w2_lo);
+    }
+    split(o + d.wproj, (size_t)PROJ * H, wproj_hi_off_h(n_layers), wproj_lo_off_h(n_layers));
+  }
   // synchronous copy: the staging vector dies at return
-  HTSP_CHECK_CUDA(cudaMemcpyAsync(dev_blob, o, d.end * sizeof(float), cudaMemcpyHostToDevice,
+  HTSP_CHECK_CUDA(cudaMemcpyAsync(dev_blob, o, total_bytes, cudaMemcpyHostToDevice,
                                   (cudaStream_t)stream));
   HTSP_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return HTSP_OK;
 }
 
 extern "C" size_t htsp_encode_workspace_bytes(int Bp, int N, int mode) {
-  (void)mode;
   if (Bp <= 0 || N <= 0) return 0;
+  if (mode != HTSP_MODE_FP32) return encode_tc_ws_bytes(Bp, N);
   return encode_f32_ws_floats(Bp, N) * sizeof(float);
 }
 
@@ -119,6 +140,8 @@ extern "C" int htsp_encode(const void* blob, int n_layers, const float* x, int B
               htsp_encode_workspace_bytes(Bp, N, mode));
     return HTSP_ERR_WORKSPACE;
   }
+  if (mode != HTSP_MODE_FP32)
+    return launch_encode_tc(blob, n_layers, x, Bp, N, emb, workspace, (cudaStream_t)stream);
   return launch_encode_f32((const float*)blob, n_layers, x, Bp, N, emb, (float*)workspace,
                            (cudaStream_t)stream);
 }
@@ -131,7 +154,7 @@ extern "C" size_t htsp_decode_workspace_bytes(int Bp, int N, int G, int mode) {
   (void)G;
   if (Bp <= 0 || N <= 0) return 0;
   size_t b = dec_proj_bytes(Bp, N) + dec_qfix_bytes(Bp) + dec_c0_bytes(Bp, N);
-  if (mode != HTSP_MODE_FP32) b += decode_mma_pack_bytes(Bp, N);
+  if (mode != HTSP_MODE_FP32) b += decode_mma_pack_bytes(Bp, N) + decode_prep_tc_ws_bytes(Bp, N);
   return b;
 }
 
@@ -154,11 +177,14 @@ extern "C" int htsp_decode(const void* blob, int n_layers, const float* x, const
   float* proj = (float*)w; w += dec_proj_bytes(Bp, N);
   float* qfix = (float*)w; w += dec_qfix_bytes(Bp);
   float* c0 = (float*)w;   w += dec_c0_bytes(Bp, N);
-  int rc = launch_decode_prep((const float*)blob, n_layers, emb, src, tgt, Bp, N, proj, qfix, c0, s);
+  const bool tc = mode != HTSP_MODE_FP32;
+  void* pack_ws = w;
+  void* prep_ws = tc ? (void*)(w + decode_mma_pack_bytes(Bp, N)) : nullptr;
+  int rc = launch_decode_prep(blob, n_layers, emb, src, tgt, Bp, N, proj, qfix, c0, tc, prep_ws, s);
   if (rc) return rc;
   if (mode == HTSP_MODE_FP32)
     return launch_decode_f32((const float*)blob, n_layers, x, emb, proj, qfix, src, tgt, first, Bp,
                              N, G, forced_pi, pi, reward, logits_out, s);
   return launch_decode_mma(x, proj, qfix, c0, src, tgt, first, Bp, N, G, mode, forced_pi, pi, reward,
-                           logits_out, w, s);
+                           logits_out, pack_ws, s);
 }

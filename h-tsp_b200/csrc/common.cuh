@@ -56,6 +56,35 @@ __host__ __device__ inline DecOff dec_off(int n_layers) {
   return d;
 }
 
+// ---- fp16 hi/lo copies of the GEMM weights (tensor-core modes), offsets in halfs from the start of
+// the fp16 section that follows the fp32 section (256-byte aligned)
+struct EncLayerOffH {
+  size_t wqkv_hi, wqkv_lo, wo_hi, wo_lo, w1_hi, w1_lo, w2_hi, w2_lo;
+};
+constexpr size_t kEncLayerHalfs = 2 * ((size_t)3 * H * H + (size_t)H * H + (size_t)FF * H + (size_t)H * FF);
+__host__ __device__ inline EncLayerOffH enc_layer_off_h(int l) {
+  EncLayerOffH o;
+  size_t p = (size_t)l * kEncLayerHalfs;
+  o.wqkv_hi = p; p += (size_t)3 * H * H;
+  o.wqkv_lo = p; p += (size_t)3 * H * H;
+  o.wo_hi = p;   p += (size_t)H * H;
+  o.wo_lo = p;   p += (size_t)H * H;
+  o.w1_hi = p;   p += (size_t)FF * H;
+  o.w1_lo = p;   p += (size_t)FF * H;
+  o.w2_hi = p;   p += (size_t)H * FF;
+  o.w2_lo = p;   p += (size_t)H * FF;
+  return o;
+}
+__host__ __device__ inline size_t wproj_hi_off_h(int n_layers) { return (size_t)n_layers * kEncLayerHalfs; }
+__host__ __device__ inline size_t wproj_lo_off_h(int n_layers) { return wproj_hi_off_h(n_layers) + (size_t)PROJ * H; }
+__host__ __device__ inline size_t half_section_halfs(int n_layers) { return wproj_lo_off_h(n_layers) + (size_t)PROJ * H; }
+__host__ __device__ inline size_t half_section_byte_off(int n_layers) {
+  return (dec_off(n_layers).end * sizeof(float) + 255) / 256 * 256;
+}
+inline const __half* blob_halfs(const void* blob, int n_layers) {
+  return (const __half*)((const char*)blob + half_section_byte_off(n_layers));
+}
+
 // ---- error plumbing -------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
@@ -97,10 +126,24 @@ int launch_linear_f32(const float* X, const float* W, const float* bias, const f
 int launch_encode_f32(const float* blob, int n_layers, const float* x, int Bp, int N, float* emb,
                       float* ws, cudaStream_t s);
 size_t encode_f32_ws_floats(int Bp, int N);
+// gemm_tc.cu (tcgen05 + TMA)
+int launch_linear_tc(const __half* xhi, const __half* xlo, const __half* whi, const __half* wlo,
+                     const float* bias, const float* residual, const float* bn_alpha,
+                     const float* bn_beta, bool relu, float* y32, __half* yhi, __half* ylo, int M,
+                     int Nout, int K, cudaStream_t s);
+int launch_split_f16(const float* x, __half* hi, __half* lo, size_t n, cudaStream_t s);
+// encoder_tc.cu
+size_t encode_tc_ws_bytes(int Bp, int N);
+int launch_encode_tc(const void* blob, int n_layers, const float* x, int Bp, int N, float* emb,
+                     void* ws, cudaStream_t s);
+int launch_init_proj(const float* blob, const float* x, float* emb, size_t M, cudaStream_t s);
+int launch_enc_attention(const float* qkv, float* out, __half* ohi, __half* olo, int Bp, int N,
+                         cudaStream_t s);
 // decode_prep.cu
-int launch_decode_prep(const float* blob, int n_layers, const float* emb, const int32_t* src,
+size_t decode_prep_tc_ws_bytes(int Bp, int N);
+int launch_decode_prep(const void* blob, int n_layers, const float* emb, const int32_t* src,
                        const int32_t* tgt, int Bp, int N, float* proj, float* qfix, float* c0,
-                       cudaStream_t s);
+                       bool tensor_cores, void* tc_ws, cudaStream_t s);
 // decode_f32.cu
 int launch_decode_f32(const float* blob, int n_layers, const float* x, const float* emb,
                       const float* proj, const float* qfix, const int32_t* src,

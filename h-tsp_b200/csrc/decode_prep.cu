@@ -41,12 +41,29 @@ decode_prep_kernel(const float* __restrict__ emb, const float* __restrict__ Wg,
   }
 }
 
-int launch_decode_prep(const float* blob, int n_layers, const float* emb, const int32_t* src,
+size_t decode_prep_tc_ws_bytes(int Bp, int N) {
+  return align_up((size_t)Bp * N * H * 2 * 2, 256) + 256;   // emb hi/lo
+}
+
+int launch_decode_prep(const void* blobv, int n_layers, const float* emb, const int32_t* src,
                        const int32_t* tgt, int Bp, int N, float* proj, float* qfix, float* c0,
-                       cudaStream_t s) {
+                       bool tensor_cores, void* tc_ws, cudaStream_t s) {
+  const float* blob = (const float*)blobv;
   DecOff d = dec_off(n_layers);
-  int rc = launch_linear_f32(emb, blob + d.wproj, nullptr, nullptr, nullptr, nullptr, false, proj,
-                             Bp * N, PROJ, H, s);
+  int rc;
+  if (tensor_cores) {
+    const size_t M = (size_t)Bp * N;
+    __half* e_hi = (__half*)(((uintptr_t)tc_ws + 255) & ~(uintptr_t)255);
+    __half* e_lo = e_hi + M * H;
+    const __half* hb = blob_halfs(blobv, n_layers);
+    if ((rc = launch_split_f16(emb, e_hi, e_lo, M * H, s))) return rc;
+    rc = launch_linear_tc(e_hi, e_lo, hb + wproj_hi_off_h(n_layers), hb + wproj_lo_off_h(n_layers),
+                          nullptr, nullptr, nullptr, nullptr, false, proj, nullptr, nullptr, (int)M,
+                          PROJ, H, s);
+  } else {
+    rc = launch_linear_f32(emb, blob + d.wproj, nullptr, nullptr, nullptr, nullptr, false, proj,
+                           Bp * N, PROJ, H, s);
+  }
   if (rc) return rc;
   decode_prep_kernel<<<Bp, 128, 0, s>>>(emb, blob + d.wg, blob + d.ws, blob + d.wt, blob + d.bc,
                                         src, tgt, N, qfix, c0);

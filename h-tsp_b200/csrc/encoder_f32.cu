@@ -132,7 +132,8 @@ __global__ void init_proj_kernel(const float2* __restrict__ x, const float* __re
 // the keys (max, then exp/accumulate) with K_h and V_h staged in shared memory; one query per
 // thread.  qkv row layout: [q(128) | k(128) | v(128)].           (utils.py:12-29)
 __global__ void __launch_bounds__(256)
-enc_attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int N) {
+enc_attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out,
+                         __half* __restrict__ ohi, __half* __restrict__ olo, int N) {
   extern __shared__ __align__(16) float sm[];
   float* Ks = sm;
   float* Vs = sm + (size_t)N * DK;
@@ -171,16 +172,45 @@ enc_attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out,
       for (int c = 0; c < DK; ++c) o[c] = fmaf(p, Vs[j * DK + c], o[c]);
     }
     float inv = 1.f / l;
-    float* dst = out + ((size_t)b * N + i) * H + h * DK;
+    const size_t doff = ((size_t)b * N + i) * H + h * DK;
 #pragma unroll
-    for (int c = 0; c < DK; c += 4)
-      *(float4*)(dst + c) = make_float4(o[c] * inv, o[c + 1] * inv, o[c + 2] * inv, o[c + 3] * inv);
+    for (int c = 0; c < DK; c += 4) {
+      const float v0 = o[c] * inv, v1 = o[c + 1] * inv, v2 = o[c + 2] * inv, v3 = o[c + 3] * inv;
+      if (out != nullptr) *(float4*)(out + doff + c) = make_float4(v0, v1, v2, v3);
+      if (ohi != nullptr) {   // fp16 hi/lo split for the tensor-core combine GEMM
+        __half2 h0 = __floats2half2_rn(v0, v1), h1 = __floats2half2_rn(v2, v3);
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        __half2 l0 = __floats2half2_rn(v0 - f0.x, v1 - f0.y), l1 = __floats2half2_rn(v2 - f1.x, v3 - f1.y);
+        *(uint2*)(ohi + doff + c) = make_uint2(*(uint32_t*)&h0, *(uint32_t*)&h1);
+        *(uint2*)(olo + doff + c) = make_uint2(*(uint32_t*)&l0, *(uint32_t*)&l1);
+      }
+    }
   }
 }
 
 size_t encode_f32_ws_floats(int Bp, int N) {
   size_t M = (size_t)Bp * N;
   return M * (size_t)(3 * H + H + H + FF);
+}
+
+int launch_init_proj(const float* blob, const float* x, float* emb, size_t M, cudaStream_t s) {
+  size_t total = M * H;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  init_proj_kernel<<<blocks, 256, 0, s>>>((const float2*)x, blob + kEncInitW, blob + kEncInitB, emb, M);
+  HTSP_CHECK_LAUNCH();
+  return HTSP_OK;
+}
+
+int launch_enc_attention(const float* qkv, float* out, __half* ohi, __half* olo, int Bp, int N,
+                         cudaStream_t s) {
+  const size_t att_smem = (size_t)N * DK * 2 * sizeof(float);
+  if (att_smem > 48 * 1024)
+    HTSP_CHECK_CUDA(cudaFuncSetAttribute(enc_attention_f32_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
+  enc_attention_f32_kernel<<<dim3(NH, Bp), 256, att_smem, s>>>(qkv, out, ohi, olo, N);
+  HTSP_CHECK_LAUNCH();
+  return HTSP_OK;
 }
 
 int launch_encode_f32(const float* blob, int n_layers, const float* x, int Bp, int N, float* emb,
@@ -191,23 +221,16 @@ int launch_encode_f32(const float* blob, int n_layers, const float* x, int Bp, i
   float* h1 = att + M * H;
   float* hid = h1 + M * H;
   {
-    size_t total = M * H;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 32) blocks = 148 * 32;
-    init_proj_kernel<<<blocks, 256, 0, s>>>((const float2*)x, blob + kEncInitW, blob + kEncInitB, emb, M);
-    HTSP_CHECK_LAUNCH();
+    int rc = launch_init_proj(blob, x, emb, M, s);
+    if (rc) return rc;
   }
-  const size_t att_smem = (size_t)N * DK * 2 * sizeof(float);
-  if (att_smem > 48 * 1024)
-    HTSP_CHECK_CUDA(cudaFuncSetAttribute(enc_attention_f32_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
   for (int l = 0; l < n_layers; ++l) {
     EncLayerOff o = enc_layer_off(l);
     int rc;
     rc = launch_linear_f32(emb, blob + o.wqkv, nullptr, nullptr, nullptr, nullptr, false, qkv, (int)M, 3 * H, H, s);
     if (rc) return rc;
-    enc_attention_f32_kernel<<<dim3(NH, Bp), 256, att_smem, s>>>(qkv, att, N);
-    HTSP_CHECK_LAUNCH();
+    rc = launch_enc_attention(qkv, att, nullptr, nullptr, Bp, N, s);
+    if (rc) return rc;
     rc = launch_linear_f32(att, blob + o.wo, blob + o.bo, emb, blob + o.bn1a, blob + o.bn1b, false, h1, (int)M, H, H, s);
     if (rc) return rc;
     rc = launch_linear_f32(h1, blob + o.w1, blob + o.b1, nullptr, nullptr, nullptr, true, hid, (int)M, FF, H, s);

@@ -1,0 +1,347 @@
+// Blackwell-native dense layers for the encoder and the decoder projections (K2, prep):
+//   Y[M,Nout] = epi( X[M,K] * W[Nout,K]^T )      (torch.nn.Linear, rl4cop/models/models.py:22-38,47,
+//                                                  375-402), split-fp16 arithmetic:
+//   X = Xhi + Xlo, W = Whi + Wlo (fp16 each);  acc = Xhi*Whi + Xhi*Wlo + Xlo*Whi  in fp32.
+//
+// One persistent, warp-specialised CTA per SM:
+//   warp 0   : TMA producer  -- cp.async.bulk.tensor.2d (SWIZZLE_128B boxes of 128 rows x 64 halves)
+//              of the four operand tiles per k-block into a 3-stage shared-memory ring
+//   warp 1   : MMA issuer    -- tcgen05.mma.cta_group::1.kind::f16, M=128, N=128, K=16, three MMAs
+//              per k16 step (hi*hi, hi*lo, lo*hi) into one of two TMEM accumulators (128 columns each)
+//   warps 2-5: epilogue      -- tcgen05.ld (32 lanes x 32 columns per warp), bias / ReLU / residual /
+//              eval-BatchNorm affine in registers, stores fp32 and/or the fp16 hi/lo split that the
+//              next layer's TMA reads; overlaps with the next tile's MMAs through the second accumulator.
+// Synchronisation is mbarrier-only (full/empty per stage, tmem_full/tmem_empty per accumulator);
+// tcgen05.commit releases shared-memory stages and publishes accumulators.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace htsp {
+
+constexpr int GT_BM = 128, GT_BN = 128, GT_BK = 64, GT_STAGES = 3;
+constexpr int GT_TILE_BYTES = GT_BM * GT_BK * 2;            // 16 KB, one operand tile
+constexpr int GT_STAGE_BYTES = 4 * GT_TILE_BYTES;           // A_hi, A_lo, B_hi, B_lo
+constexpr int GT_THREADS = 192;
+constexpr uint32_t GT_TMEM_COLS = 256;
+constexpr size_t GT_SMEM_BYTES = (size_t)GT_STAGES * GT_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct GemmEpi {
+  const float* bias;       // [Nout] or null
+  const float* residual;   // [M,Nout] fp32 or null
+  const float* bn_alpha;   // [Nout] or null
+  const float* bn_beta;
+  float* y32;              // [M,Nout] or null
+  __half* yhi;             // [M,Nout] or null (both or neither)
+  __half* ylo;
+  int M, Nout, K, relu;
+};
+
+__device__ __forceinline__ uint32_t gt_smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void gt_mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void gt_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void gt_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU
+__device__ __forceinline__ void gt_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void gt_tma_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+// start>>4 | LBO=0 | SBO = 8 rows * 128 B = 1024 B (>>4) | version 1 | layout SWIZZLE_128B (2)
+__device__ __forceinline__ uint64_t gt_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void gt_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void gt_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void gt_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void gt_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void gt_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(GT_THREADS, 1)
+gemm_x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                  const GemmEpi E) {
+  extern __shared__ unsigned char gt_smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment
+  unsigned char* smem = (unsigned char*)(((uintptr_t)gt_smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + (size_t)GT_STAGES * GT_STAGE_BYTES);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * GT_STAGES + 4);
+  const uint32_t full0 = gt_smem_u32(bars), empty0 = gt_smem_u32(bars + GT_STAGES);
+  const uint32_t tfull0 = gt_smem_u32(bars + 2 * GT_STAGES), tempty0 = gt_smem_u32(bars + 2 * GT_STAGES + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int num_m = (E.M + GT_BM - 1) / GT_BM, num_n = E.Nout / GT_BN;
+  const int num_tiles = num_m * num_n, num_kb = E.K / GT_BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < GT_STAGES; ++s) { gt_mbar_init(full0 + 8 * s, 1); gt_mbar_init(empty0 + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { gt_mbar_init(tfull0 + 8 * a, 1); gt_mbar_init(tempty0 + 8 * a, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM allocation is warp-collective; the same warp frees it
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(gt_smem_u32(tmem_slot)),
+                 "r"(GT_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  gt_fence_before();
+  __syncthreads();
+  gt_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % GT_STAGES, use = it / GT_STAGES;
+          gt_mbar_wait(empty0 + 8 * s, (use & 1) ^ 1);
+          const uint32_t dst = gt_smem_u32(smem + (size_t)s * GT_STAGE_BYTES);
+          gt_mbar_expect_tx(full0 + 8 * s, GT_STAGE_BYTES);
+          gt_tma_2d(dst + 0 * GT_TILE_BYTES, &tmA_hi, kb * GT_BK, m_blk * GT_BM, full0 + 8 * s);
+          gt_tma_2d(dst + 1 * GT_TILE_BYTES, &tmA_lo, kb * GT_BK, m_blk * GT_BM, full0 + 8 * s);
+          gt_tma_2d(dst + 2 * GT_TILE_BYTES, &tmB_hi, kb * GT_BK, n_blk * GT_BN, full0 + 8 * s);
+          gt_tma_2d(dst + 3 * GT_TILE_BYTES, &tmB_lo, kb * GT_BK, n_blk * GT_BN, full0 + 8 * s);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=F32 (bit 4), A=B=F16,
+      // both K-major, N>>3 at bit 17, M>>4 at bit 24
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(GT_BN >> 3) << 17) | ((uint32_t)(GT_BM >> 4) << 24);
+      uint32_t it = 0, local = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        const uint32_t acc = local & 1, acc_use = local >> 1;
+        gt_mbar_wait(tempty0 + 8 * acc, (acc_use & 1) ^ 1);
+        gt_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * GT_BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % GT_STAGES, use = it / GT_STAGES;
+          gt_mbar_wait(full0 + 8 * s, use & 1);
+          gt_fence_after();
+          const uint32_t base = gt_smem_u32(smem + (size_t)s * GT_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < GT_BK / 16; ++k) {
+            const uint64_t a_hi = gt_desc(base + 0 * GT_TILE_BYTES + k * 32);
+            const uint64_t a_lo = gt_desc(base + 1 * GT_TILE_BYTES + k * 32);
+            const uint64_t b_hi = gt_desc(base + 2 * GT_TILE_BYTES + k * 32);
+            const uint64_t b_lo = gt_desc(base + 3 * GT_TILE_BYTES + k * 32);
+            gt_mma(tmem_d, a_hi, b_hi, idesc, (kb | k) != 0);
+            gt_mma(tmem_d, a_hi, b_lo, idesc, 1);
+            gt_mma(tmem_d, a_lo, b_hi, idesc, 1);
+          }
+          gt_commit(empty0 + 8 * s);          // frees the stage once these MMAs have read it
+        }
+        gt_commit(tfull0 + 8 * acc);          // accumulator complete
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;                   // TMEM lane quarter this warp may access
+    uint32_t local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const uint32_t acc = local & 1, acc_use = local >> 1;
+      gt_mbar_wait(tfull0 + 8 * acc, acc_use & 1);
+      gt_fence_after();
+      const int row = m_blk * GT_BM + q * 32 + lane;
+      const bool ok = row < E.M;
+#pragma unroll 1
+      for (int c = 0; c < GT_BN / 32; ++c) {
+        uint32_t r[32];
+        gt_tmem_ld32(tmem_base + acc * GT_BN + c * 32 + ((uint32_t)(q * 32) << 16), r);
+        const int col0 = n_blk * GT_BN + c * 32;
+        if (ok) {
+          const size_t off = (size_t)row * E.Nout + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float v[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                          __uint_as_float(r[j + 3])};
+            if (E.bias != nullptr) {
+              const float4 b = __ldg((const float4*)(E.bias + col0 + j));
+              v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+            }
+            if (E.relu) {
+#pragma unroll
+              for (int t = 0; t < 4; ++t) v[t] = fmaxf(v[t], 0.f);
+            }
+            if (E.residual != nullptr) {
+              const float4 x = __ldg((const float4*)(E.residual + off + j));
+              v[0] = x.x + v[0]; v[1] = x.y + v[1]; v[2] = x.z + v[2]; v[3] = x.w + v[3];
+            }
+            if (E.bn_alpha != nullptr) {
+              const float4 al = __ldg((const float4*)(E.bn_alpha + col0 + j));
+              const float4 be = __ldg((const float4*)(E.bn_beta + col0 + j));
+              v[0] = fmaf(v[0], al.x, be.x); v[1] = fmaf(v[1], al.y, be.y);
+              v[2] = fmaf(v[2], al.z, be.z); v[3] = fmaf(v[3], al.w, be.w);
+            }
+            if (E.y32 != nullptr) *(float4*)(E.y32 + off + j) = make_float4(v[0], v[1], v[2], v[3]);
+            if (E.yhi != nullptr) {
+              __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+              const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+              __half2 l0 = __floats2half2_rn(v[0] - f0.x, v[1] - f0.y);
+              __half2 l1 = __floats2half2_rn(v[2] - f1.x, v[3] - f1.y);
+              *(uint2*)(E.yhi + off + j) = make_uint2(*(uint32_t*)&h0, *(uint32_t*)&h1);
+              *(uint2*)(E.ylo + off + j) = make_uint2(*(uint32_t*)&l0, *(uint32_t*)&l1);
+            }
+          }
+        }
+      }
+      gt_fence_before();
+      __syncwarp();
+      if (lane == 0) gt_mbar_arrive(tempty0 + 8 * acc);
+    }
+  }
+  gt_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    gt_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(GT_TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// fp32 -> fp16 hi/lo split (x = hi + lo), used where a producer kernel only writes fp32
+__global__ void split_f16_kernel(const float* __restrict__ x, __half* __restrict__ hi,
+                                 __half* __restrict__ lo, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg((const float4*)x + i);
+    __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+    ((uint2*)hi)[i] = make_uint2(*(uint32_t*)&h0, *(uint32_t*)&h1);
+    ((uint2*)lo)[i] = make_uint2(*(uint32_t*)&l0, *(uint32_t*)&l1);
+  }
+}
+
+int launch_split_f16(const float* x, __half* hi, __half* lo, size_t n, cudaStream_t s) {
+  HTSP_REQUIRE(n % 4 == 0, "split size");
+  const size_t n4 = n / 4;
+  int blocks = (int)((n4 + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  split_f16_kernel<<<blocks, 256, 0, s>>>(x, hi, lo, n4);
+  HTSP_CHECK_LAUNCH();
+  return HTSP_OK;
+}
+
+// ---- host: tensor maps -------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// row-major fp16 matrix [rows, K] -> boxes of 128 rows x 64 halves (128 B), SWIZZLE_128B
+static int make_map(CUtensorMap* m, const __half* ptr, int rows, int K) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return HTSP_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)GT_BK, (cuuint32_t)GT_BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)ptr, gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%d K=%d", (int)r, rows, K);
+    return HTSP_ERR_CUDA;
+  }
+  return HTSP_OK;
+}
+
+int launch_linear_tc(const __half* xhi, const __half* xlo, const __half* whi, const __half* wlo,
+                     const float* bias, const float* residual, const float* bn_alpha,
+                     const float* bn_beta, bool relu, float* y32, __half* yhi, __half* ylo, int M,
+                     int Nout, int K, cudaStream_t s) {
+  HTSP_REQUIRE(M > 0 && Nout % GT_BN == 0 && K % GT_BK == 0, "linear_tc shape");
+  HTSP_REQUIRE((yhi == nullptr) == (ylo == nullptr), "hi/lo outputs come in pairs");
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int rc;
+  if ((rc = make_map(&ma_hi, xhi, M, K))) return rc;
+  if ((rc = make_map(&ma_lo, xlo, M, K))) return rc;
+  if ((rc = make_map(&mb_hi, whi, Nout, K))) return rc;
+  if ((rc = make_map(&mb_lo, wlo, Nout, K))) return rc;
+  GemmEpi e;
+  e.bias = bias; e.residual = residual; e.bn_alpha = bn_alpha; e.bn_beta = bn_beta;
+  e.y32 = y32; e.yhi = yhi; e.ylo = ylo; e.M = M; e.Nout = Nout; e.K = K; e.relu = relu ? 1 : 0;
+  HTSP_CHECK_CUDA(cudaFuncSetAttribute(gemm_x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)GT_SMEM_BYTES));
+  const int tiles = ((M + GT_BM - 1) / GT_BM) * (Nout / GT_BN);
+  const int grid = tiles < 148 ? tiles : 148;
+  gemm_x3_tc_kernel<<<grid, GT_THREADS, GT_SMEM_BYTES, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, e);
+  HTSP_CHECK_LAUNCH();
+  return HTSP_OK;
+}
+
+}  // namespace htsp

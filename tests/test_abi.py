@@ -34,8 +34,12 @@ def test_python_binding_covers_the_header(built_lib):
     assert sorted(_abi.SIGNATURES) == _declared_symbols()
     lib = _abi.lib()
     assert lib.htsp_n_weight_tensors(6) == 2 + 17 * 6 + 9
-    # packed blob = all reference parameters (BN folded 4->2 vectors) + the transposed combine
-    assert lib.htsp_weights_blob_bytes(6) == (1318912 + 128 * 128) * 4
+    # packed blob = fp32 section (all reference parameters, BN folded 4->2 vectors, + the transposed
+    # combine) followed by fp16 hi/lo copies of every GEMM weight for the tensor-core layers
+    fp32_bytes = (1318912 + 128 * 128) * 4
+    gemm_weights = 6 * (3 * 128 * 128 + 128 * 128 + 2 * 512 * 128) + 640 * 128
+    assert fp32_bytes % 256 == 0
+    assert lib.htsp_weights_blob_bytes(6) == fp32_bytes + 2 * 2 * gemm_weights
 
 
 def test_library_contains_sm100a_code_only(built_lib):
