@@ -139,6 +139,9 @@ int launch_encode_tc(const void* blob, int n_layers, const float* x, int Bp, int
 int launch_init_proj(const float* blob, const float* x, float* emb, size_t M, cudaStream_t s);
 int launch_enc_attention(const float* qkv, float* out, __half* ohi, __half* olo, int Bp, int N,
                          cudaStream_t s);
+// enc_attention_mma.cu
+int launch_enc_attention_mma(const __half* qkv_hi, const __half* qkv_lo, __half* out_hi, __half* out_lo,
+                             int Bp, int N, cudaStream_t s);
 // decode_prep.cu
 size_t decode_prep_tc_ws_bytes(int Bp, int N);
 int launch_decode_prep(const void* blob, int n_layers, const float* emb, const int32_t* src,

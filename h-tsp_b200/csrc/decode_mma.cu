@@ -18,6 +18,7 @@
 // a shared-memory ring by one producer warp with cp.async.bulk (TMA bulk copy, SASS UBLKCP) +
 // mbarrier full/empty pairs; consumers read them with ldmatrix.  Nothing else is staged.
 #include "common.cuh"
+#include "mma_util.cuh"
 
 namespace htsp {
 
@@ -32,8 +33,6 @@ namespace htsp {
 #endif
 constexpr int MM_STAGES = HTSP_MMA_STAGES;
 constexpr int MM_KT = 48;            // keys per K2 tile (multiple of 16)
-constexpr float kScoreScale = 0.25f * 1.4426950408889634f;   // 1/sqrt(dk) * log2(e)
-constexpr float kLazy = 6.0f;                                 // lazy-rescale threshold (log2 units)
 constexpr float kInvSqrtH = 0.08838834764831845f;            // 1/sqrt(128)
 
 // image layout per instance (bytes): 8 KV tiles of 128*NP, then K2 tiles of 512*rows_t
@@ -99,89 +98,6 @@ decode_pack_kernel(const float* __restrict__ proj, int Bp, int N, int NP,
       *(uint4*)(tile + (size_t)rows_t * 256 + off) = lo;
     }
   }
-}
-
-// ------------------------------------------------------------------------------------------
-// PTX helpers
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-      "l"(src), "r"(bytes), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
-                                        uint32_t& r3) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-               : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
-                                          uint32_t& r3) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-               : "r"(addr));
-}
-__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
-                                         uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
-      "{%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
-  __half2 h = __floats2half2_rn(x, y);
-  float2 f = __half22float2(h);
-  __half2 l = __floats2half2_rn(x - f.x, y - f.y);
-  hi = *reinterpret_cast<uint32_t*>(&h);
-  lo = *reinterpret_cast<uint32_t*>(&l);
-}
-__device__ __forceinline__ float ex2_approx(float x) {   // 2^x, rel. error 2^-22, -inf -> +0
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// 10*tanh(u) = 10 - 20/(2^(2u*log2e)+1): MUFU.EX2 + MUFU.RCP, abs. error < 4e-6 on the logit
-__device__ __forceinline__ float clip_tanh10(float u) {
-  const float e = ex2_approx(u * 2.8853900817779268f);
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
-  return fmaf(-20.0f, r, 10.0f);
-}
-__device__ __forceinline__ float quad_max(float v) {
-  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
-  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
-}
-__device__ __forceinline__ float quad_sum(float v) {
-  v += __shfl_xor_sync(0xffffffffu, v, 1);
-  return v + __shfl_xor_sync(0xffffffffu, v, 2);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -361,34 +277,32 @@ __global__ void __launch_bounds__((NWARPS + 1) * 32, 1) decode_mma_kernel(const 
       float o0l[4] = {0.f, 0.f, 0.f, 0.f}, o1l[4] = {0.f, 0.f, 0.f, 0.f};
       // shift starts at a finite floor so (-inf) - m never produces NaN; any real score lifts it
       float mA = -1e30f, mB = -1e30f, lA = 0.f, lB = 0.f;
-#pragma unroll
-      for (int kc = 0; kc < NCHUNK; ++kc) {
-        // ---- S = Q K^T for 16 keys (two n8 tiles)
+      // S = Q K^T for the 16 keys of chunk kc (two n8 tiles); software-pipelined: the MMAs of chunk
+      // kc+1 are issued before the softmax of chunk kc so the tensor pipe overlaps the ALU/MUFU work
+      auto qk_chunk = [&](int kc, float (&s0)[4], float (&s1)[4]) {
         const int keyK = kc * 16 + (mi >> 1) * 8 + l7;
         const uint32_t offK = keyK * 32 + (((mi & 1) ^ ((keyK >> 2) & 1)) * 16);
         uint32_t bh0, bh1, bh2, bh3;
         ldsm_x4(khi + offK, bh0, bh1, bh2, bh3);
-        float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+        s0[0] = s0[1] = s0[2] = s0[3] = 0.f;
+        s1[0] = s1[1] = s1[2] = s1[3] = 0.f;
         mma16816(s0, qh, bh0, bh1);
         mma16816(s1, qh, bh2, bh3);
         if (!A.fast) {
           uint32_t bl0, bl1, bl2, bl3;
           ldsm_x4(klo + offK, bl0, bl1, bl2, bl3);
-#if HTSP_MMA_SPLIT_ACC
-          float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
-          mma16816(c0, qh, bl0, bl1);
-          mma16816(c1, qh, bl2, bl3);
-          mma16816(c0, ql, bh0, bh1);
-          mma16816(c1, ql, bh2, bh3);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) { s0[e] += c0[e]; s1[e] += c1[e]; }
-#else
           mma16816(s0, qh, bl0, bl1);
           mma16816(s1, qh, bl2, bl3);
           mma16816(s0, ql, bh0, bh1);
           mma16816(s1, ql, bh2, bh3);
-#endif
         }
+      };
+      float sn0[4], sn1[4];
+      qk_chunk(0, sn0, sn1);
+#pragma unroll
+      for (int kc = 0; kc < NCHUNK; ++kc) {
+        float s0[4] = {sn0[0], sn0[1], sn0[2], sn0[3]}, s1[4] = {sn1[0], sn1[1], sn1[2], sn1[3]};
+        if (kc + 1 < NCHUNK) qk_chunk(kc + 1, sn0, sn1);
         // ---- mask + online softmax (utils.py:20-27), exponent base 2
         const int key0 = kc * 16 + 2 * q4;                 // keys key0,key0+1 (tile 0), +8,+9 (tile 1)
         const unsigned wA = visA[key0 >> 5] >> (key0 & 31);

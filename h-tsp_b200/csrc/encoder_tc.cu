@@ -1,7 +1,7 @@
 // K2 (tensor-core variant): MHAEncoder.forward (rl4cop/models/models.py:30-60) with every Linear on
 // tcgen05 (gemm_tc.cu, split-fp16 x3) and the bias / ReLU / residual / eval-BatchNorm epilogues fused.
 // Activations travel between layers as fp32 (residual stream) plus the fp16 hi/lo split the next
-// GEMM's TMA loads consume.  The [N x N] self-attention itself still runs in the fp32 kernel.
+// GEMM's TMA loads consume.  The [N x N] self-attention runs on mma.sync tensor cores (enc_attention_mma.cu) for N <= 208.
 #include "common.cuh"
 
 namespace htsp {
@@ -21,7 +21,9 @@ int launch_encode_tc(const void* blob, int n_layers, const float* x, int Bp, int
   char* w = (char*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
   __half* h_hi = (__half*)w;   w += M * H * 2;
   __half* h_lo = (__half*)w;   w += M * H * 2;
-  float* qkv = (float*)w;      w += M * 3 * H * 4;
+  float* qkv = (float*)w;      w += M * 3 * H * 4;   // fp32 [M,384] or, aliased, fp16 hi | lo [M,384] each
+  __half* q_hi = (__half*)qkv;
+  __half* q_lo = q_hi + M * 3 * H;
   __half* a_hi = (__half*)w;   w += M * H * 2;
   __half* a_lo = (__half*)w;   w += M * H * 2;
   float* h1 = (float*)w;       w += M * H * 4;
@@ -36,10 +38,16 @@ int launch_encode_tc(const void* blob, int n_layers, const float* x, int Bp, int
     const EncLayerOff o = enc_layer_off(l);
     const EncLayerOffH oh = enc_layer_off_h(l);
     // q,k,v projections (models.py:31-33), no bias
+    const bool tc_att = N <= 208;     // tensor-core attention kernel stages one head's K/V tile
     if ((rc = launch_linear_tc(h_hi, h_lo, hb + oh.wqkv_hi, hb + oh.wqkv_lo, nullptr, nullptr, nullptr,
-                               nullptr, false, qkv, nullptr, nullptr, (int)M, 3 * H, H, s))) return rc;
+                               nullptr, false, tc_att ? nullptr : qkv, tc_att ? q_hi : nullptr,
+                               tc_att ? q_lo : nullptr, (int)M, 3 * H, H, s))) return rc;
     // softmax(q k^T / 4) v  (utils.py:12-29)
-    if ((rc = launch_enc_attention(qkv, nullptr, a_hi, a_lo, Bp, N, s))) return rc;
+    if (tc_att) {
+      if ((rc = launch_enc_attention_mma(q_hi, q_lo, a_hi, a_lo, Bp, N, s))) return rc;
+    } else {
+      if ((rc = launch_enc_attention(qkv, nullptr, a_hi, a_lo, Bp, N, s))) return rc;
+    }
     // x = norm1(x + combine(attn))  (models.py:34-35)
     if ((rc = launch_linear_tc(a_hi, a_lo, hb + oh.wo_hi, hb + oh.wo_lo, fb + o.bo, emb, fb + o.bn1a,
                                fb + o.bn1b, false, h1, h1_hi, h1_lo, (int)M, H, H, s))) return rc;
