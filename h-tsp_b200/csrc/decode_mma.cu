@@ -38,8 +38,11 @@ constexpr float kInvSqrtH = 0.08838834764831845f;            // 1/sqrt(128)
 // image layout per instance (bytes): 8 KV tiles of 128*NP, then K2 tiles of 512*rows_t
 __host__ __device__ inline size_t img_bytes(int NP) { return (size_t)1536 * NP; }
 __host__ __device__ inline int n_k2_tiles(int NP) { return (NP + MM_KT - 1) / MM_KT; }
+// keys per K/V tile: the whole (padded) key range while it fits one stage, else 128-key slices
+__host__ __device__ inline int kv_tile_keys(int NP) { return NP <= 208 ? NP : 128; }
+__host__ __device__ inline int n_kv_tiles(int NP) { return (NP + kv_tile_keys(NP) - 1) / kv_tile_keys(NP); }
 __host__ __device__ inline int stage_bytes(int NP) {
-  int a = 128 * NP, b = 512 * MM_KT;
+  int a = 128 * kv_tile_keys(NP), b = 512 * MM_KT;
   return a > b ? a : b;
 }
 
@@ -84,11 +87,13 @@ decode_pack_kernel(const float* __restrict__ proj, int Bp, int N, int NP,
     unsigned char* base = img + (size_t)b * img_bytes(NP);
     if (m < 2) {
       const int h = c16 >> 1, chunk = c16 & 1;
-      unsigned char* tile = base + (size_t)h * 128 * NP;
-      const int off = r * 32 + ((chunk ^ ((r >> 2) & 1)) * 16);
-      // tile = [K hi | K lo | V hi | V lo], each NP*32 bytes
-      *(uint4*)(tile + (size_t)(2 * m) * NP * 32 + off) = hi;
-      *(uint4*)(tile + (size_t)(2 * m + 1) * NP * 32 + off) = lo;
+      const int T = kv_tile_keys(NP), j = r / T, rl = r - j * T;
+      const int rows_t = min(T, NP - j * T);
+      // head h, key slice j: tile = [K hi | K lo | V hi | V lo], each rows_t*32 bytes
+      unsigned char* tile = base + (size_t)h * 128 * NP + (size_t)j * 128 * T;
+      const int off = rl * 32 + ((chunk ^ ((rl >> 2) & 1)) * 16);
+      *(uint4*)(tile + (size_t)(2 * m) * rows_t * 32 + off) = hi;
+      *(uint4*)(tile + (size_t)(2 * m + 1) * rows_t * 32 + off) = lo;
     } else {
       const int t = r / MM_KT, rl = r - t * MM_KT;
       const int rows_t = min(MM_KT, NP - t * MM_KT);
@@ -125,7 +130,6 @@ __global__ void __launch_bounds__((NWARPS + 1) * 32, 1) decode_mma_kernel(const 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y;
   const int N = A.N, NP = A.NP, G = A.G;
-  const int NCHUNK = NCHUNK_T > 0 ? NCHUNK_T : NP / 16;
   const int g0 = blockIdx.x * A.rows_per_cta;
   const int rows_here = min(A.rows_per_cta, G - g0);
   const int active_warps = (rows_here + 15) / 16;
@@ -133,7 +137,10 @@ __global__ void __launch_bounds__((NWARPS + 1) * 32, 1) decode_mma_kernel(const 
   const int VSTRIDE = NWORDS | 1;       // odd stride: the 8 rows of a warp quarter hit distinct banks
   const int STAGE = stage_bytes(NP);
   const int NT2 = n_k2_tiles(NP);
-  const int tiles_per_step = NH + NT2;
+  // the NCHUNK_T > 0 instantiation is the single-slice case (NP = 16*NCHUNK_T <= 208)
+  const int KVT = NCHUNK_T > 0 ? NCHUNK_T * 16 : kv_tile_keys(NP);
+  const int NKV = NCHUNK_T > 0 ? 1 : n_kv_tiles(NP);
+  const int tiles_per_step = NH * NKV + NT2;
 
   // shared memory carve-up
   unsigned char* ring = smem;                                           // MM_STAGES * STAGE
@@ -183,11 +190,12 @@ __global__ void __launch_bounds__((NWARPS + 1) * 32, 1) decode_mma_kernel(const 
           mbar_wait(empty0 + 8 * s, (use & 1) ^ 1);
           const unsigned char* srcp;
           uint32_t bytes;
-          if (t < NH) {
-            srcp = imgb + (size_t)t * 128 * NP;
-            bytes = 128 * NP;
+          if (t < NH * NKV) {
+            const int hh = t / NKV, j = t - hh * NKV;
+            srcp = imgb + (size_t)hh * 128 * NP + (size_t)j * 128 * KVT;
+            bytes = 128 * min(KVT, NP - j * KVT);
           } else {
-            const int k2 = t - NH;
+            const int k2 = t - NH * NKV;
             srcp = imgb + (size_t)8 * 128 * NP + (size_t)k2 * 512 * MM_KT;
             bytes = 512 * min(MM_KT, NP - k2 * MM_KT);
           }
@@ -253,7 +261,7 @@ __global__ void __launch_bounds__((NWARPS + 1) * 32, 1) decode_mma_kernel(const 
     fetch_q(0);
     // ------------------------------------------------------------ glimpse, one head at a time
 #pragma unroll 1
-    for (int h = 0; h < NH; ++h, ++it) {
+    for (int h = 0; h < NH; ++h) {
       // q = ((q_graph+q_source+q_target) + q_first) + q_last  (models.py:413); 1/sqrt(dk)*log2(e) is
       // folded in so the MMA result is the base-2 exponent directly.  A fragments hi/lo.
       uint32_t qh[4], ql[4];
@@ -266,17 +274,20 @@ __global__ void __launch_bounds__((NWARPS + 1) * 32, 1) decode_mma_kernel(const 
         split2(((x1.x + pf[3].x) + pf[7].x) * kScoreScale, ((x1.y + pf[3].y) + pf[7].y) * kScoreScale, qh[3], ql[3]);
       }
       if (h + 1 < NH) fetch_q(h + 1);
-      const uint32_t s = it % MM_STAGES, use = it / MM_STAGES;
-      mbar_wait(full0 + 8 * s, use & 1);
-      const uint32_t tile = smem_u32(ring + (size_t)s * STAGE);
-      const uint32_t khi = tile, klo = tile + NP * 32, vhi = tile + 2 * NP * 32, vlo = tile + 3 * NP * 32;
-
       // hi*hi and (hi*lo + lo*hi) are accumulated separately: independent MMA chains (ILP) and the
       // small cross terms do not get absorbed into the large sum
       float o0h[4] = {0.f, 0.f, 0.f, 0.f}, o1h[4] = {0.f, 0.f, 0.f, 0.f};
       float o0l[4] = {0.f, 0.f, 0.f, 0.f}, o1l[4] = {0.f, 0.f, 0.f, 0.f};
       // shift starts at a finite floor so (-inf) - m never produces NaN; any real score lifts it
       float mA = -1e30f, mB = -1e30f, lA = 0.f, lB = 0.f;
+#pragma unroll 1
+      for (int jt = 0; jt < NKV; ++jt, ++it) {   // key slices of this head (one slice when NP <= 208)
+      const uint32_t s = it % MM_STAGES, use = it / MM_STAGES;
+      mbar_wait(full0 + 8 * s, use & 1);
+      const int rows_t = NCHUNK_T > 0 ? NCHUNK_T * 16 : min(KVT, NP - jt * KVT), kbase = jt * KVT;
+      const int nchunk = NCHUNK_T > 0 ? NCHUNK_T : rows_t / 16;
+      const uint32_t tile = smem_u32(ring + (size_t)s * STAGE);
+      const uint32_t khi = tile, klo = tile + rows_t * 32, vhi = tile + 2 * rows_t * 32, vlo = tile + 3 * rows_t * 32;
       // S = Q K^T for the 16 keys of chunk kc (two n8 tiles); software-pipelined: the MMAs of chunk
       // kc+1 are issued before the softmax of chunk kc so the tensor pipe overlaps the ALU/MUFU work
       auto qk_chunk = [&](int kc, float (&s0)[4], float (&s1)[4]) {
@@ -300,11 +311,11 @@ __global__ void __launch_bounds__((NWARPS + 1) * 32, 1) decode_mma_kernel(const 
       float sn0[4], sn1[4];
       qk_chunk(0, sn0, sn1);
 #pragma unroll
-      for (int kc = 0; kc < NCHUNK; ++kc) {
+      for (int kc = 0; kc < nchunk; ++kc) {
         float s0[4] = {sn0[0], sn0[1], sn0[2], sn0[3]}, s1[4] = {sn1[0], sn1[1], sn1[2], sn1[3]};
-        if (kc + 1 < NCHUNK) qk_chunk(kc + 1, sn0, sn1);
+        if (kc + 1 < nchunk) qk_chunk(kc + 1, sn0, sn1);
         // ---- mask + online softmax (utils.py:20-27), exponent base 2
-        const int key0 = kc * 16 + 2 * q4;                 // keys key0,key0+1 (tile 0), +8,+9 (tile 1)
+        const int key0 = kbase + kc * 16 + 2 * q4;         // keys key0,key0+1 (tile 0), +8,+9 (tile 1)
         const unsigned wA = visA[key0 >> 5] >> (key0 & 31);
         const unsigned wB = visB[key0 >> 5] >> (key0 & 31);
         float t0 = (wA & 1u) ? -INFINITY : s0[0];
@@ -366,6 +377,7 @@ __global__ void __launch_bounds__((NWARPS + 1) * 32, 1) decode_mma_kernel(const 
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty0 + 8 * s);
+      }   // key slices
       const float iA = 1.f / quad_sum(lA), iB = 1.f / quad_sum(lB);
       uint4 fh, fl;
       split2((o0h[0] + o0l[0]) * iA, (o0h[1] + o0l[1]) * iA, fh.x, fl.x);

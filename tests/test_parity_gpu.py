@@ -55,7 +55,7 @@ def test_extract_normalize_bit_exact(built_lib, B, Ntot, N):
 
 # ---------------------------------------------------------------- K2 encoder
 @pytest.mark.parametrize("mode", MODES)
-@pytest.mark.parametrize("Bp,N", [(1, 200), (3, 50), (9, 137)])
+@pytest.mark.parametrize("Bp,N", [(1, 200), (3, 50), (9, 137), (2, 500)])
 def test_encoder_matches_oracle(solvers, sd6, mode, Bp, N):
     g = torch.Generator().manual_seed(Bp * 100 + N)
     x = torch.rand(Bp, N, 2, generator=g)
@@ -99,7 +99,8 @@ def test_teacher_forced_logits_match_golden_n200(solvers, golden, mode):
 
 
 @pytest.mark.parametrize("mode", MODES)
-@pytest.mark.parametrize("Bp,N,G", [(2, 20, 20), (3, 50, 7), (1, 200, 33), (2, 100, 100)])
+@pytest.mark.parametrize("Bp,N,G", [(2, 20, 20), (3, 50, 7), (1, 200, 33), (2, 100, 100), (1, 500, 12),
+                                    (1, 230, 230)])
 def test_teacher_forced_logits_match_oracle(solvers, sd6, mode, Bp, N, G):
     s = solvers[mode]
     g = torch.Generator().manual_seed(N + G)
@@ -123,7 +124,7 @@ def test_teacher_forced_logits_match_oracle(solvers, sd6, mode, Bp, N, G):
 
 # ---------------------------------------------------------------- K3 decode: free-running greedy
 @pytest.mark.parametrize("mode", MODES)
-@pytest.mark.parametrize("Bp,N,G", [(4, 50, 50), (2, 200, 16), (16, 30, 5)])
+@pytest.mark.parametrize("Bp,N,G", [(4, 50, 50), (2, 200, 16), (16, 30, 5), (1, 500, 20)])
 def test_greedy_rollout_is_tie_aware_identical(solvers, sd6, mode, Bp, N, G):
     s = solvers[mode]
     g = torch.Generator().manual_seed(1000 + N)
@@ -142,8 +143,8 @@ def test_greedy_rollout_is_tie_aware_identical(solvers, sd6, mode, Bp, N, G):
         free = po.rollout(sd6, x, src, tgt, first)
     same = (free.pi == pi).all(dim=2).float().mean().item()
     print(f"[{mode}] rows identical to the oracle's free run: {same:.3f}; worst regret {worst:.2e}")
-    if mode == "fp32":
-        assert same >= 0.9
+    if mode == "fp32":      # longer rollouts meet more near-ties (each bounded by the regret check above)
+        assert same >= (0.9 if N <= 200 else 0.5)
     # reward of the tours actually produced, recomputed by the oracle: 1e-5 relative
     assert rel_err(reward, forced.reward) <= 1e-5
 
