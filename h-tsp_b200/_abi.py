@@ -29,6 +29,9 @@ SIGNATURES = {
     "htsp_decode_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "htsp_decode": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp,
                          _vp, _sz, _vp]),
+    "htsp_decode_debug_floats": (_sz, [_i]),
+    "htsp_decode_debug": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp,
+                               _vp, _sz, _vp, _i, _vp]),
     "htsp_select_best": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "htsp_finalize_paths": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "htsp_tour_length": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),

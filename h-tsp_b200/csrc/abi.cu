@@ -2,7 +2,9 @@
 // library bookkeeping, weight packing, encode and decode dispatch.  See include/htsp_b200.h.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <atomic>
 #include <vector>
 #include "common.cuh"
@@ -150,19 +152,31 @@ static size_t dec_proj_bytes(int Bp, int N) { return align_up((size_t)Bp * N * P
 static size_t dec_qfix_bytes(int Bp) { return align_up((size_t)Bp * H * 4, 256); }
 static size_t dec_c0_bytes(int Bp, int N) { return align_up((size_t)Bp * N * 4, 256); }
 
+static size_t dec_pack_bytes(int Bp, int N, int G) {
+  size_t a = decode_mma_pack_bytes(Bp, N);
+  if (decode_tc_supported(N, G)) a = std::max(a, decode_tc_pack_bytes(Bp, N));
+  return a;
+}
+// HTSP_DECODE_IMPL=mma forces the mma.sync rollout kernel (A/B comparisons); default is tcgen05 when it fits
+static bool use_tc_kernel(int N, int G) {
+  const char* e = getenv("HTSP_DECODE_IMPL");
+  if (e != nullptr && strcmp(e, "mma") == 0) return false;
+  return decode_tc_supported(N, G);
+}
+
 extern "C" size_t htsp_decode_workspace_bytes(int Bp, int N, int G, int mode) {
   (void)G;
   if (Bp <= 0 || N <= 0) return 0;
   size_t b = dec_proj_bytes(Bp, N) + dec_qfix_bytes(Bp) + dec_c0_bytes(Bp, N);
-  if (mode != HTSP_MODE_FP32) b += decode_mma_pack_bytes(Bp, N) + decode_prep_tc_ws_bytes(Bp, N);
+  if (mode != HTSP_MODE_FP32) b += dec_pack_bytes(Bp, N, G) + decode_prep_tc_ws_bytes(Bp, N);
   return b;
 }
 
-extern "C" int htsp_decode(const void* blob, int n_layers, const float* x, const float* emb,
-                           const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp,
-                           int N, int G, int mode, const int32_t* forced_pi, int32_t* pi,
-                           float* reward, float* logits_out, void* workspace,
-                           size_t workspace_bytes, void* stream) {
+static int decode_impl(const void* blob, int n_layers, const float* x, const float* emb,
+                       const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp,
+                       int N, int G, int mode, const int32_t* forced_pi, int32_t* pi,
+                       float* reward, float* logits_out, void* workspace,
+                       size_t workspace_bytes, float* dbg, int dbg_step, void* stream) {
   HTSP_REQUIRE(blob && x && emb && src && tgt && first && pi && reward, "null pointer");
   HTSP_REQUIRE(Bp >= 0 && N >= 3 && G >= 1 && G <= N && n_layers >= 0, "bad shape");
   HTSP_REQUIRE(mode >= HTSP_MODE_FP32 && mode <= HTSP_MODE_TC_FAST, "bad mode");
@@ -179,12 +193,36 @@ extern "C" int htsp_decode(const void* blob, int n_layers, const float* x, const
   float* c0 = (float*)w;   w += dec_c0_bytes(Bp, N);
   const bool tc = mode != HTSP_MODE_FP32;
   void* pack_ws = w;
-  void* prep_ws = tc ? (void*)(w + decode_mma_pack_bytes(Bp, N)) : nullptr;
+  void* prep_ws = tc ? (void*)(w + dec_pack_bytes(Bp, N, G)) : nullptr;
   int rc = launch_decode_prep(blob, n_layers, emb, src, tgt, Bp, N, proj, qfix, c0, tc, prep_ws, s);
   if (rc) return rc;
   if (mode == HTSP_MODE_FP32)
     return launch_decode_f32((const float*)blob, n_layers, x, emb, proj, qfix, src, tgt, first, Bp,
                              N, G, forced_pi, pi, reward, logits_out, s);
+  if (use_tc_kernel(N, G))
+    return launch_decode_tc(x, proj, qfix, c0, src, tgt, first, Bp, N, G, mode, forced_pi, pi, reward,
+                            logits_out, pack_ws, dbg, dbg_step, s);
+  HTSP_REQUIRE(dbg == nullptr, "debug dump needs the tcgen05 kernel");
   return launch_decode_mma(x, proj, qfix, c0, src, tgt, first, Bp, N, G, mode, forced_pi, pi, reward,
                            logits_out, pack_ws, s);
+}
+
+extern "C" int htsp_decode(const void* blob, int n_layers, const float* x, const float* emb,
+                           const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp,
+                           int N, int G, int mode, const int32_t* forced_pi, int32_t* pi,
+                           float* reward, float* logits_out, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  return decode_impl(blob, n_layers, x, emb, src, tgt, first, Bp, N, G, mode, forced_pi, pi, reward,
+                     logits_out, workspace, workspace_bytes, nullptr, 0, stream);
+}
+
+extern "C" size_t htsp_decode_debug_floats(int N) { return decode_tc_dbg_floats(N); }
+extern "C" int htsp_decode_debug(const void* blob, int n_layers, const float* x, const float* emb,
+                                 const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp,
+                                 int N, int G, int mode, const int32_t* forced_pi, int32_t* pi,
+                                 float* reward, void* workspace, size_t workspace_bytes, float* dbg,
+                                 int dbg_step, void* stream) {
+  HTSP_REQUIRE(dbg != nullptr && mode != HTSP_MODE_FP32, "debug dump: tensor-core modes only");
+  return decode_impl(blob, n_layers, x, emb, src, tgt, first, Bp, N, G, mode, forced_pi, pi, reward,
+                     nullptr, workspace, workspace_bytes, dbg, dbg_step, stream);
 }

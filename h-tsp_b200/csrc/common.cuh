@@ -160,4 +160,13 @@ int launch_decode_mma(const float* x, const float* proj, const float* qfix, cons
                       int G, int mode, const int32_t* forced_pi, int32_t* pi, float* reward,
                       float* logits_out, void* pack_ws, cudaStream_t s);
 
+// decode_tc.cu (tcgen05 + TMEM rollout kernel, N <= 224)
+bool decode_tc_supported(int N, int G);
+size_t decode_tc_pack_bytes(int Bp, int N);
+size_t decode_tc_dbg_floats(int N);
+int launch_decode_tc(const float* x, const float* proj, const float* qfix, const float* c0,
+                     const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp, int N,
+                     int G, int mode, const int32_t* forced_pi, int32_t* pi, float* reward,
+                     float* logits_out, void* pack_ws, float* dbg, int dbg_step, cudaStream_t s);
+
 }  // namespace htsp

@@ -172,6 +172,40 @@ class B200PathSolver(torch.nn.Module):
                                        self._stream()), "htsp_decode")
         return pi, reward, logits
 
+    def rollout_debug(self, x, emb, src, tgt, first, forced_pi, dbg_step: int):
+        """Test hook (htsp_decode_debug): teacher-forced rollout on the tcgen05 kernel that also
+        returns the raw S [2,8,128,NP], normalised O [256,128] and raw U [256,NP] of instance 0
+        at decode step `dbg_step`."""
+        lib = _abi.lib()
+        Bp, N, _ = x.shape
+        G = first.numel()
+        dev = self.device
+        mode = _abi.MODES[self.mode]
+        src = src.reshape(-1).to(dev, torch.int32).contiguous()
+        tgt = tgt.reshape(-1).to(dev, torch.int32).contiguous()
+        first = first.reshape(-1).to(dev, torch.int32).contiguous()
+        if forced_pi is not None:
+            forced_pi = forced_pi.to(dev, torch.int32).contiguous()
+        pi = torch.empty(Bp, G, N, dtype=torch.int32, device=dev)
+        reward = torch.empty(Bp, G, dtype=torch.float32, device=dev)
+        NP = (N + 15) // 16 * 16
+        dbg = torch.zeros(lib.htsp_decode_debug_floats(N), dtype=torch.float32, device=dev)
+        nbytes = lib.htsp_decode_workspace_bytes(Bp, N, G, mode)
+        ws = self._ws.get("dec", nbytes, dev)
+        with torch.cuda.device(dev):
+            _abi.check(lib.htsp_decode_debug(self._packed_weights().data_ptr(), self.cfg.n_layers,
+                                             x.data_ptr(), emb.data_ptr(), src.data_ptr(),
+                                             tgt.data_ptr(), first.data_ptr(), Bp, N, G, mode,
+                                             _abi.ptr(forced_pi), pi.data_ptr(), reward.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), dbg.data_ptr(), int(dbg_step),
+                                             self._stream()), "htsp_decode_debug")
+        nS = 2 * 8 * 128 * NP
+        S = dbg[:nS].reshape(2, 8, 128, NP)
+        O = dbg[nS:nS + 256 * 128].reshape(256, 128)
+        U = dbg[nS + 256 * 128:nS + 256 * 128 + 256 * NP].reshape(256, NP)
+        self.last_debug_cycles = dbg[nS + 256 * 128 + 256 * NP:].reshape(8, 8)[:, :6]
+        return pi, reward, S, O, U
+
     def select_best(self, reward: torch.Tensor, pi: torch.Tensor, n_aug: int):
         """train_path_solver.py:293-306 -> (best_len [B] f32, best_pi [B,N] i64, best_row [B])."""
         lib = _abi.lib()

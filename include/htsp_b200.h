@@ -96,6 +96,17 @@ int htsp_decode(const void* blob, int n_layers, const float* x, const float* emb
                 const int32_t* forced_pi, int32_t* pi, float* reward, float* logits_out,
                 void* workspace, size_t workspace_bytes, void* stream);
 
+/* Test hook (tests/test_parity_gpu.py): as htsp_decode in a tensor-core mode on the tcgen05 kernel
+ * (N <= 224, G <= 256), additionally dumping the intermediates of instance 0 at decode step
+ * `dbg_step` into dbg [htsp_decode_debug_floats(N)] f32: raw glimpse scores S [2,8,128,NP]
+ * (row tile, head, row, key; base-2 exponent units), normalised glimpse outputs O [256,128] and raw
+ * pointer scores U [256,NP] (before c0 and 1/sqrt(128)); NP = N rounded up to 16.              */
+size_t htsp_decode_debug_floats(int N);
+int htsp_decode_debug(const void* blob, int n_layers, const float* x, const float* emb,
+                      const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp, int N,
+                      int G, int mode, const int32_t* forced_pi, int32_t* pi, float* reward,
+                      void* workspace, size_t workspace_bytes, float* dbg, int dbg_step, void* stream);
+
 /* ---- K4: best-of selection and path orientation ---------------------------------------
  * train_path_solver.py:290-306 (max over G, then over the 8 augmentation blocks; first max
  * wins) -> best_len [B] (= -max reward), best_pi [B,N] i64, best_row [B] i32 (a*G+g).
