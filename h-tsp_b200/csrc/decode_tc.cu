@@ -26,8 +26,9 @@
 
 namespace htsp {
 
-constexpr int TCD_THREADS = 320;
+constexpr int TCD_THREADS = 384;          // 12 warps: producer, 2 MMA issuers, (idle), 2 x 4 softmax warps
 constexpr int TCD_STAGES = 3;
+constexpr int TCD_STAGE = 16384;          // ring stage (one key group of a K block, or one head of V^T)
 constexpr int TCD_TILE_STAGING = 65536;   // per row tile: [hi k0-63 | hi k64-127 | lo k0-63 | lo k64-127], 16 KB each
 constexpr int TCD_OCOL = 448;             // O accumulators: column 448 + 32*tile + 16*(head&1)
 constexpr float kTcdInvSqrtH = 0.08838834764831845f;   // 1/sqrt(128)
@@ -36,29 +37,17 @@ constexpr float kTcdThresh = 32768.f;     // chunk sum above this => some p may 
 
 // ---- per-instance operand image (bytes) ----------------------------------------------------------
 //   for p in 0..3:  KA_p [NP keys x 64 halfs]  = K hi/lo of heads 2p, 2p+1   (cols: hi_2p|lo_2p|hi_2p+1|lo_2p+1)
-//                   VT_p [64 rows x keys]      = V^T hi/lo of heads 2p, 2p+1 (rows: hi_2p|lo_2p|hi_2p+1|lo_2p+1),
-//                                                blocks of 64 keys (8 KB each)
+//                   VT_2p, VT_2p+1: [32 rows x keys] = V^T of one head (rows: hi d0-15 | lo d0-15),
+//                                                blocks of 64 keys (4 KB each)
 //   K2 hi cols 0-63, K2 hi cols 64-127, K2 lo cols 0-63, K2 lo cols 64-127: [NP keys x 64 halfs] each
-// every block is K-major SWIZZLE_128B and is copied verbatim into a ring stage.
+// every block is K-major SWIZZLE_128B (rows of 128 bytes).  Key-major blocks (KA, K2) are streamed in
+// one or two key groups ([0,K0) and [K0,NP), K0 = 112 when NP > 128) so that a ring stage is 16 KB.
 __host__ __device__ inline int tcd_kb(int NP) { return (NP + 63) / 64; }
 __host__ __device__ inline size_t tcd_szk(int NP) { return (size_t)NP * 128; }
-__host__ __device__ inline size_t tcd_szv(int NP) { return (size_t)tcd_kb(NP) * 8192; }
-__host__ __device__ inline size_t tcd_img_bytes(int NP) { return 8 * tcd_szk(NP) + 4 * tcd_szv(NP); }
-__host__ __device__ inline int tcd_stage_bytes(int NP) {
-  const size_t a = tcd_szk(NP), b = tcd_szv(NP);
-  return (int)(a > b ? a : b);
-}
-// i-th tile of a step's stream: KA_0, VT_0, KA_1, VT_1, KA_2, VT_2, KA_3, VT_3, K2 x 4
-__device__ __forceinline__ void tcd_stream_tile(int i, int NP, size_t& off, uint32_t& bytes) {
-  const size_t szk = tcd_szk(NP), szv = tcd_szv(NP);
-  if (i < 8) {
-    off = (size_t)(i >> 1) * (szk + szv) + ((i & 1) ? szk : 0);
-    bytes = (uint32_t)((i & 1) ? szv : szk);
-  } else {
-    off = 4 * (szk + szv) + (size_t)(i - 8) * szk;
-    bytes = (uint32_t)szk;
-  }
-}
+__host__ __device__ inline size_t tcd_szvh(int NP) { return (size_t)tcd_kb(NP) * 4096; }
+__host__ __device__ inline size_t tcd_pair_bytes(int NP) { return tcd_szk(NP) + 2 * tcd_szvh(NP); }
+__host__ __device__ inline size_t tcd_img_bytes(int NP) { return 4 * tcd_pair_bytes(NP) + 4 * tcd_szk(NP); }
+__host__ __device__ inline int tcd_k0(int NP) { return NP > 128 ? 112 : NP; }
 
 __device__ __forceinline__ void tcd_split8(const float* v, uint4& hi, uint4& lo) {
   __half2 h[4], l[4];
@@ -75,7 +64,7 @@ __device__ __forceinline__ void tcd_split8(const float* v, uint4& hi, uint4& lo)
 // proj fp32 [Bp*N, 640] (K | V | QL | QF | K2) -> operand image
 __global__ void __launch_bounds__(256)
 decode_tc_pack_kernel(const float* __restrict__ proj, int Bp, int N, int NP, unsigned char* __restrict__ img) {
-  const size_t szk = tcd_szk(NP), szv = tcd_szv(NP), per = tcd_img_bytes(NP);
+  const size_t szk = tcd_szk(NP), szvh = tcd_szvh(NP), pair = tcd_pair_bytes(NP), per = tcd_img_bytes(NP);
   // K and K2: one thread per (instance, key r, matrix m in {K, K2}, 8-column chunk c16)
   const size_t total_a = (size_t)Bp * NP * 32;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_a;
@@ -98,11 +87,11 @@ decode_tc_pack_kernel(const float* __restrict__ proj, int Bp, int N, int NP, uns
     unsigned char* base = img + (size_t)b * per;
     if (m == 0) {
       const int h = c16 >> 1, p = h >> 1, e = h & 1;
-      unsigned char* blk = base + (size_t)p * (szk + szv);
+      unsigned char* blk = base + (size_t)p * pair;
       *(uint4*)(blk + tc::sw128_off(r, e * 4 + (c16 & 1))) = hi;
       *(uint4*)(blk + tc::sw128_off(r, e * 4 + 2 + (c16 & 1))) = lo;
     } else {
-      unsigned char* blk = base + 4 * (szk + szv) + (size_t)(c16 >> 3) * szk;
+      unsigned char* blk = base + 4 * pair + (size_t)(c16 >> 3) * szk;
       *(uint4*)(blk + tc::sw128_off(r, c16 & 7)) = hi;
       *(uint4*)(blk + 2 * szk + tc::sw128_off(r, c16 & 7)) = lo;
     }
@@ -124,9 +113,9 @@ decode_tc_pack_kernel(const float* __restrict__ proj, int Bp, int N, int NP, uns
     uint4 hi, lo;
     tcd_split8(v, hi, lo);
     const int h = c >> 4, d = c & 15, p = h >> 1, e = h & 1;
-    unsigned char* blk = img + (size_t)b * per + (size_t)p * (szk + szv) + szk + (size_t)(r8 >> 3) * 8192;
-    *(uint4*)(blk + tc::sw128_off(e * 32 + d, r8 & 7)) = hi;
-    *(uint4*)(blk + tc::sw128_off(e * 32 + 16 + d, r8 & 7)) = lo;
+    unsigned char* blk = img + (size_t)b * per + (size_t)p * pair + szk + (size_t)e * szvh + (size_t)(r8 >> 3) * 4096;
+    *(uint4*)(blk + tc::sw128_off(d, r8 & 7)) = hi;
+    *(uint4*)(blk + tc::sw128_off(16 + d, r8 & 7)) = lo;
   }
 }
 
@@ -143,13 +132,13 @@ struct TcdArgs {
   int32_t* pi;
   float* reward;
   float* logits_out;
-  float* dbg;            // DEBUG builds: [S raw 2*8*128*NP | O 256*128 | U raw 256*NP] of instance 0 at dbg_step
+  float* dbg;            // DEBUG builds: [S raw 2*8*128*NP | O 256*128 | U raw 256*NP | phase cycles] of instance 0
   int N, NP, G, fast, dbg_step;
 };
 
-// barrier slots
-enum { TB_FULL = 0, TB_EMPTY = 3, TB_QFULL = 6, TB_SFULL = 8, TB_PFULL = 10, TB_OFULL = 12, TB_OREADY = 16,
-       TB_UFULL = 18, TB_COUNT = 20 };
+// barrier slots of one row tile
+enum { TB_FULL = 0, TB_EMPTY = 3, TB_QFULL = 6, TB_SFULL = 7, TB_PFULL = 8, TB_OFULL = 9, TB_OREADY = 11,
+       TB_UFULL = 12, TB_PER_TILE = 13 };
 
 __device__ __forceinline__ unsigned tcd_word(const unsigned (&vis)[7], int w) {
   unsigned r = vis[0];
@@ -158,50 +147,103 @@ __device__ __forceinline__ unsigned tcd_word(const unsigned (&vis)[7], int w) {
   return r;
 }
 
-__device__ __forceinline__ void st16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
+// TMEM <-> registers for W = 16 or 32 columns into / from the first W entries of a 32-register array
+template <int W>
+__device__ __forceinline__ void tld(uint32_t taddr, uint32_t (&r)[32]) {
+  if (W == 32) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+  } else {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+  }
+}
+// completes every earlier tcgen05.ld of this thread; the "+r" operands tie the registers to the wait
+__device__ __forceinline__ void tld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
+                 "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]),
+                 "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]),
+                 "+r"(r[29]), "+r"(r[30]), "+r"(r[31])::"memory");
+}
+__device__ __forceinline__ void tld_wait16(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
+                 "+r"(r[15])::"memory");
+}
+template <int W>
+__device__ __forceinline__ void tst(uint32_t taddr, const uint32_t (&r)[32]) {
+  if (W == 32) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),
+        "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
+        "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+  } else {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+  }
 }
 
 template <bool LOGITS, bool DEBUG>
 __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs A) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler too
   const int b = blockIdx.x;
   const int N = A.N, NP = A.NP, G = A.G;
-  const int nch = NP >> 4;                       // 16-key chunks
   const int n_steps = N - 2;
-  const int STAGE = tcd_stage_bytes(NP);
   const int n_tiles = G > 128 ? 2 : 1;
+  const int K0 = tcd_k0(NP), K1 = NP - K0, ng = K1 > 0 ? 2 : 1;
+  const int nks = NP >> 4;                                               // k16 steps of P V
 
   unsigned char* staging = smem;                                         // 2 x 64 KB
-  unsigned char* ring = smem + 2 * TCD_TILE_STAGING;                     // TCD_STAGES x STAGE
-  float* c0s = (float*)(ring + (size_t)TCD_STAGES * STAGE);              // [NP]
+  unsigned char* rings = smem + 2 * TCD_TILE_STAGING;                    // 2 tiles x TCD_STAGES x 16 KB
+  float* c0s = (float*)(rings + (size_t)2 * TCD_STAGES * TCD_STAGE);     // [NP]
   uint64_t* bars = (uint64_t*)(c0s + NP);
-  uint32_t* tmem_slot = (uint32_t*)(bars + TB_COUNT);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TB_PER_TILE);
   const uint32_t bar0 = tc::smem_u32(bars);
-  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
 
   const unsigned char* imgb = A.img + (size_t)b * tcd_img_bytes(NP);
   const float* projb = A.proj + (size_t)b * N * PROJ;
 
   if ((tc::smem_u32(smem) & 1023u) != 0u) __trap();   // SWIZZLE_128B atoms need 1024-byte alignment
   if (tid == 0) {
-    for (int s = 0; s < TCD_STAGES; ++s) { tc::mbar_init(BAR(TB_FULL + s), 1); tc::mbar_init(BAR(TB_EMPTY + s), 1); }
     for (int t = 0; t < 2; ++t) {
+      const uint32_t bt = bar0 + 8u * (uint32_t)(t * TB_PER_TILE);
       const int rows_t = min(128, G - 128 * t);
       const int warps_t = rows_t > 0 ? (rows_t + 31) / 32 : 1;
-      tc::mbar_init(BAR(TB_QFULL + t), warps_t);
-      tc::mbar_init(BAR(TB_SFULL + t), 1);
-      tc::mbar_init(BAR(TB_PFULL + t), warps_t);
-      tc::mbar_init(BAR(TB_OFULL + 2 * t), 1);
-      tc::mbar_init(BAR(TB_OFULL + 2 * t + 1), 1);
-      tc::mbar_init(BAR(TB_OREADY + t), warps_t);
-      tc::mbar_init(BAR(TB_UFULL + t), 1);
+      for (int s = 0; s < TCD_STAGES; ++s) { tc::mbar_init(bt + 8 * (TB_FULL + s), 1); tc::mbar_init(bt + 8 * (TB_EMPTY + s), 1); }
+      tc::mbar_init(bt + 8 * TB_QFULL, warps_t);
+      tc::mbar_init(bt + 8 * TB_SFULL, 1);
+      tc::mbar_init(bt + 8 * TB_PFULL, warps_t);
+      tc::mbar_init(bt + 8 * TB_OFULL, 1);
+      tc::mbar_init(bt + 8 * (TB_OFULL + 1), 1);
+      tc::mbar_init(bt + 8 * TB_OREADY, warps_t);
+      tc::mbar_init(bt + 8 * TB_UFULL, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -220,114 +262,157 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
   tc::fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // register budget: the role warpgroup (warps 0-3) hands registers to the two softmax warpgroups
+  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
+
   if (warp == 0) {
-    // ================================================================== operand producer
+    // ================================================================== operand producer (both row tiles)
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int step = 0; step < n_steps; ++step) {
-        for (int i = 0; i < 12; ++i, ++it) {
-          const uint32_t s = it % TCD_STAGES, use = it / TCD_STAGES;
-          tc::mbar_wait(BAR(TB_EMPTY + s), (use & 1) ^ 1);
+      const size_t szk = tcd_szk(NP), szvh = tcd_szvh(NP), pair = tcd_pair_bytes(NP);
+      const int per_step = 4 * (ng + 2) + 4 * ng;          // ring stages one tile consumes per decode step
+      const uint32_t total = (uint32_t)n_steps * (uint32_t)per_step;
+      uint32_t it[2] = {0, 0};
+      int rem = n_tiles;
+      uint32_t idle = 0;
+      while (rem > 0) {
+        bool pushed = false;
+        for (int t = 0; t < n_tiles; ++t) {
+          if (it[t] >= total) continue;
+          const uint32_t bt = bar0 + 8u * (uint32_t)(t * TB_PER_TILE);
+          const uint32_t s = it[t] % TCD_STAGES, use = it[t] / TCD_STAGES;
+          if (!tc::mbar_test(bt + 8 * (TB_EMPTY + s), (use & 1) ^ 1)) continue;
+          // i-th stage of the step: per head pair [KA g0, (KA g1), V 2p, V 2p+1], then K2 blocks by key group
+          const int i = (int)(it[t] % (uint32_t)per_step);
           size_t off;
           uint32_t bytes;
-          tcd_stream_tile(i, NP, off, bytes);
-          tc::mbar_expect_tx(BAR(TB_FULL + s), bytes);
-          tc::bulk_g2s(tc::smem_u32(ring + (size_t)s * STAGE), imgb + off, bytes, BAR(TB_FULL + s));
+          if (i < 4 * (ng + 2)) {
+            const int p = i / (ng + 2), j = i % (ng + 2);
+            if (j < ng) { off = (size_t)p * pair + (j ? (size_t)K0 * 128 : 0); bytes = (uint32_t)(j ? K1 : K0) * 128u; }
+            else { off = (size_t)p * pair + szk + (size_t)(j - ng) * szvh; bytes = (uint32_t)szvh; }
+          } else {
+            const int i2 = i - 4 * (ng + 2), blk = i2 / ng, gi = i2 % ng;
+            off = 4 * pair + (size_t)blk * szk + (gi ? (size_t)K0 * 128 : 0);
+            bytes = (uint32_t)(gi ? K1 : K0) * 128u;
+          }
+          tc::mbar_expect_tx(bt + 8 * (TB_FULL + s), bytes);
+          tc::bulk_g2s(tc::smem_u32(rings + ((size_t)t * TCD_STAGES + s) * TCD_STAGE), imgb + off, bytes,
+                       bt + 8 * (TB_FULL + s));
+          if (++it[t] == total) --rem;
+          pushed = true;
         }
+        if (pushed) idle = 0;
+        else if (++idle > (1u << 28)) __trap();
+        else __nanosleep(64);
       }
     }
-  } else if (warp == 1) {
-    // ================================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idS = tc::idesc_f16(NP), idO = tc::idesc_f16(16);
-      const uint32_t stg0 = tc::smem_u32(staging), ring0 = tc::smem_u32(ring);
-      auto stage_addr = [&](uint32_t k) { return ring0 + (k % TCD_STAGES) * (uint32_t)STAGE; };
-      auto stage_wait = [&](uint32_t k) {
-        tc::mbar_wait(BAR(TB_FULL + (k % TCD_STAGES)), (k / TCD_STAGES) & 1);
-        tc::fence_after();
-      };
-      auto stage_free = [&](uint32_t k) { tc::commit(BAR(TB_EMPTY + (k % TCD_STAGES))); };
-      // S_h(t) = Q_h K_h^T into TMEM columns [t*NP, t*NP+NP)
-      auto issue_S = [&](int t, int h, uint32_t ka) {
-        const uint32_t a_hi = stg0 + t * TCD_TILE_STAGING + (h >> 2) * 16384 + (h & 3) * 32, a_lo = a_hi + 32768;
-        const uint32_t b_hi = ka + (h & 1) * 64, b_lo = b_hi + 32;
-        const uint32_t d = tmem_base + (uint32_t)(t * NP);
-        tc::mma_ss(d, tc::desc_sw128(a_hi), tc::desc_sw128(b_hi), idS, 0);
-        if (!A.fast) {
-          tc::mma_ss(d, tc::desc_sw128(a_hi), tc::desc_sw128(b_lo), idS, 1);
-          tc::mma_ss(d, tc::desc_sw128(a_lo), tc::desc_sw128(b_hi), idS, 1);
-        }
-        tc::commit(BAR(TB_SFULL + t));
-      };
-      // O_h(t) = P_h V_h: A = P hi/lo in TMEM (8 + 8 columns per 16 keys), B = V^T rows of head h
-      auto issue_PV = [&](int t, int h, uint32_t va) {
-        const uint32_t d = tmem_base + (uint32_t)(TCD_OCOL + 32 * t + 16 * (h & 1));
-        const uint32_t pa = tmem_base + (uint32_t)(t * NP);
-        const uint32_t vb = va + (h & 1) * 4096;
-        for (int ks = 0; ks < nch; ++ks) {
-          const uint32_t v_hi = vb + (ks >> 2) * 8192 + (ks & 3) * 32, v_lo = v_hi + 2048;
-          const uint32_t p_hi = pa + 16 * ks, p_lo = p_hi + 8;
-          tc::mma_ts(d, p_hi, tc::desc_sw128(v_hi), idO, ks > 0);
-          tc::mma_ts(d, p_hi, tc::desc_sw128(v_lo), idO, 1);
-          tc::mma_ts(d, p_lo, tc::desc_sw128(v_hi), idO, 1);
-        }
-        tc::commit(BAR(TB_OFULL + 2 * t + (h & 1)));
-      };
-      for (int step = 0; step < n_steps; ++step) {
-        const uint32_t k0 = (uint32_t)step * 12;
-        stage_wait(k0);
-        for (int t = 0; t < n_tiles; ++t) {
-          tc::mbar_wait(BAR(TB_QFULL + t), step & 1);
+  } else if (warp < 3) {
+    const int t = warp - 1;                       // warp 1 issues for row tile 0, warp 2 for row tile 1
+    const uint32_t bt = bar0 + 8u * (uint32_t)(t * TB_PER_TILE);
+    auto BAR = [&](int i) { return bt + 8u * (uint32_t)i; };
+    const uint32_t ring0 = tc::smem_u32(rings + (size_t)t * TCD_STAGES * TCD_STAGE);
+    if (t < n_tiles) {
+      {
+        // ================================================================== MMA issuer of tile t
+        // (the whole warp runs the control flow so that addresses stay in uniform registers; one
+        // elected lane issues the tcgen05 instructions)
+        const bool leader = tc::elect_one();
+        const uint32_t idK0 = tc::idesc_f16(K0), idK1 = tc::idesc_f16(K1 > 0 ? K1 : 16), idO = tc::idesc_f16(16);
+        const uint32_t stg = tc::smem_u32(staging) + t * TCD_TILE_STAGING;
+        const uint32_t dS = tmem_base + (uint32_t)(t * NP);
+        uint32_t it = 0;
+        auto take = [&]() {                      // next ring stage, in stream order
+          const uint32_t s = it % TCD_STAGES, use = it / TCD_STAGES;
+          tc::mbar_wait(BAR(TB_FULL + s), use & 1);
           tc::fence_after();
-          issue_S(t, 0, stage_addr(k0));
-        }
-        for (int h = 0; h < NH; ++h) {
-          const int p = h >> 1;
-          const uint32_t kv = k0 + 2 * p + 1;
-          if ((h & 1) == 0) stage_wait(kv);
-          for (int t = 0; t < n_tiles; ++t) {
-            tc::mbar_wait(BAR(TB_PFULL + t), (step * NH + h) & 1);
-            tc::fence_after();
-            issue_PV(t, h, stage_addr(kv));
-            if (h + 1 < NH) {
-              const uint32_t kk = k0 + 2 * ((h + 1) >> 1);
-              if (t == 0 && ((h + 1) & 1) == 0) stage_wait(kk);
-              issue_S(t, h + 1, stage_addr(kk));
-            }
-          }
-          if ((h & 1) == 0) stage_free(k0 + 2 * p);   // KA_p: S of both heads of the pair issued
-          else stage_free(kv);                         // VT_p: PV of both heads issued
-        }
-        // pointer logits U(t) = O K2^T into the (consumed) S columns
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t k = k0 + 8 + i;
-          stage_wait(k);
-          const uint32_t kb = stage_addr(k);
-          const int half = i & 1;                      // O columns 64*half .. +63
-          for (int t = 0; t < n_tiles; ++t) {
-            if (i == 0) {
-              tc::mbar_wait(BAR(TB_OREADY + t), step & 1);
+          ++it;
+          return s;
+        };
+        auto release = [&](uint32_t s) { if (leader) tc::commit(BAR(TB_EMPTY + s)); };
+        for (int step = 0; step < n_steps; ++step) {
+          for (int p = 0; p < 4; ++p) {
+            const uint32_t sk0 = take(), sk1 = (ng == 2) ? take() : 0u;
+            for (int e = 0; e < 2; ++e) {
+              const int h = 2 * p + e;
+              if (h == 0) {
+                tc::mbar_wait(BAR(TB_QFULL), step & 1);
+                tc::fence_after();
+              }
+              // S_h = Q_h K_h^T into TMEM columns [t*NP, t*NP+NP), one MMA group per key group
+              const uint32_t a_hi = (stg >> 4) + (h >> 2) * 1024 + (h & 3) * 2, a_lo = a_hi + 2048;
+              for (int gi = 0; gi < ng; ++gi) {
+                const uint32_t b_hi = ((ring0 + (gi ? sk1 : sk0) * TCD_STAGE) >> 4) + e * 4, b_lo = b_hi + 2;
+                const uint32_t d = dS + (gi ? K0 : 0), id = gi ? idK1 : idK0;
+                if (leader) {
+                  tc::mma_ss_lo(d, a_hi, b_hi, id, 0);
+                  if (!A.fast) {
+                    tc::mma_ss_lo(d, a_hi, b_lo, id, 1);
+                    tc::mma_ss_lo(d, a_lo, b_hi, id, 1);
+                  }
+                }
+              }
+              if (leader) tc::commit(BAR(TB_SFULL));
+              __syncwarp();
+              if (e == 1) {
+                release(sk0);
+                if (ng == 2) release(sk1);
+              }
+              // O_h = P_h V_h: A = P hi/lo in TMEM (8 + 8 columns per 16 keys), B = V^T of head h
+              const uint32_t sv = take();
+              tc::mbar_wait(BAR(TB_PFULL), (step * NH + h) & 1);
               tc::fence_after();
-            }
-            const uint32_t d = tmem_base + (uint32_t)(t * NP);
-            const uint32_t o_hi = stg0 + t * TCD_TILE_STAGING + half * 16384, o_lo = o_hi + 32768;
+              const uint32_t dO = tmem_base + (uint32_t)(TCD_OCOL + 32 * t + 16 * e);
+              const uint32_t vb = (ring0 + sv * TCD_STAGE) >> 4;
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t bd = tc::desc_sw128(kb + kk * 32);
-              tc::mma_ss(d, tc::desc_sw128(o_hi + kk * 32), bd, idS, (i | kk) != 0);
-              if (i < 2) tc::mma_ss(d, tc::desc_sw128(o_lo + kk * 32), bd, idS, 1);
+              for (int ks = 0; ks < 14; ++ks) {
+                if (ks < nks && leader) {
+                  const uint32_t v_hi = vb + (ks >> 2) * 256 + (ks & 3) * 2, v_lo = v_hi + 128;
+                  const uint32_t p_hi = dS + 16 * ks, p_lo = p_hi + 8;
+                  tc::mma_ts_lo(dO, p_hi, v_hi, idO, ks > 0);
+                  tc::mma_ts_lo(dO, p_hi, v_lo, idO, 1);
+                  tc::mma_ts_lo(dO, p_lo, v_hi, idO, 1);
+                }
+              }
+              if (leader) tc::commit(BAR(TB_OFULL + e));
+              __syncwarp();
+              release(sv);
             }
           }
-          stage_free(k);
+          // pointer logits U = O K2^T into the (consumed) S columns
+          for (int i = 0; i < 4; ++i) {
+            const int half = i & 1;                    // O / K2 columns 64*half .. +63
+            const uint32_t o_hi = (stg >> 4) + half * 1024, o_lo = o_hi + 2048;
+            for (int gi = 0; gi < ng; ++gi) {
+              const uint32_t sk = take();
+              if (i == 0 && gi == 0) {
+                tc::mbar_wait(BAR(TB_OREADY), step & 1);
+                tc::fence_after();
+              }
+              const uint32_t kb = (ring0 + sk * TCD_STAGE) >> 4;
+              const uint32_t d = dS + (gi ? K0 : 0), id = gi ? idK1 : idK0;
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                if (leader) {
+                  tc::mma_ss_lo(d, o_hi + kk * 2, kb + kk * 2, id, (i | kk) != 0);
+                  if (i < 2) tc::mma_ss_lo(d, o_lo + kk * 2, kb + kk * 2, id, 1);
+                }
+              }
+              release(sk);
+              __syncwarp();
+            }
+          }
+          if (leader) tc::commit(BAR(TB_UFULL));
+          __syncwarp();
         }
-        for (int t = 0; t < n_tiles; ++t) tc::commit(BAR(TB_UFULL + t));
       }
     }
-  } else {
+  } else if (warp >= 4) {
     // ================================================================== softmax / state warps
-    const int t = (warp - 2) >> 2, q = warp & 3;
+    const int t = (warp - 4) >> 2, q = warp & 3;
     const int rows_t = min(128, G - 128 * t);
     if (q * 32 < rows_t) {
+      const uint32_t bt = bar0 + 8u * (uint32_t)(t * TB_PER_TILE);
+      auto BAR = [&](int i) { return bt + 8u * (uint32_t)i; };
       const int row = q * 32 + lane;                 // row inside the tile = TMEM lane
       const int g = t * 128 + row;
       const bool valid = g < G;
@@ -367,27 +452,36 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
         }
       };
       // query rows of this warp's 32 starts -> A tile (fp16 hi/lo, K-major SWIZZLE_128B):
-      // q = ((q_graph+q_source+q_target) + q_first) + q_last (models.py:413), 1/sqrt(dk)*log2(e) folded in
+      // q = ((q_graph+q_source+q_target) + q_first) + q_last (models.py:413), 1/sqrt(dk)*log2(e) folded in.
+      // Lane l carries columns 4l..4l+3 of every row; 8 rows (16 L2 loads) are in flight at a time.
       auto gather_q = [&]() {
         const uint32_t sub = (uint32_t)(lane >> 4) * 16384u + (uint32_t)(lane & 1) * 8u;
         const uint32_t chunk = (uint32_t)(lane & 15) >> 1;
-#pragma unroll 4
-        for (int r = 0; r < 32; ++r) {
-          const int rr = q * 32 + r;
-          if (t * 128 + rr >= G) break;
-          const int cr = __shfl_sync(0xffffffffu, cur, r), fr = __shfl_sync(0xffffffffu, first, r);
-          const float4 ql = __ldg((const float4*)(projb + (size_t)cr * PROJ + 2 * H) + lane);
-          const float4 qf = __ldg((const float4*)(projb + (size_t)fr * PROJ + 3 * H) + lane);
-          uint32_t h0, l0, h1, l1;
-          split2(((qfix4.x + qf.x) + ql.x) * kScoreScale, ((qfix4.y + qf.y) + ql.y) * kScoreScale, h0, l0);
-          split2(((qfix4.z + qf.z) + ql.z) * kScoreScale, ((qfix4.w + qf.w) + ql.w) * kScoreScale, h1, l1);
-          unsigned char* p = stg + sub + tc::sw128_off((uint32_t)rr, chunk);
-          *(uint2*)p = make_uint2(h0, h1);
-          *(uint2*)(p + 32768) = make_uint2(l0, l1);
+        const int nrows = min(32, rows_t - q * 32);
+#pragma unroll 1
+        for (int r0 = 0; r0 < nrows; r0 += 8) {
+          float4 ql[8], qf[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int cr = __shfl_sync(0xffffffffu, cur, r0 + i), fr = __shfl_sync(0xffffffffu, first, r0 + i);
+            ql[i] = __ldg((const float4*)(projb + (size_t)cr * PROJ + 2 * H) + lane);
+            qf[i] = __ldg((const float4*)(projb + (size_t)fr * PROJ + 3 * H) + lane);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (r0 + i < nrows) {
+              uint32_t h0, l0, h1, l1;
+              split2(((qfix4.x + qf[i].x) + ql[i].x) * kScoreScale, ((qfix4.y + qf[i].y) + ql[i].y) * kScoreScale, h0, l0);
+              split2(((qfix4.z + qf[i].z) + ql[i].z) * kScoreScale, ((qfix4.w + qf[i].w) + ql[i].w) * kScoreScale, h1, l1);
+              unsigned char* p = stg + sub + tc::sw128_off((uint32_t)(q * 32 + r0 + i), chunk);
+              *(uint2*)p = make_uint2(h0, h1);
+              *(uint2*)(p + 32768) = make_uint2(l0, l1);
+            }
+          }
         }
         tc::fence_async_smem();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(BAR(TB_QFULL + t));
+        if (lane == 0) tc::mbar_arrive(BAR(TB_QFULL));
       };
 
       // step 0: no decoder call (train_path_solver.py:256-257)
@@ -408,7 +502,7 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
       };
       // drain O_h: TMEM -> /l -> fp16 hi/lo -> A tile columns 16h..16h+15 (the consumed Q_h slot)
       auto drain_o = [&](int step, int h, float l) {
-        tc::mbar_wait(BAR(TB_OFULL + 2 * t + (h & 1)), (step * 4 + (h >> 1)) & 1);
+        tc::mbar_wait(BAR(TB_OFULL + (h & 1)), (step * 4 + (h >> 1)) & 1);
         tc::fence_after();
         uint32_t o[16];
         tc::ld16(tO + 16 * (h & 1), o);
@@ -437,49 +531,70 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
         // ------------------------------------------------------------ glimpse, one head at a time
 #pragma unroll 1
         for (int h = 0; h < NH; ++h) {
-          tc::mbar_wait(BAR(TB_SFULL + t), (step * NH + h) & 1);
+          tc::mbar_wait(BAR(TB_SFULL), (step * NH + h) & 1);
           tc::fence_after();
           tick(0);
           float m = valid ? kTcdFloor : 0.f, l = 0.f;
-          uint32_t sA[16], sB[16];
-          tc::ld16(tS, sA);
-          // one 16-key chunk: mask, 2^(s-m), row sum, fp16 hi/lo, store in place
-          auto chunk = [&](int c, uint32_t (&s)[16], unsigned bits) {
+          uint32_t sA[32], sB[32];     // only the first 16 entries are used (16-key chunks)
+          float pA[32], pB[32];
+          // fp16 hi/lo of the probabilities of a finished chunk -> TMEM, in place over its scores;
+          // per 16 keys: 8 columns of hi pairs, then 8 columns of lo pairs (one MMA k-step each)
+          auto finish = [&](auto wtag, int c0, const float (&p)[32]) {
+            constexpr int W = decltype(wtag)::value;
+            uint32_t out[32];
+#pragma unroll
+            for (int j = 0; j < W; j += 2)
+              split2(p[j], p[j + 1], out[(j >> 4) * 16 + ((j & 15) >> 1)], out[(j >> 4) * 16 + 8 + ((j & 15) >> 1)]);
+            tst<W>(tS + c0, out);
+          };
+          // one W-key chunk at column c0: mask, 2^(s-m), row sum.  The fp16 split + store of the PREVIOUS
+          // chunk (WP keys at column c0-WP) is issued in the same basic block as this chunk's exponentials
+          // so that the ALU work overlaps the MUFU stream.
+          auto chunk = [&](auto wtag, auto wptag, int c0, uint32_t (&s)[32], unsigned bits, float (&p)[32],
+                           const float (&pprev)[32]) {
+            constexpr int W = decltype(wtag)::value;
+            constexpr int WP = decltype(wptag)::value;
             if (DEBUG && b == 0 && step == A.dbg_step) {
-              float* dS = A.dbg + ((size_t)(t * 8 + h) * 128 + row) * NP + 16 * c;
+              float* dS = A.dbg + ((size_t)(t * 8 + h) * 128 + row) * NP + c0;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) dS[j] = __uint_as_float(s[j]);
+              for (int j = 0; j < W; ++j) dS[j] = __uint_as_float(s[j]);
             }
-            float tv[16], p[16];
+            float tv[W];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) tv[j] = ((bits >> j) & 1u) ? -INFINITY : __uint_as_float(s[j]);
+            for (int j = 0; j < W; ++j) tv[j] = ((bits >> j) & 1u) ? -INFINITY : __uint_as_float(s[j]);
             float csum;
             auto expo = [&]() {
-              float2 acc = make_float2(0.f, 0.f);
+              float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
               const float2 nm = make_float2(-m, -m);
 #pragma unroll
-              for (int j = 0; j < 16; j += 2) {
-                const float2 d = __fadd2_rn(make_float2(tv[j], tv[j + 1]), nm);
-                p[j] = ex2_approx(d.x);
-                p[j + 1] = ex2_approx(d.y);
-                acc = __fadd2_rn(acc, make_float2(p[j], p[j + 1]));
+              for (int j = 0; j < W; j += 4) {
+                const float2 d0 = __fadd2_rn(make_float2(tv[j], tv[j + 1]), nm);
+                const float2 d1 = __fadd2_rn(make_float2(tv[j + 2], tv[j + 3]), nm);
+                p[j] = ex2_approx(d0.x);
+                p[j + 1] = ex2_approx(d0.y);
+                p[j + 2] = ex2_approx(d1.x);
+                p[j + 3] = ex2_approx(d1.y);
+                acc0 = __fadd2_rn(acc0, make_float2(p[j], p[j + 1]));
+                acc1 = __fadd2_rn(acc1, make_float2(p[j + 2], p[j + 3]));
               }
-              csum = acc.x + acc.y;
+              acc0 = __fadd2_rn(acc0, acc1);
+              csum = acc0.x + acc0.y;
             };
             expo();
+            if (WP > 0) finish(wptag, c0 - WP, pprev);
             const bool need = valid && !(csum <= kTcdThresh);
             if (__any_sync(0xffffffffu, need)) {
               // move the shift (to an integer, so rescaling earlier chunks by 2^(m-m') is exact)
               float cm = tv[0];
 #pragma unroll
-              for (int j = 1; j < 16; ++j) cm = fmaxf(cm, tv[j]);
+              for (int j = 1; j < W; ++j) cm = fmaxf(cm, tv[j]);
               const float m_new = (need && cm > m) ? ceilf(cm) : m;
               const float alpha = ex2_approx(m - m_new);
               if (__any_sync(0xffffffffu, (m_new != m) && (l > 0.f))) {
                 tc::st_wait();
-                for (int cc = 0; cc < c; ++cc) {
+                for (int cc = 0; cc < c0; cc += 16) {
                   uint32_t r[16];
-                  tc::ld16(tS + 16 * cc, r);
+                  tc::ld16(tS + cc, r);
                   tc::ld16_wait(r);
 #pragma unroll
                   for (int j = 0; j < 16; ++j) {
@@ -487,7 +602,7 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
                     __half2 hh = __floats2half2_rn(f.x * alpha, f.y * alpha);
                     r[j] = *reinterpret_cast<uint32_t*>(&hh);
                   }
-                  st16(tS + 16 * cc, r);
+                  tc::st16(tS + cc, r);
                 }
               }
               l *= alpha;
@@ -495,27 +610,31 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
               expo();
             }
             l += csum;
-            uint32_t out[16];
-#pragma unroll
-            for (int j = 0; j < 16; j += 2) split2(p[j], p[j + 1], out[j >> 1], out[8 + (j >> 1)]);
-            st16(tS + 16 * c, out);
           };
+          using W0 = std::integral_constant<int, 0>;
+          using W16 = std::integral_constant<int, 16>;
+          // software pipeline over 16-key chunks: the TMEM load of chunk c+1 is in flight while chunk c
+          // is processed, and chunk c-1 is split/stored under chunk c's exponentials
+          const int nch = NP >> 4;
+          auto stepc = [&](int c, uint32_t (&curb)[32], uint32_t (&nxt)[32], float (&p)[32], const float (&pprev)[32]) {
+            tld_wait16(curb);
+            if (c + 1 < nch) tld<16>(tS + 16 * (c + 1), nxt);
+            const unsigned bits = (tcd_word(vis, c >> 1) >> ((c & 1) * 16)) & 0xffffu;
+            if (c == 0) chunk(W16{}, W0{}, 0, curb, bits, p, pprev);
+            else chunk(W16{}, W16{}, 16 * c, curb, bits, p, pprev);
+          };
+          tld<16>(tS, sA);
 #pragma unroll 1
-          for (int w = 0; 2 * w < nch; ++w) {
-            const unsigned word = tcd_word(vis, w);
-            tc::ld16_wait(sA);
-            if (2 * w + 1 < nch) tc::ld16(tS + 16 * (2 * w + 1), sB);
-            chunk(2 * w, sA, word & 0xffffu);
-            if (2 * w + 1 < nch) {
-              tc::ld16_wait(sB);
-              if (2 * w + 2 < nch) tc::ld16(tS + 16 * (2 * w + 2), sA);
-              chunk(2 * w + 1, sB, word >> 16);
-            }
+          for (int c = 0; c < nch; c += 2) {
+            stepc(c, sA, sB, pA, pB);
+            if (c + 1 < nch) stepc(c + 1, sB, sA, pB, pA);
           }
+          if (nch & 1) finish(W16{}, 16 * (nch - 1), pA);
+          else finish(W16{}, 16 * (nch - 1), pB);
           tc::st_wait();
           tc::fence_before();
           __syncwarp();
-          if (lane == 0) tc::mbar_arrive(BAR(TB_PFULL + t));
+          if (lane == 0) tc::mbar_arrive(BAR(TB_PFULL));
           tick(1);
           if (h > 0) drain_o(step, h - 1, l_prev);
           l_prev = l;
@@ -525,11 +644,11 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
         tc::fence_async_smem();
         tc::fence_before();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(BAR(TB_OREADY + t));
+        if (lane == 0) tc::mbar_arrive(BAR(TB_OREADY));
         tick(2);
 
         // ------------------------------------------------------------ pointer logits + arg-max
-        tc::mbar_wait(BAR(TB_UFULL + t), step & 1);
+        tc::mbar_wait(BAR(TB_UFULL), step & 1);
         tc::fence_after();
         tick(3);
         float best = -INFINITY;
@@ -539,30 +658,54 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
           lo_out = A.logits_out + (((size_t)b * G + gc) * n_steps + step) * N;
         // pass(EXACT): EXACT compares the clipped logits 10*tanh(.) themselves (models.py:438-440);
         // otherwise the monotone pre-activation is compared, which picks the same key except when two
-        // clipped logits round to the same float (handled by re-running EXACT near the clip)
+        // clipped logits round to the same float (handled by re-running EXACT near the clip).
+        // 16 independent running maxima (one per column slot of a 16-key chunk), merged at the end
+        // with the lowest key winning ties (torch.argmax returns the first maximum).
         auto pass = [&](auto exact_tag) {
           constexpr bool EXACT = decltype(exact_tag)::value;
-          best = -INFINITY;
-          idx = 0x7fffffff;
-          uint32_t u[16];
-#pragma unroll 1
-          for (int c = 0; c < nch; ++c) {
-            tc::ld16(tS + 16 * c, u);
+          float bj[16];
+          int cj[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { bj[j] = -INFINITY; cj[j] = 0; }
+          uint32_t u[32], u2[32];
+          const int nch = NP >> 4;
+          auto body = [&](int c, uint32_t (&uu)[32], uint32_t (&nx)[32]) {
+            tld_wait16(uu);
+            if (c + 1 < nch) tld<16>(tS + 16 * (c + 1), nx);
             const unsigned bits = (tcd_word(vis, c >> 1) >> ((c & 1) * 16)) & 0xffffu;
-            tc::ld16_wait(u);
             if (DEBUG && b == 0 && step == A.dbg_step) {
               float* dU = A.dbg + (size_t)2 * 8 * 128 * NP + (size_t)256 * 128 + (size_t)(t * 128 + row) * NP + 16 * c;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) dU[j] = __uint_as_float(u[j]);
+              for (int j = 0; j < 16; ++j) dU[j] = __uint_as_float(uu[j]);
             }
+            const float4* cc4 = (const float4*)(c0s + 16 * c);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float z = (__uint_as_float(u[j]) + c0s[16 * c + j]) * kTcdInvSqrtH;
-              if (EXACT) z = clip_tanh10(z);
-              if ((bits >> j) & 1u) z = -INFINITY;
-              if (LOGITS && lo_out != nullptr && valid && 16 * c + j < N) lo_out[16 * c + j] = z;
-              if (z > best) { best = z; idx = 16 * c + j; }
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 cc = cc4[j4];
+              const float ca[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int j = 4 * j4 + jj;
+                float z = (__uint_as_float(uu[j]) + ca[jj]) * kTcdInvSqrtH;
+                if (EXACT) z = clip_tanh10(z);
+                if ((bits >> j) & 1u) z = -INFINITY;
+                if (LOGITS && lo_out != nullptr && valid && 16 * c + j < N) lo_out[16 * c + j] = z;
+                if (z > bj[j]) { bj[j] = z; cj[j] = c; }
+              }
             }
+          };
+          tld<16>(tS, u);
+#pragma unroll 1
+          for (int c = 0; c < nch; c += 2) {
+            body(c, u, u2);
+            if (c + 1 < nch) body(c + 1, u2, u);
+          }
+          best = bj[0];
+          idx = 16 * cj[0];
+#pragma unroll
+          for (int j = 1; j < 16; ++j) {
+            const int key = 16 * cj[j] + j;
+            if (bj[j] > best || (bj[j] == best && key < idx)) { best = bj[j]; idx = key; }
           }
         };
         if (LOGITS) {
@@ -580,7 +723,7 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
         tick(5);
       }
       if (DEBUG && b == 0 && lane == 0) {
-        float* dT = A.dbg + (size_t)2 * 8 * 128 * NP + (size_t)256 * 128 + (size_t)256 * NP + (warp - 2) * 8;
+        float* dT = A.dbg + (size_t)2 * 8 * 128 * NP + (size_t)256 * 128 + (size_t)256 * NP + (warp - 4) * 8;
         for (int i = 0; i < 6; ++i) dT[i] = (float)tph[i];
       }
       // ---- reward = -(closed tour length - fixed edge)   (train_path_solver.py:109-149)
@@ -624,8 +767,8 @@ size_t decode_tc_dbg_floats(int N) {
 
 template <bool LOGITS, bool DEBUG>
 static int launch_tcd(const TcdArgs& a, int Bp, cudaStream_t s) {
-  const size_t smem = (size_t)2 * TCD_TILE_STAGING + (size_t)TCD_STAGES * tcd_stage_bytes(a.NP) +
-                      (size_t)a.NP * 4 + TB_COUNT * 8 + 16;
+  const size_t smem = (size_t)2 * TCD_TILE_STAGING + (size_t)2 * TCD_STAGES * TCD_STAGE +
+                      (size_t)a.NP * 4 + 2 * TB_PER_TILE * 8 + 16;
   if (smem > 227 * 1024) {
     set_error("decode_tc: N=%d needs %zu bytes of shared memory", a.N, smem);
     return HTSP_ERR_UNSUPPORTED;
@@ -658,7 +801,7 @@ int launch_decode_tc(const float* x, const float* proj, const float* qfix, const
   a.src = src; a.tgt = tgt; a.first = first; a.forced_pi = forced_pi;
   a.pi = pi; a.reward = reward; a.logits_out = logits_out; a.dbg = dbg;
   a.N = N; a.NP = NP; a.G = G; a.fast = (mode == HTSP_MODE_TC_FAST) ? 1 : 0; a.dbg_step = dbg_step;
-  if (dbg != nullptr) return launch_tcd<true, true>(a, Bp, s);
+  if (dbg != nullptr) return launch_tcd<false, true>(a, Bp, s);
   if (logits_out != nullptr) return launch_tcd<true, false>(a, Bp, s);
   return launch_tcd<false, false>(a, Bp, s);
 }
