@@ -26,11 +26,12 @@
 
 namespace htsp {
 
-constexpr int TCD_THREADS = 384;          // 12 warps: producer, 2 MMA issuers, (idle), 2 x 4 softmax warps
+constexpr int TCD_THREADS = 640;          // 20 warps: producer, 2 MMA issuers, (idle), 2 tiles x 2 halves x 4 softmax warps
 constexpr int TCD_STAGES = 3;
 constexpr int TCD_STAGE = 16384;          // ring stage (one key group of a K block, or one head of V^T)
 constexpr int TCD_TILE_STAGING = 65536;   // per row tile: [hi k0-63 | hi k64-127 | lo k0-63 | lo k64-127], 16 KB each
-constexpr int TCD_OCOL = 448;             // O accumulators: column 448 + 32*tile + 16*(head&1)
+constexpr int TCD_OCOL = 448;             // O accumulators: column 448 + 32*tile + 16*half (split-K partials)
+constexpr int TCD_XCOL = 416;             // exchange columns: 416 + 16*tile: [head&1][half]{m,l} (8), chosen node (1)
 constexpr float kTcdInvSqrtH = 0.08838834764831845f;   // 1/sqrt(128)
 constexpr float kTcdFloor = -1e30f;       // initial softmax shift (integer valued, any real score lifts it)
 constexpr float kTcdThresh = 32768.f;     // chunk sum above this => some p may leave fp16 range: move the shift
@@ -137,8 +138,8 @@ struct TcdArgs {
 };
 
 // barrier slots of one row tile
-enum { TB_FULL = 0, TB_EMPTY = 3, TB_QFULL = 6, TB_SFULL = 7, TB_PFULL = 8, TB_OFULL = 9, TB_OREADY = 11,
-       TB_UFULL = 12, TB_PER_TILE = 13 };
+enum { TB_FULL = 0, TB_EMPTY = 3, TB_QFULL = 6, TB_SFULL = 7, TB_PFULL = 8, TB_OFULL = 9, TB_OREADY = 10,
+       TB_UFULL = 11, TB_PER_TILE = 12 };
 
 __device__ __forceinline__ unsigned tcd_word(const unsigned (&vis)[7], int w) {
   unsigned r = vis[0];
@@ -239,9 +240,8 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
       for (int s = 0; s < TCD_STAGES; ++s) { tc::mbar_init(bt + 8 * (TB_FULL + s), 1); tc::mbar_init(bt + 8 * (TB_EMPTY + s), 1); }
       tc::mbar_init(bt + 8 * TB_QFULL, warps_t);
       tc::mbar_init(bt + 8 * TB_SFULL, 1);
-      tc::mbar_init(bt + 8 * TB_PFULL, warps_t);
+      tc::mbar_init(bt + 8 * TB_PFULL, 2 * warps_t);
       tc::mbar_init(bt + 8 * TB_OFULL, 1);
-      tc::mbar_init(bt + 8 * (TB_OFULL + 1), 1);
       tc::mbar_init(bt + 8 * TB_OREADY, warps_t);
       tc::mbar_init(bt + 8 * TB_UFULL, 1);
     }
@@ -263,8 +263,8 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
   const uint32_t tmem_base = *tmem_slot;
 
   // register budget: the role warpgroup (warps 0-3) hands registers to the two softmax warpgroups
-  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
-  else asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
+  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
 
   if (warp == 0) {
     // ================================================================== operand producer (both row tiles)
@@ -361,19 +361,21 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
               const uint32_t sv = take();
               tc::mbar_wait(BAR(TB_PFULL), (step * NH + h) & 1);
               tc::fence_after();
-              const uint32_t dO = tmem_base + (uint32_t)(TCD_OCOL + 32 * t + 16 * e);
+              const uint32_t dO = tmem_base + (uint32_t)(TCD_OCOL + 32 * t);
               const uint32_t vb = (ring0 + sv * TCD_STAGE) >> 4;
+              const int n0 = nks >> 1;                       // split-K: chunks [0,n0) -> O_0, [n0,nks) -> O_1
 #pragma unroll
               for (int ks = 0; ks < 14; ++ks) {
                 if (ks < nks && leader) {
                   const uint32_t v_hi = vb + (ks >> 2) * 256 + (ks & 3) * 2, v_lo = v_hi + 128;
                   const uint32_t p_hi = dS + 16 * ks, p_lo = p_hi + 8;
-                  tc::mma_ts_lo(dO, p_hi, v_hi, idO, ks > 0);
-                  tc::mma_ts_lo(dO, p_hi, v_lo, idO, 1);
-                  tc::mma_ts_lo(dO, p_lo, v_hi, idO, 1);
+                  const uint32_t d = dO + (ks >= n0 ? 16 : 0);
+                  tc::mma_ts_lo(d, p_hi, v_hi, idO, (ks != 0 && ks != n0) ? 1u : 0u);
+                  tc::mma_ts_lo(d, p_hi, v_lo, idO, 1);
+                  tc::mma_ts_lo(d, p_lo, v_hi, idO, 1);
                 }
               }
-              if (leader) tc::commit(BAR(TB_OFULL + e));
+              if (leader) tc::commit(BAR(TB_OFULL));
               __syncwarp();
               release(sv);
             }
@@ -408,7 +410,14 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
     }
   } else if (warp >= 4) {
     // ================================================================== softmax / state warps
-    const int t = (warp - 4) >> 2, q = warp & 3;
+    // Two warps share every 32-row lane quarter of a tile ("split-K"): the primary (half 0) owns key
+    // chunks [0,n0), the secondary (half 1) chunks [n0,nch).  Each runs its own online softmax
+    // (own shift m, own row sum l) and its P V partial lands in its own accumulator O_half; the
+    // primary merges the two partials when it drains them (O = sum_i 2^(m_i-M) O_i / sum_i 2^(m_i-M) l_i).
+    // Only the primary carries the rollout state machine; it publishes the chosen node through a
+    // TMEM exchange column so that the secondary can keep its copy of the visited mask.
+    const int sw = warp - 4;
+    const int t = sw >> 3, half = (sw >> 2) & 1, q = warp & 3;
     const int rows_t = min(128, G - 128 * t);
     if (q * 32 < rows_t) {
       const uint32_t bt = bar0 + 8u * (uint32_t)(t * TB_PER_TILE);
@@ -420,11 +429,13 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
       const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
       const uint32_t tS = tmem_base + lane_addr + (uint32_t)(t * NP);
       const uint32_t tO = tmem_base + lane_addr + (uint32_t)(TCD_OCOL + 32 * t);
+      const uint32_t tX = tmem_base + lane_addr + (uint32_t)(TCD_XCOL + 16 * t);
       unsigned char* stg = staging + t * TCD_TILE_STAGING;
       const int src = A.src[b], tgt = A.tgt[b];
       const int first = A.first[gc];
       int32_t* pirow = A.pi + ((size_t)b * G + gc) * N;
-      const float4 qfix4 = __ldg((const float4*)(A.qfix + (size_t)b * H) + lane);
+      const int nch = NP >> 4, n0 = nch >> 1;
+      const int c_lo = half ? n0 : 0, c_hi = half ? nch : n0;
 
       unsigned vis[7];
 #pragma unroll
@@ -437,38 +448,159 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
 #pragma unroll
         for (int w = 0; w < 7; ++w) vis[w] |= ((a >> 5) == w) ? (1u << (a & 31)) : 0u;
       };
-      // visit(a) with source<->target coupling (train_path_solver.py:45-66)
+      // visit(a) with source<->target coupling (train_path_solver.py:45-66); only the primary records pi
       auto visit = [&](int a) {
-        if (valid) pirow[cnt] = a;
+        if (valid && half == 0) pirow[cnt] = a;
         mark(a);
         cnt++;
         cur = a;
         const int partner = (a == src) ? tgt : ((a == tgt) ? src : -1);
         if (partner >= 0) {
-          if (valid) pirow[cnt] = partner;
+          if (valid && half == 0) pirow[cnt] = partner;
           mark(partner);
           cnt++;
           cur = partner;
         }
       };
+
+      // DEBUG builds: cycles this warp spends per phase (0 wait S, 1 softmax, 2 wait O + drain,
+      // 3 wait U, 4 arg-max, 5 state + query gather), written behind the dumps
+      long long tph[6] = {0, 0, 0, 0, 0, 0};
+      long long tlast = DEBUG ? clock64() : 0;
+      auto tick = [&](int ph) {
+        if (DEBUG) {
+          const long long now = clock64();
+          tph[ph] += now - tlast;
+          tlast = now;
+        }
+      };
+
+      // ---- online softmax of this warp's key chunks of head h; publishes (m, l) and arrives on PFULL
+      auto softmax_pass = [&](int step, int h) {
+        float m = valid ? kTcdFloor : 0.f, l = 0.f;
+        uint32_t sA[32];             // only the first 16 entries are used (16-key chunks)
+        // one 16-key chunk at column c0: mask, 2^(s-m), row sum, fp16 hi/lo split, store in place;
+        // per 16 keys: 8 columns of hi pairs, then 8 columns of lo pairs (one MMA k-step each)
+        auto chunk = [&](int c0, uint32_t (&s)[32], unsigned bits) {
+          float p[16];
+          if (DEBUG && b == 0 && step == A.dbg_step) {
+            float* dS = A.dbg + ((size_t)(t * 8 + h) * 128 + row) * NP + c0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dS[j] = __uint_as_float(s[j]);
+          }
+          float tv[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) tv[j] = ((bits >> j) & 1u) ? -INFINITY : __uint_as_float(s[j]);
+          float csum;
+          auto expo = [&]() {
+            float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+            const float2 nm = make_float2(-m, -m);
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float2 d0 = __fadd2_rn(make_float2(tv[j], tv[j + 1]), nm);
+              const float2 d1 = __fadd2_rn(make_float2(tv[j + 2], tv[j + 3]), nm);
+              p[j] = ex2_approx(d0.x);
+              p[j + 1] = ex2_approx(d0.y);
+              p[j + 2] = ex2_approx(d1.x);
+              p[j + 3] = ex2_approx(d1.y);
+              acc0 = __fadd2_rn(acc0, make_float2(p[j], p[j + 1]));
+              acc1 = __fadd2_rn(acc1, make_float2(p[j + 2], p[j + 3]));
+            }
+            acc0 = __fadd2_rn(acc0, acc1);
+            csum = acc0.x + acc0.y;
+          };
+          expo();
+          const bool need = valid && !(csum <= kTcdThresh);
+          if (__any_sync(0xffffffffu, need)) {
+            // move the shift (to an integer, so rescaling earlier chunks by 2^(m-m') is exact)
+            float cm = tv[0];
+#pragma unroll
+            for (int j = 1; j < 16; ++j) cm = fmaxf(cm, tv[j]);
+            const float m_new = (need && cm > m) ? ceilf(cm) : m;
+            const float alpha = ex2_approx(m - m_new);
+            if (__any_sync(0xffffffffu, (m_new != m) && (l > 0.f))) {
+              tc::st_wait();
+              for (int cc = 16 * c_lo; cc < c0; cc += 16) {
+                uint32_t r[16];
+                tc::ld16(tS + cc, r);
+                tc::ld16_wait(r);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  float2 f = __half22float2(*reinterpret_cast<__half2*>(&r[j]));
+                  __half2 hh = __floats2half2_rn(f.x * alpha, f.y * alpha);
+                  r[j] = *reinterpret_cast<uint32_t*>(&hh);
+                }
+                tc::st16(tS + cc, r);
+              }
+            }
+            l *= alpha;
+            m = m_new;
+            expo();
+          }
+          l += csum;
+          uint32_t out[32];
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) split2(p[j], p[j + 1], out[j >> 1], out[8 + (j >> 1)]);
+          tst<16>(tS + c0, out);
+        };
+        // 16-key chunks; four warps per scheduler hide the TMEM load latency
+#pragma unroll 1
+        for (int c = c_lo; c < c_hi; ++c) {
+          tld<16>(tS + 16 * c, sA);
+          const unsigned bits = (tcd_word(vis, c >> 1) >> ((c & 1) * 16)) & 0xffffu;
+          tld_wait16(sA);
+          chunk(16 * c, sA, bits);
+        }
+        // publish (m, l) of this half for the merge at drain time
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(tX + (h & 1) * 4 + half * 2),
+                     "r"(__float_as_uint(m)), "r"(__float_as_uint(l))
+                     : "memory");
+        tc::st_wait();
+        tc::fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(BAR(TB_PFULL));
+      };
+
+      if (half == 1) {
+        // ================================================================ secondary: softmax only
+        visit(first);
+        for (int step = 0; step < n_steps; ++step) {
+#pragma unroll 1
+          for (int h = 0; h < NH; ++h) {
+            tc::mbar_wait(BAR(TB_SFULL), (step * NH + h) & 1);
+            tc::fence_after();
+            if (h == 0 && step > 0) {     // the node the primary chose at the end of the previous step
+              uint32_t a;
+              asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(a) : "r"(tX + 8) : "memory");
+              asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(a)::"memory");
+              visit((int)a);
+            }
+            tick(0);
+            softmax_pass(step, h);
+            tick(1);
+          }
+        }
+      } else {
+      // ================================================================== primary
+      const float4 qfix4 = __ldg((const float4*)(A.qfix + (size_t)b * H) + lane);
       // query rows of this warp's 32 starts -> A tile (fp16 hi/lo, K-major SWIZZLE_128B):
       // q = ((q_graph+q_source+q_target) + q_first) + q_last (models.py:413), 1/sqrt(dk)*log2(e) folded in.
-      // Lane l carries columns 4l..4l+3 of every row; 8 rows (16 L2 loads) are in flight at a time.
+      // Lane l carries columns 4l..4l+3 of every row; 4 rows (8 L2 loads) are in flight at a time.
       auto gather_q = [&]() {
         const uint32_t sub = (uint32_t)(lane >> 4) * 16384u + (uint32_t)(lane & 1) * 8u;
         const uint32_t chunk = (uint32_t)(lane & 15) >> 1;
         const int nrows = min(32, rows_t - q * 32);
 #pragma unroll 1
-        for (int r0 = 0; r0 < nrows; r0 += 8) {
-          float4 ql[8], qf[8];
+        for (int r0 = 0; r0 < nrows; r0 += 4) {
+          float4 ql[4], qf[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 4; ++i) {
             const int cr = __shfl_sync(0xffffffffu, cur, r0 + i), fr = __shfl_sync(0xffffffffu, first, r0 + i);
             ql[i] = __ldg((const float4*)(projb + (size_t)cr * PROJ + 2 * H) + lane);
             qf[i] = __ldg((const float4*)(projb + (size_t)fr * PROJ + 3 * H) + lane);
           }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 4; ++i) {
             if (r0 + i < nrows) {
               uint32_t h0, l0, h1, l1;
               split2(((qfix4.x + qf[i].x) + ql[i].x) * kScoreScale, ((qfix4.y + qf[i].y) + ql[i].y) * kScoreScale, h0, l0);
@@ -488,29 +620,35 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
       visit(first);
       gather_q();
 
-      float l_prev = 1.f;
-      // DEBUG builds: cycles this warp spends per phase (0 wait S, 1 softmax, 2 wait O + drain,
-      // 3 wait U, 4 arg-max, 5 state + query gather), written behind the dumps
-      long long tph[6] = {0, 0, 0, 0, 0, 0};
-      long long tlast = DEBUG ? clock64() : 0;
-      auto tick = [&](int ph) {
-        if (DEBUG) {
-          const long long now = clock64();
-          tph[ph] += now - tlast;
-          tlast = now;
-        }
-      };
-      // drain O_h: TMEM -> /l -> fp16 hi/lo -> A tile columns 16h..16h+15 (the consumed Q_h slot)
-      auto drain_o = [&](int step, int h, float l) {
-        tc::mbar_wait(BAR(TB_OFULL + (h & 1)), (step * 4 + (h >> 1)) & 1);
+      // drain O_h: merge the two split-K partials, /l -> fp16 hi/lo -> A tile columns 16h..16h+15
+      // (the consumed Q_h slot)
+      auto drain_o = [&](int step, int h) {
+        tc::mbar_wait(BAR(TB_OFULL), (step * NH + h) & 1);
         tc::fence_after();
-        uint32_t o[16];
-        tc::ld16(tO + 16 * (h & 1), o);
-        tc::ld16_wait(o);
-        const float inv = 1.f / l;
+        uint32_t oa[16], ob[16], x0, x1, x2, x3;
+        tc::ld16(tO, oa);
+        tc::ld16(tO + 16, ob);
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)
+                     : "r"(tX + (h & 1) * 4)
+                     : "memory");
+        tc::ld16_wait(oa);
+        tc::ld16_wait(ob);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(x0), "+r"(x1), "+r"(x2), "+r"(x3)::"memory");
+        const float ma = __uint_as_float(x0), la = __uint_as_float(x1);
+        const float mb = __uint_as_float(x2), lb = __uint_as_float(x3);
+        const float M = fmaxf(ma, mb);
+        // a half without a finite score (or without chunks) has l = 0 and contributes nothing
+        const float sa = (n0 > 0 && la > 0.f) ? ex2_approx(ma - M) : 0.f;
+        const float sb = (lb > 0.f) ? ex2_approx(mb - M) : 0.f;
+        const float inv = 1.f / (la * sa + lb * sb);
+        const float wa = sa * inv, wb = sb * inv;
         float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(o[j]) * inv;
+        for (int j = 0; j < 16; ++j) {
+          const float a = (sa > 0.f) ? __uint_as_float(oa[j]) * wa : 0.f;
+          v[j] = (sb > 0.f) ? fmaf(__uint_as_float(ob[j]), wb, a) : a;
+        }
         if (DEBUG && b == 0 && step == A.dbg_step) {
           float* dO = A.dbg + (size_t)2 * 8 * 128 * NP + (size_t)(t * 128 + row) * 128 + 16 * h;
 #pragma unroll
@@ -534,113 +672,14 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
           tc::mbar_wait(BAR(TB_SFULL), (step * NH + h) & 1);
           tc::fence_after();
           tick(0);
-          float m = valid ? kTcdFloor : 0.f, l = 0.f;
-          uint32_t sA[32], sB[32];     // only the first 16 entries are used (16-key chunks)
-          float pA[32], pB[32];
-          // fp16 hi/lo of the probabilities of a finished chunk -> TMEM, in place over its scores;
-          // per 16 keys: 8 columns of hi pairs, then 8 columns of lo pairs (one MMA k-step each)
-          auto finish = [&](auto wtag, int c0, const float (&p)[32]) {
-            constexpr int W = decltype(wtag)::value;
-            uint32_t out[32];
-#pragma unroll
-            for (int j = 0; j < W; j += 2)
-              split2(p[j], p[j + 1], out[(j >> 4) * 16 + ((j & 15) >> 1)], out[(j >> 4) * 16 + 8 + ((j & 15) >> 1)]);
-            tst<W>(tS + c0, out);
-          };
-          // one W-key chunk at column c0: mask, 2^(s-m), row sum.  The fp16 split + store of the PREVIOUS
-          // chunk (WP keys at column c0-WP) is issued in the same basic block as this chunk's exponentials
-          // so that the ALU work overlaps the MUFU stream.
-          auto chunk = [&](auto wtag, auto wptag, int c0, uint32_t (&s)[32], unsigned bits, float (&p)[32],
-                           const float (&pprev)[32]) {
-            constexpr int W = decltype(wtag)::value;
-            constexpr int WP = decltype(wptag)::value;
-            if (DEBUG && b == 0 && step == A.dbg_step) {
-              float* dS = A.dbg + ((size_t)(t * 8 + h) * 128 + row) * NP + c0;
-#pragma unroll
-              for (int j = 0; j < W; ++j) dS[j] = __uint_as_float(s[j]);
-            }
-            float tv[W];
-#pragma unroll
-            for (int j = 0; j < W; ++j) tv[j] = ((bits >> j) & 1u) ? -INFINITY : __uint_as_float(s[j]);
-            float csum;
-            auto expo = [&]() {
-              float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-              const float2 nm = make_float2(-m, -m);
-#pragma unroll
-              for (int j = 0; j < W; j += 4) {
-                const float2 d0 = __fadd2_rn(make_float2(tv[j], tv[j + 1]), nm);
-                const float2 d1 = __fadd2_rn(make_float2(tv[j + 2], tv[j + 3]), nm);
-                p[j] = ex2_approx(d0.x);
-                p[j + 1] = ex2_approx(d0.y);
-                p[j + 2] = ex2_approx(d1.x);
-                p[j + 3] = ex2_approx(d1.y);
-                acc0 = __fadd2_rn(acc0, make_float2(p[j], p[j + 1]));
-                acc1 = __fadd2_rn(acc1, make_float2(p[j + 2], p[j + 3]));
-              }
-              acc0 = __fadd2_rn(acc0, acc1);
-              csum = acc0.x + acc0.y;
-            };
-            expo();
-            if (WP > 0) finish(wptag, c0 - WP, pprev);
-            const bool need = valid && !(csum <= kTcdThresh);
-            if (__any_sync(0xffffffffu, need)) {
-              // move the shift (to an integer, so rescaling earlier chunks by 2^(m-m') is exact)
-              float cm = tv[0];
-#pragma unroll
-              for (int j = 1; j < W; ++j) cm = fmaxf(cm, tv[j]);
-              const float m_new = (need && cm > m) ? ceilf(cm) : m;
-              const float alpha = ex2_approx(m - m_new);
-              if (__any_sync(0xffffffffu, (m_new != m) && (l > 0.f))) {
-                tc::st_wait();
-                for (int cc = 0; cc < c0; cc += 16) {
-                  uint32_t r[16];
-                  tc::ld16(tS + cc, r);
-                  tc::ld16_wait(r);
-#pragma unroll
-                  for (int j = 0; j < 16; ++j) {
-                    float2 f = __half22float2(*reinterpret_cast<__half2*>(&r[j]));
-                    __half2 hh = __floats2half2_rn(f.x * alpha, f.y * alpha);
-                    r[j] = *reinterpret_cast<uint32_t*>(&hh);
-                  }
-                  tc::st16(tS + cc, r);
-                }
-              }
-              l *= alpha;
-              m = m_new;
-              expo();
-            }
-            l += csum;
-          };
-          using W0 = std::integral_constant<int, 0>;
-          using W16 = std::integral_constant<int, 16>;
-          // software pipeline over 16-key chunks: the TMEM load of chunk c+1 is in flight while chunk c
-          // is processed, and chunk c-1 is split/stored under chunk c's exponentials
-          const int nch = NP >> 4;
-          auto stepc = [&](int c, uint32_t (&curb)[32], uint32_t (&nxt)[32], float (&p)[32], const float (&pprev)[32]) {
-            tld_wait16(curb);
-            if (c + 1 < nch) tld<16>(tS + 16 * (c + 1), nxt);
-            const unsigned bits = (tcd_word(vis, c >> 1) >> ((c & 1) * 16)) & 0xffffu;
-            if (c == 0) chunk(W16{}, W0{}, 0, curb, bits, p, pprev);
-            else chunk(W16{}, W16{}, 16 * c, curb, bits, p, pprev);
-          };
-          tld<16>(tS, sA);
-#pragma unroll 1
-          for (int c = 0; c < nch; c += 2) {
-            stepc(c, sA, sB, pA, pB);
-            if (c + 1 < nch) stepc(c + 1, sB, sA, pB, pA);
-          }
-          if (nch & 1) finish(W16{}, 16 * (nch - 1), pA);
-          else finish(W16{}, 16 * (nch - 1), pB);
-          tc::st_wait();
-          tc::fence_before();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(BAR(TB_PFULL));
-          tick(1);
-          if (h > 0) drain_o(step, h - 1, l_prev);
-          l_prev = l;
+          // the previous head's partials must be out of the O accumulators before this head's P is
+          // published (P V of head h overwrites them): drain first, then compute
+          if (h > 0) drain_o(step, h - 1);
           tick(2);
+          softmax_pass(step, h);
+          tick(1);
         }
-        drain_o(step, NH - 1, l_prev);
+        drain_o(step, NH - 1);
         tc::fence_async_smem();
         tc::fence_before();
         __syncwarp();
@@ -668,7 +707,6 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
 #pragma unroll
           for (int j = 0; j < 16; ++j) { bj[j] = -INFINITY; cj[j] = 0; }
           uint32_t u[32], u2[32];
-          const int nch = NP >> 4;
           auto body = [&](int c, uint32_t (&uu)[32], uint32_t (&nx)[32]) {
             tld_wait16(uu);
             if (c + 1 < nch) tld<16>(tS + 16 * (c + 1), nx);
@@ -715,16 +753,14 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
           if (__any_sync(0xffffffffu, valid && best > 3.0f)) pass(std::true_type{});
         }
         tick(4);
-        // ---- state update (train_path_solver.py:45-72)
+        // ---- state update (train_path_solver.py:45-72); the chosen node goes to the secondary warp
         const int a = A.forced_pi ? A.forced_pi[((size_t)b * G + gc) * N + cnt] : idx;
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tX + 8), "r"((uint32_t)a) : "memory");
         visit(a);
+        tc::st_wait();
         tc::fence_before();
         if (step + 1 < n_steps) gather_q();
         tick(5);
-      }
-      if (DEBUG && b == 0 && lane == 0) {
-        float* dT = A.dbg + (size_t)2 * 8 * 128 * NP + (size_t)256 * 128 + (size_t)256 * NP + (warp - 4) * 8;
-        for (int i = 0; i < 6; ++i) dT[i] = (float)tph[i];
       }
       // ---- reward = -(closed tour length - fixed edge)   (train_path_solver.py:109-149)
       if (valid) {
@@ -743,6 +779,11 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
         const float fixed = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
         A.reward[(size_t)b * G + g] = -(len - fixed);
       }
+      }   // primary
+      if (DEBUG && b == 0 && lane == 0) {
+        float* dT = A.dbg + (size_t)2 * 8 * 128 * NP + (size_t)256 * 128 + (size_t)256 * NP + sw * 8;
+        for (int i = 0; i < 6; ++i) dT[i] = (float)tph[i];
+      }
     }
   }
   tc::fence_before();
@@ -758,11 +799,11 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
 // ------------------------------------------------------------------------------------------
 static int tcd_np_of(int N) { return (N + 15) / 16 * 16; }
 
-bool decode_tc_supported(int N, int G) { return tcd_np_of(N) <= 224 && G <= 256 && N >= 3; }
+bool decode_tc_supported(int N, int G) { return tcd_np_of(N) <= 208 && G <= 256 && N >= 3; }
 size_t decode_tc_pack_bytes(int Bp, int N) { return align_up((size_t)Bp * tcd_img_bytes(tcd_np_of(N)), 256) + 1024; }
 size_t decode_tc_dbg_floats(int N) {
   const int NP = tcd_np_of(N);
-  return (size_t)2 * 8 * 128 * NP + (size_t)256 * 128 + (size_t)256 * NP + 64;
+  return (size_t)2 * 8 * 128 * NP + (size_t)256 * 128 + (size_t)256 * NP + 256;
 }
 
 template <bool LOGITS, bool DEBUG>

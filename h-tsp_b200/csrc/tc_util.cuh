@@ -32,7 +32,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
-    if (spin > (1u << 24)) __trap();
+    if (spin > (1u << 21)) __trap();
   }
 }
 // one lane of a converged warp (the others get false)
