@@ -42,13 +42,13 @@ constexpr float kTcdThresh = 32768.f;     // chunk sum above this => some p may 
 //                                                blocks of 64 keys (4 KB each)
 //   K2 hi cols 0-63, K2 hi cols 64-127, K2 lo cols 0-63, K2 lo cols 64-127: [NP keys x 64 halfs] each
 // every block is K-major SWIZZLE_128B (rows of 128 bytes).  Key-major blocks (KA, K2) are streamed in
-// one or two key groups ([0,K0) and [K0,NP), K0 = 112 when NP > 128) so that a ring stage is 16 KB.
+// two key halves ([0,K0) and [K0,NP), K0 = 16*floor(NP/32)) so that a ring stage is at most 16 KB.
 __host__ __device__ inline int tcd_kb(int NP) { return (NP + 63) / 64; }
 __host__ __device__ inline size_t tcd_szk(int NP) { return (size_t)NP * 128; }
 __host__ __device__ inline size_t tcd_szvh(int NP) { return (size_t)tcd_kb(NP) * 4096; }
 __host__ __device__ inline size_t tcd_pair_bytes(int NP) { return tcd_szk(NP) + 2 * tcd_szvh(NP); }
 __host__ __device__ inline size_t tcd_img_bytes(int NP) { return 4 * tcd_pair_bytes(NP) + 4 * tcd_szk(NP); }
-__host__ __device__ inline int tcd_k0(int NP) { return NP > 128 ? 112 : NP; }
+__host__ __device__ inline int tcd_k0(int NP) { return 16 * ((NP >> 4) >> 1); }
 
 __device__ __forceinline__ void tcd_split8(const float* v, uint4& hi, uint4& lo) {
   __half2 h[4], l[4];
@@ -138,8 +138,8 @@ struct TcdArgs {
 };
 
 // barrier slots of one row tile
-enum { TB_FULL = 0, TB_EMPTY = 3, TB_QFULL = 6, TB_SFULL = 7, TB_PFULL = 8, TB_OFULL = 9, TB_OREADY = 10,
-       TB_UFULL = 11, TB_PER_TILE = 12 };
+enum { TB_FULL = 0, TB_EMPTY = 3, TB_QFULL = 6, TB_SFULL = 7, TB_PFULL = 9, TB_OFULL = 11, TB_OREADY = 13,
+       TB_UFULL = 14, TB_PER_TILE = 15 };   // SFULL / PFULL / OFULL: one per key half
 
 __device__ __forceinline__ unsigned tcd_word(const unsigned (&vis)[7], int w) {
   unsigned r = vis[0];
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
   const int N = A.N, NP = A.NP, G = A.G;
   const int n_steps = N - 2;
   const int n_tiles = G > 128 ? 2 : 1;
-  const int K0 = tcd_k0(NP), K1 = NP - K0, ng = K1 > 0 ? 2 : 1;
+  const int K0 = tcd_k0(NP), K1 = NP - K0;     // key halves A = [0,K0), B = [K0,NP): one softmax warp each
   const int nks = NP >> 4;                                               // k16 steps of P V
 
   unsigned char* staging = smem;                                         // 2 x 64 KB
@@ -240,8 +240,11 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
       for (int s = 0; s < TCD_STAGES; ++s) { tc::mbar_init(bt + 8 * (TB_FULL + s), 1); tc::mbar_init(bt + 8 * (TB_EMPTY + s), 1); }
       tc::mbar_init(bt + 8 * TB_QFULL, warps_t);
       tc::mbar_init(bt + 8 * TB_SFULL, 1);
-      tc::mbar_init(bt + 8 * TB_PFULL, 2 * warps_t);
+      tc::mbar_init(bt + 8 * (TB_SFULL + 1), 1);
+      tc::mbar_init(bt + 8 * TB_PFULL, warps_t);            // half A: its softmax warps
+      tc::mbar_init(bt + 8 * (TB_PFULL + 1), 2 * warps_t);  // half B: its softmax warps + the primaries' "O drained"
       tc::mbar_init(bt + 8 * TB_OFULL, 1);
+      tc::mbar_init(bt + 8 * (TB_OFULL + 1), 1);
       tc::mbar_init(bt + 8 * TB_OREADY, warps_t);
       tc::mbar_init(bt + 8 * TB_UFULL, 1);
     }
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
     // ================================================================== operand producer (both row tiles)
     if (lane == 0) {
       const size_t szk = tcd_szk(NP), szvh = tcd_szvh(NP), pair = tcd_pair_bytes(NP);
-      const int per_step = 4 * (ng + 2) + 4 * ng;          // ring stages one tile consumes per decode step
+      const int per_step = 24;                             // ring stages one tile consumes per decode step
       const uint32_t total = (uint32_t)n_steps * (uint32_t)per_step;
       uint32_t it[2] = {0, 0};
       int rem = n_tiles;
@@ -282,16 +285,17 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
           const uint32_t bt = bar0 + 8u * (uint32_t)(t * TB_PER_TILE);
           const uint32_t s = it[t] % TCD_STAGES, use = it[t] / TCD_STAGES;
           if (!tc::mbar_test(bt + 8 * (TB_EMPTY + s), (use & 1) ^ 1)) continue;
-          // i-th stage of the step: per head pair [KA g0, (KA g1), V 2p, V 2p+1], then K2 blocks by key group
+          // i-th stage of the step: per head pair p [K_p half A, K_p half B, V 2p, V 2p+1], then the four K2
+          // blocks by key half
           const int i = (int)(it[t] % (uint32_t)per_step);
           size_t off;
           uint32_t bytes;
-          if (i < 4 * (ng + 2)) {
-            const int p = i / (ng + 2), j = i % (ng + 2);
-            if (j < ng) { off = (size_t)p * pair + (j ? (size_t)K0 * 128 : 0); bytes = (uint32_t)(j ? K1 : K0) * 128u; }
-            else { off = (size_t)p * pair + szk + (size_t)(j - ng) * szvh; bytes = (uint32_t)szvh; }
+          if (i < 16) {
+            const int p = i >> 2, j = i & 3;
+            if (j < 2) { off = (size_t)p * pair + (j ? (size_t)K0 * 128 : 0); bytes = (uint32_t)(j ? K1 : K0) * 128u; }
+            else { off = (size_t)p * pair + szk + (size_t)(j - 2) * szvh; bytes = (uint32_t)szvh; }
           } else {
-            const int i2 = i - 4 * (ng + 2), blk = i2 / ng, gi = i2 % ng;
+            const int i2 = i - 16, blk = i2 >> 1, gi = i2 & 1;
             off = 4 * pair + (size_t)blk * szk + (gi ? (size_t)K0 * 128 : 0);
             bytes = (uint32_t)(gi ? K1 : K0) * 128u;
           }
@@ -315,96 +319,148 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
       {
         // ================================================================== MMA issuer of tile t
         // (the whole warp runs the control flow so that addresses stay in uniform registers; one
-        // elected lane issues the tcgen05 instructions)
-        const bool leader = tc::elect_one();
-        const uint32_t idK0 = tc::idesc_f16(K0), idK1 = tc::idesc_f16(K1 > 0 ? K1 : 16), idO = tc::idesc_f16(16);
+        // elected lane issues the tcgen05 instructions).  The two key halves X = A, B of a tile are
+        // independent sub-pipelines: as soon as half X has published P_h^X the issuer runs its turn
+        //   O_X = P_h^X V_h[keys of X]   and   S_{h+1}^X = Q_{h+1} K_{h+1}[keys of X]^T
+        // without waiting for the other half.
+        const uint32_t idK[2] = {tc::idesc_f16(K0), tc::idesc_f16(K1)};
+        const uint32_t idO = tc::idesc_f16(16);
         const uint32_t stg = tc::smem_u32(staging) + t * TCD_TILE_STAGING;
         const uint32_t dS = tmem_base + (uint32_t)(t * NP);
+        const uint32_t dO = tmem_base + (uint32_t)(TCD_OCOL + 32 * t);
+        const int n0 = nks >> 1;
         uint32_t it = 0;
+        // DEBUG builds: cycles of this issuer per phase (0 ring-stage wait, 1 idle polling for P,
+        // 2 P V / S turns, 3 wait Q, 4 wait O staged, 5 logits issue)
+        long long tph[6] = {0, 0, 0, 0, 0, 0};
+        long long tlast = DEBUG ? clock64() : 0;
+        auto tick = [&](int ph) {
+          if (DEBUG) {
+            const long long now = clock64();
+            tph[ph] += now - tlast;
+            tlast = now;
+          }
+        };
         auto take = [&]() {                      // next ring stage, in stream order
           const uint32_t s = it % TCD_STAGES, use = it / TCD_STAGES;
+          tick(2);
           tc::mbar_wait(BAR(TB_FULL + s), use & 1);
           tc::fence_after();
+          tick(0);
           ++it;
           return s;
         };
-        auto release = [&](uint32_t s) { if (leader) tc::commit(BAR(TB_EMPTY + s)); };
-        for (int step = 0; step < n_steps; ++step) {
-          for (int p = 0; p < 4; ++p) {
-            const uint32_t sk0 = take(), sk1 = (ng == 2) ? take() : 0u;
-            for (int e = 0; e < 2; ++e) {
-              const int h = 2 * p + e;
-              if (h == 0) {
-                tc::mbar_wait(BAR(TB_QFULL), step & 1);
-                tc::fence_after();
-              }
-              // S_h = Q_h K_h^T into TMEM columns [t*NP, t*NP+NP), one MMA group per key group
-              const uint32_t a_hi = (stg >> 4) + (h >> 2) * 1024 + (h & 3) * 2, a_lo = a_hi + 2048;
-              for (int gi = 0; gi < ng; ++gi) {
-                const uint32_t b_hi = ((ring0 + (gi ? sk1 : sk0) * TCD_STAGE) >> 4) + e * 4, b_lo = b_hi + 2;
-                const uint32_t d = dS + (gi ? K0 : 0), id = gi ? idK1 : idK0;
-                if (leader) {
-                  tc::mma_ss_lo(d, a_hi, b_hi, id, 0);
-                  if (!A.fast) {
-                    tc::mma_ss_lo(d, a_hi, b_lo, id, 1);
-                    tc::mma_ss_lo(d, a_lo, b_hi, id, 1);
-                  }
-                }
-              }
-              if (leader) tc::commit(BAR(TB_SFULL));
-              __syncwarp();
-              if (e == 1) {
-                release(sk0);
-                if (ng == 2) release(sk1);
-              }
-              // O_h = P_h V_h: A = P hi/lo in TMEM (8 + 8 columns per 16 keys), B = V^T of head h
-              const uint32_t sv = take();
-              tc::mbar_wait(BAR(TB_PFULL), (step * NH + h) & 1);
-              tc::fence_after();
-              const uint32_t dO = tmem_base + (uint32_t)(TCD_OCOL + 32 * t);
-              const uint32_t vb = (ring0 + sv * TCD_STAGE) >> 4;
-              const int n0 = nks >> 1;                       // split-K: chunks [0,n0) -> O_0, [n0,nks) -> O_1
-#pragma unroll
-              for (int ks = 0; ks < 14; ++ks) {
-                if (ks < nks && leader) {
-                  const uint32_t v_hi = vb + (ks >> 2) * 256 + (ks & 3) * 2, v_lo = v_hi + 128;
-                  const uint32_t p_hi = dS + 16 * ks, p_lo = p_hi + 8;
-                  const uint32_t d = dO + (ks >= n0 ? 16 : 0);
-                  tc::mma_ts_lo(d, p_hi, v_hi, idO, (ks != 0 && ks != n0) ? 1u : 0u);
-                  tc::mma_ts_lo(d, p_hi, v_lo, idO, 1);
-                  tc::mma_ts_lo(d, p_lo, v_hi, idO, 1);
-                }
-              }
-              if (leader) tc::commit(BAR(TB_OFULL));
-              __syncwarp();
-              release(sv);
+        // every tcgen05.mma / commit sits inside an elect.sync block: one lane issues, and inside
+        // the block ptxas keeps the operands in uniform registers (no per-lane predicates)
+        auto release = [&](uint32_t s) {
+          if (tc::elect_one()) tc::commit(BAR(TB_EMPTY + s));
+          __syncwarp();
+        };
+        // S_h^X into the TMEM columns of half X; ka = ring slot holding K hi/lo of heads 2p,2p+1, keys of X
+        auto issue_S = [&](int X, int h, uint32_t ka) {
+          const uint32_t a_hi = (stg >> 4) + (h >> 2) * 1024 + (h & 3) * 2, a_lo = a_hi + 2048;
+          const uint32_t b_hi = ((ring0 + ka * TCD_STAGE) >> 4) + (h & 1) * 4, b_lo = b_hi + 2;
+          const uint32_t d = dS + (X ? K0 : 0);
+          if (tc::elect_one()) {
+            tc::mma_ss_lo(d, a_hi, b_hi, idK[X], 0);
+            if (!A.fast) {
+              tc::mma_ss_lo(d, a_hi, b_lo, idK[X], 1);
+              tc::mma_ss_lo(d, a_lo, b_hi, idK[X], 1);
             }
+            tc::commit(BAR(TB_SFULL + X));
+          }
+          __syncwarp();
+        };
+        // O_X = P_h^X V_h: A = P hi/lo in TMEM (8 + 8 columns per 16 keys), B = V^T of head h in slot sv
+        auto issue_PV = [&](int X, uint32_t sv) {
+          const uint32_t vb = (ring0 + sv * TCD_STAGE) >> 4;
+          const int k_lo = X ? n0 : 0, k_hi = X ? nks : n0;
+          if (tc::elect_one()) {
+#pragma unroll 1
+            for (int ks = k_lo; ks < k_hi; ++ks) {
+              const uint32_t v_hi = vb + (ks >> 2) * 256 + (ks & 3) * 2, v_lo = v_hi + 128;
+              const uint32_t p_hi = dS + 16 * ks, p_lo = p_hi + 8;
+              tc::mma_ts_lo(dO + 16 * X, p_hi, v_hi, idO, ks != k_lo);
+              tc::mma_ts_lo(dO + 16 * X, p_hi, v_lo, idO, 1);
+              tc::mma_ts_lo(dO + 16 * X, p_lo, v_hi, idO, 1);
+            }
+            tc::commit(BAR(TB_OFULL + X));
+          }
+          __syncwarp();
+        };
+        for (int step = 0; step < n_steps; ++step) {
+          uint32_t ka[2];                        // ring slots of the K blocks (key halves A, B) in use
+          ka[0] = take();
+          ka[1] = take();
+          tc::mbar_wait(BAR(TB_QFULL), step & 1);
+          tc::fence_after();
+          tick(3);
+          issue_S(0, 0, ka[0]);
+          issue_S(1, 0, ka[1]);
+          for (int h = 0; h < NH; ++h) {
+            const uint32_t sv = take();          // V^T of head h
+            uint32_t kn[2] = {ka[0], ka[1]};
+            if ((h & 1) && h + 1 < NH) {         // K blocks of the next head pair follow in the stream
+              kn[0] = take();
+              kn[1] = take();
+            }
+            const uint32_t par = (uint32_t)(step * NH + h) & 1u;
+            bool done[2] = {false, false};
+            uint32_t idle = 0;
+            while (!(done[0] && done[1])) {
+              bool any = false;
+#pragma unroll
+              for (int X = 0; X < 2; ++X) {
+                if (!done[X] && tc::mbar_test(BAR(TB_PFULL + X), par)) {
+                  tc::fence_after();
+                  tick(1);
+                  issue_PV(X, sv);
+                  if (h + 1 < NH) {
+                    issue_S(X, h + 1, kn[X]);
+                    if (((h + 1) & 1)) release(kn[X]);   // second head of the pair: K block of X is done
+                  }
+                  done[X] = true;
+                  any = true;
+                  tick(2);
+                }
+              }
+              if (!any && ++idle > (1u << 26)) __trap();
+            }
+            release(sv);
+            ka[0] = kn[0];
+            ka[1] = kn[1];
           }
           // pointer logits U = O K2^T into the (consumed) S columns
           for (int i = 0; i < 4; ++i) {
             const int half = i & 1;                    // O / K2 columns 64*half .. +63
             const uint32_t o_hi = (stg >> 4) + half * 1024, o_lo = o_hi + 2048;
-            for (int gi = 0; gi < ng; ++gi) {
+            for (int gi = 0; gi < 2; ++gi) {
               const uint32_t sk = take();
               if (i == 0 && gi == 0) {
                 tc::mbar_wait(BAR(TB_OREADY), step & 1);
                 tc::fence_after();
+                tick(4);
               }
               const uint32_t kb = (ring0 + sk * TCD_STAGE) >> 4;
-              const uint32_t d = dS + (gi ? K0 : 0), id = gi ? idK1 : idK0;
+              const uint32_t d = dS + (gi ? K0 : 0);
+              if (tc::elect_one()) {
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                if (leader) {
-                  tc::mma_ss_lo(d, o_hi + kk * 2, kb + kk * 2, id, (i | kk) != 0);
-                  if (i < 2) tc::mma_ss_lo(d, o_lo + kk * 2, kb + kk * 2, id, 1);
+                for (int kk = 0; kk < 4; ++kk) {
+                  tc::mma_ss_lo(d, o_hi + kk * 2, kb + kk * 2, idK[gi], (i | kk) != 0);
+                  if (i < 2) tc::mma_ss_lo(d, o_lo + kk * 2, kb + kk * 2, idK[gi], 1);
                 }
+                tc::commit(BAR(TB_EMPTY + sk));
               }
-              release(sk);
               __syncwarp();
             }
           }
-          if (leader) tc::commit(BAR(TB_UFULL));
+          if (tc::elect_one()) tc::commit(BAR(TB_UFULL));
           __syncwarp();
+          tick(5);
+        }
+        if (DEBUG && b == 0 && lane == 0) {
+          float* dT = A.dbg + (size_t)2 * 8 * 128 * NP + (size_t)256 * 128 + (size_t)256 * NP + (16 + t) * 8;
+          for (int i = 0; i < 6; ++i) dT[i] = (float)tph[i];
         }
       }
     }
@@ -540,16 +596,29 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
           l += csum;
           uint32_t out[32];
 #pragma unroll
-          for (int j = 0; j < 16; j += 2) split2(p[j], p[j + 1], out[j >> 1], out[8 + (j >> 1)]);
+          for (int j = 0; j < 16; j += 2) {     // x = hi + lo; the residual is one packed FFMA2 (exact)
+            const __half2 hh = __floats2half2_rn(p[j], p[j + 1]);
+            const float2 r = __ffma2_rn(__half22float2(hh), make_float2(-1.f, -1.f), make_float2(p[j], p[j + 1]));
+            const __half2 ll = __floats2half2_rn(r.x, r.y);
+            out[j >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+            out[8 + (j >> 1)] = *reinterpret_cast<const uint32_t*>(&ll);
+          }
           tst<16>(tS + c0, out);
         };
-        // 16-key chunks; four warps per scheduler hide the TMEM load latency
+        // 16-key chunks, two per 32-bit word of the visited mask; four warps per scheduler hide the
+        // TMEM load latency
 #pragma unroll 1
-        for (int c = c_lo; c < c_hi; ++c) {
-          tld<16>(tS + 16 * c, sA);
-          const unsigned bits = (tcd_word(vis, c >> 1) >> ((c & 1) * 16)) & 0xffffu;
-          tld_wait16(sA);
-          chunk(16 * c, sA, bits);
+        for (int w = c_lo >> 1; 2 * w < c_hi; ++w) {
+          const unsigned word = tcd_word(vis, w);
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int c = 2 * w + e;
+            if (c >= c_lo && c < c_hi) {
+              tld<16>(tS + 16 * c, sA);
+              tld_wait16(sA);
+              chunk(16 * c, sA, e ? (word >> 16) : (word & 0xffffu));
+            }
+          }
         }
         // publish (m, l) of this half for the merge at drain time
         asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(tX + (h & 1) * 4 + half * 2),
@@ -558,7 +627,7 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
         tc::st_wait();
         tc::fence_before();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(BAR(TB_PFULL));
+        if (lane == 0) tc::mbar_arrive(BAR(TB_PFULL + half));
       };
 
       if (half == 1) {
@@ -567,7 +636,7 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
         for (int step = 0; step < n_steps; ++step) {
 #pragma unroll 1
           for (int h = 0; h < NH; ++h) {
-            tc::mbar_wait(BAR(TB_SFULL), (step * NH + h) & 1);
+            tc::mbar_wait(BAR(TB_SFULL + 1), (step * NH + h) & 1);
             tc::fence_after();
             if (h == 0 && step > 0) {     // the node the primary chose at the end of the previous step
               uint32_t a;
@@ -624,6 +693,7 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
       // (the consumed Q_h slot)
       auto drain_o = [&](int step, int h) {
         tc::mbar_wait(BAR(TB_OFULL), (step * NH + h) & 1);
+        tc::mbar_wait(BAR(TB_OFULL + 1), (step * NH + h) & 1);
         tc::fence_after();
         uint32_t oa[16], ob[16], x0, x1, x2, x3;
         tc::ld16(tO, oa);
@@ -675,6 +745,10 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
           // the previous head's partials must be out of the O accumulators before this head's P is
           // published (P V of head h overwrites them): drain first, then compute
           if (h > 0) drain_o(step, h - 1);
+          // O_B of the previous head is out of TMEM: half B's P V of this head may overwrite it
+          tc::fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(BAR(TB_PFULL + 1));
           tick(2);
           softmax_pass(step, h);
           tick(1);
@@ -799,7 +873,7 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
 // ------------------------------------------------------------------------------------------
 static int tcd_np_of(int N) { return (N + 15) / 16 * 16; }
 
-bool decode_tc_supported(int N, int G) { return tcd_np_of(N) <= 208 && G <= 256 && N >= 3; }
+bool decode_tc_supported(int N, int G) { return tcd_np_of(N) <= 208 && tcd_np_of(N) >= 32 && G <= 256; }
 size_t decode_tc_pack_bytes(int Bp, int N) { return align_up((size_t)Bp * tcd_img_bytes(tcd_np_of(N)), 256) + 1024; }
 size_t decode_tc_dbg_floats(int N) {
   const int NP = tcd_np_of(N);
@@ -809,7 +883,7 @@ size_t decode_tc_dbg_floats(int N) {
 template <bool LOGITS, bool DEBUG>
 static int launch_tcd(const TcdArgs& a, int Bp, cudaStream_t s) {
   const size_t smem = (size_t)2 * TCD_TILE_STAGING + (size_t)2 * TCD_STAGES * TCD_STAGE +
-                      (size_t)a.NP * 4 + 2 * TB_PER_TILE * 8 + 16;
+                      (size_t)a.NP * 4 + 2 * TB_PER_TILE * 8 + 16;   // 224 KB + c0 + barriers
   if (smem > 227 * 1024) {
     set_error("decode_tc: N=%d needs %zu bytes of shared memory", a.N, smem);
     return HTSP_ERR_UNSUPPORTED;
