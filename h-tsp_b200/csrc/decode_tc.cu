@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
       const int rows_t = min(128, G - 128 * t);
       const int warps_t = rows_t > 0 ? (rows_t + 31) / 32 : 1;
       for (int s = 0; s < TCD_STAGES; ++s) { tc::mbar_init(bt + 8 * (TB_FULL + s), 1); tc::mbar_init(bt + 8 * (TB_EMPTY + s), 1); }
-      tc::mbar_init(bt + 8 * TB_QFULL, warps_t);
+      tc::mbar_init(bt + 8 * TB_QFULL, 2 * warps_t);
       tc::mbar_init(bt + 8 * TB_SFULL, 1);
       tc::mbar_init(bt + 8 * (TB_SFULL + 1), 1);
       tc::mbar_init(bt + 8 * TB_PFULL, warps_t);            // half A: its softmax warps
@@ -565,6 +565,14 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
             acc0 = __fadd2_rn(acc0, acc1);
             csum = acc0.x + acc0.y;
           };
+          // rows that have not seen a finite score yet (always the case in the first chunk) take their
+          // shift from this chunk's maximum up front instead of tripping the overflow path below
+          if (__any_sync(0xffffffffu, valid && m == kTcdFloor)) {
+            float cm = tv[0];
+#pragma unroll
+            for (int j = 1; j < 16; ++j) cm = fmaxf(cm, tv[j]);
+            if (valid && m == kTcdFloor && cm > kTcdFloor) m = ceilf(cm);
+          }
           expo();
           const bool need = valid && !(csum <= kTcdThresh);
           if (__any_sync(0xffffffffu, need)) {
@@ -620,7 +628,11 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
             }
           }
         }
-        // publish (m, l) of this half for the merge at drain time
+        return make_float2(m, l);
+      };
+      // publish (m, l) of this half for the merge at drain time, then P itself
+      auto publish = [&](int h, float2 ml) {
+        const float m = ml.x, l = ml.y;
         asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(tX + (h & 1) * 4 + half * 2),
                      "r"(__float_as_uint(m)), "r"(__float_as_uint(l))
                      : "memory");
@@ -630,47 +642,30 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
         if (lane == 0) tc::mbar_arrive(BAR(TB_PFULL + half));
       };
 
-      if (half == 1) {
-        // ================================================================ secondary: softmax only
-        visit(first);
-        for (int step = 0; step < n_steps; ++step) {
-#pragma unroll 1
-          for (int h = 0; h < NH; ++h) {
-            tc::mbar_wait(BAR(TB_SFULL + 1), (step * NH + h) & 1);
-            tc::fence_after();
-            if (h == 0 && step > 0) {     // the node the primary chose at the end of the previous step
-              uint32_t a;
-              asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(a) : "r"(tX + 8) : "memory");
-              asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(a)::"memory");
-              visit((int)a);
-            }
-            tick(0);
-            softmax_pass(step, h);
-            tick(1);
-          }
-        }
-      } else {
-      // ================================================================== primary
       const float4 qfix4 = __ldg((const float4*)(A.qfix + (size_t)b * H) + lane);
-      // query rows of this warp's 32 starts -> A tile (fp16 hi/lo, K-major SWIZZLE_128B):
+      const uint32_t pair_bar = 1u + (uint32_t)(t * 4 + q);     // named barrier of this warp pair (64 threads)
+      auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory"); };
+      // query rows -> A tile (fp16 hi/lo, K-major SWIZZLE_128B):
       // q = ((q_graph+q_source+q_target) + q_first) + q_last (models.py:413), 1/sqrt(dk)*log2(e) folded in.
-      // Lane l carries columns 4l..4l+3 of every row; 4 rows (8 L2 loads) are in flight at a time.
+      // The primary gathers rows 0-15 of the lane quarter, the secondary rows 16-31; lane l carries
+      // columns 4l..4l+3 of every row; 8 rows (16 L2 loads) are in flight at a time.
       auto gather_q = [&]() {
         const uint32_t sub = (uint32_t)(lane >> 4) * 16384u + (uint32_t)(lane & 1) * 8u;
         const uint32_t chunk = (uint32_t)(lane & 15) >> 1;
         const int nrows = min(32, rows_t - q * 32);
+        const int r_end = half ? nrows : min(16, nrows);
 #pragma unroll 1
-        for (int r0 = 0; r0 < nrows; r0 += 4) {
-          float4 ql[4], qf[4];
+        for (int r0 = 16 * half; r0 < r_end; r0 += 8) {
+          float4 ql[8], qf[8];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < 8; ++i) {
             const int cr = __shfl_sync(0xffffffffu, cur, r0 + i), fr = __shfl_sync(0xffffffffu, first, r0 + i);
             ql[i] = __ldg((const float4*)(projb + (size_t)cr * PROJ + 2 * H) + lane);
             qf[i] = __ldg((const float4*)(projb + (size_t)fr * PROJ + 3 * H) + lane);
           }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (r0 + i < nrows) {
+          for (int i = 0; i < 8; ++i) {
+            if (r0 + i < r_end) {
               uint32_t h0, l0, h1, l1;
               split2(((qfix4.x + qf[i].x) + ql[i].x) * kScoreScale, ((qfix4.y + qf[i].y) + ql[i].y) * kScoreScale, h0, l0);
               split2(((qfix4.z + qf[i].z) + ql[i].z) * kScoreScale, ((qfix4.w + qf[i].w) + ql[i].w) * kScoreScale, h1, l1);
@@ -689,8 +684,8 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
       visit(first);
       gather_q();
 
-      // drain O_h: merge the two split-K partials, /l -> fp16 hi/lo -> A tile columns 16h..16h+15
-      // (the consumed Q_h slot)
+      // drain O_h (primary): merge the two split-K partials, /l -> fp16 hi/lo -> A tile columns
+      // 16h..16h+15 (the consumed Q_h slot)
       auto drain_o = [&](int step, int h) {
         tc::mbar_wait(BAR(TB_OFULL), (step * NH + h) & 1);
         tc::mbar_wait(BAR(TB_OFULL + 1), (step * NH + h) & 1);
@@ -708,8 +703,8 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
         const float ma = __uint_as_float(x0), la = __uint_as_float(x1);
         const float mb = __uint_as_float(x2), lb = __uint_as_float(x3);
         const float M = fmaxf(ma, mb);
-        // a half without a finite score (or without chunks) has l = 0 and contributes nothing
-        const float sa = (n0 > 0 && la > 0.f) ? ex2_approx(ma - M) : 0.f;
+        // a half without a finite score has l = 0 and contributes nothing
+        const float sa = (la > 0.f) ? ex2_approx(ma - M) : 0.f;
         const float sb = (lb > 0.f) ? ex2_approx(mb - M) : 0.f;
         const float inv = 1.f / (la * sa + lb * sb);
         const float wa = sa * inv, wb = sb * inv;
@@ -739,28 +734,35 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
         // ------------------------------------------------------------ glimpse, one head at a time
 #pragma unroll 1
         for (int h = 0; h < NH; ++h) {
-          tc::mbar_wait(BAR(TB_SFULL), (step * NH + h) & 1);
+          tc::mbar_wait(BAR(TB_SFULL + half), (step * NH + h) & 1);
           tc::fence_after();
           tick(0);
-          // the previous head's partials must be out of the O accumulators before this head's P is
-          // published (P V of head h overwrites them): drain first, then compute
-          if (h > 0) drain_o(step, h - 1);
-          // O_B of the previous head is out of TMEM: half B's P V of this head may overwrite it
+          const float2 ml = softmax_pass(step, h);
+          tick(1);
+          if (half == 0) {
+            // the previous head's partials must be out of the O accumulators before this head's P V
+            // overwrites them; by now both P V of head h-1 are long done, so the drain does not wait.
+            // Then tell the issuer that O_B is free (second arrival on half B's barrier).
+            if (h > 0) drain_o(step, h - 1);
+            tc::fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(BAR(TB_PFULL + 1));
+            tick(2);
+          }
+          publish(h, ml);
+        }
+        if (half == 0) {
+          drain_o(step, NH - 1);
+          tc::fence_async_smem();
           tc::fence_before();
           __syncwarp();
-          if (lane == 0) tc::mbar_arrive(BAR(TB_PFULL + 1));
+          if (lane == 0) tc::mbar_arrive(BAR(TB_OREADY));
           tick(2);
-          softmax_pass(step, h);
-          tick(1);
         }
-        drain_o(step, NH - 1);
-        tc::fence_async_smem();
-        tc::fence_before();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(BAR(TB_OREADY));
-        tick(2);
 
         // ------------------------------------------------------------ pointer logits + arg-max
+        // Each warp of the pair scans its own key chunks and reduces them to one candidate
+        // (clipped logit, key); the primary merges the two (ties -> lower key = its own).
         tc::mbar_wait(BAR(TB_UFULL), step & 1);
         tc::fence_after();
         tick(3);
@@ -779,16 +781,17 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
           float bj[16];
           int cj[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) { bj[j] = -INFINITY; cj[j] = 0; }
-          uint32_t u[32], u2[32];
-          auto body = [&](int c, uint32_t (&uu)[32], uint32_t (&nx)[32]) {
-            tld_wait16(uu);
-            if (c + 1 < nch) tld<16>(tS + 16 * (c + 1), nx);
+          for (int j = 0; j < 16; ++j) { bj[j] = -INFINITY; cj[j] = c_lo; }
+          uint32_t u[32];
+#pragma unroll 1
+          for (int c = c_lo; c < c_hi; ++c) {
+            tld<16>(tS + 16 * c, u);
             const unsigned bits = (tcd_word(vis, c >> 1) >> ((c & 1) * 16)) & 0xffffu;
+            tld_wait16(u);
             if (DEBUG && b == 0 && step == A.dbg_step) {
               float* dU = A.dbg + (size_t)2 * 8 * 128 * NP + (size_t)256 * 128 + (size_t)(t * 128 + row) * NP + 16 * c;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) dU[j] = __uint_as_float(uu[j]);
+              for (int j = 0; j < 16; ++j) dU[j] = __uint_as_float(u[j]);
             }
             const float4* cc4 = (const float4*)(c0s + 16 * c);
 #pragma unroll
@@ -798,19 +801,13 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
 #pragma unroll
               for (int jj = 0; jj < 4; ++jj) {
                 const int j = 4 * j4 + jj;
-                float z = (__uint_as_float(uu[j]) + ca[jj]) * kTcdInvSqrtH;
+                float z = (__uint_as_float(u[j]) + ca[jj]) * kTcdInvSqrtH;
                 if (EXACT) z = clip_tanh10(z);
                 if ((bits >> j) & 1u) z = -INFINITY;
                 if (LOGITS && lo_out != nullptr && valid && 16 * c + j < N) lo_out[16 * c + j] = z;
                 if (z > bj[j]) { bj[j] = z; cj[j] = c; }
               }
             }
-          };
-          tld<16>(tS, u);
-#pragma unroll 1
-          for (int c = 0; c < nch; c += 2) {
-            body(c, u, u2);
-            if (c + 1 < nch) body(c + 1, u2, u);
           }
           best = bj[0];
           idx = 16 * cj[0];
@@ -825,19 +822,44 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
         } else {
           pass(std::false_type{});
           if (__any_sync(0xffffffffu, valid && best > 3.0f)) pass(std::true_type{});
+          else best = (best == -INFINITY) ? best : clip_tanh10(best);    // candidates are exchanged as clipped logits
         }
         tick(4);
-        // ---- state update (train_path_solver.py:45-72); the chosen node goes to the secondary warp
-        const int a = A.forced_pi ? A.forced_pi[((size_t)b * G + gc) * N + cnt] : idx;
-        asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tX + 8), "r"((uint32_t)a) : "memory");
+        int a;
+        if (half == 1) {
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(tX + 9), "r"(__float_as_uint(best)),
+                       "r"((uint32_t)idx)
+                       : "memory");
+          tc::st_wait();
+          tc::fence_before();
+          pair_sync();                // candidate published
+          pair_sync();                // the primary has published the chosen node
+          tc::fence_after();
+          uint32_t av;
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(av) : "r"(tX + 8) : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(av)::"memory");
+          a = (int)av;
+        } else {
+          pair_sync();
+          tc::fence_after();
+          uint32_t bz, bi;
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(bz), "=r"(bi) : "r"(tX + 9) : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(bz), "+r"(bi)::"memory");
+          if (__uint_as_float(bz) > best) idx = (int)bi;     // ties keep the primary's (lower) key
+          // ---- state update (train_path_solver.py:45-72); the chosen node goes to the secondary warp
+          a = A.forced_pi ? A.forced_pi[((size_t)b * G + gc) * N + cnt] : idx;
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tX + 8), "r"((uint32_t)a) : "memory");
+          tc::st_wait();
+          tc::fence_before();
+          pair_sync();
+        }
         visit(a);
-        tc::st_wait();
         tc::fence_before();
         if (step + 1 < n_steps) gather_q();
         tick(5);
       }
       // ---- reward = -(closed tour length - fixed edge)   (train_path_solver.py:109-149)
-      if (valid) {
+      if (valid && half == 0) {
         const float2* xb = (const float2*)A.x + (size_t)b * N;
         float len = 0.f;
         float2 p0 = __ldg(&xb[pirow[0]]);
@@ -853,7 +875,6 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
         const float fixed = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
         A.reward[(size_t)b * G + g] = -(len - fixed);
       }
-      }   // primary
       if (DEBUG && b == 0 && lane == 0) {
         float* dT = A.dbg + (size_t)2 * 8 * 128 * NP + (size_t)256 * 128 + (size_t)256 * NP + sw * 8;
         for (int i = 0; i < 6; ++i) dT[i] = (float)tph[i];

@@ -423,3 +423,91 @@ def test_full_size_properties(solvers, mode):
     best_len, best_pi, best_row = s.select_best(reward, pi, 1)
     assert torch.equal(best_len, (-reward).min(dim=1).values)
     assert torch.equal(best_pi, pil.gather(1, best_row.long()[:, None, None].expand(B, 1, N)).squeeze(1))
+
+
+# ---------------------------------------------------------------- K3 tcgen05 kernel internals
+def _replay_state(pi0, N, G, src, tgt, step):
+    """Current node and visited mask [G,N] before decode step `step` (reference state machine,
+    train_path_solver.py:45-72) along the tours pi0 [G,N]."""
+    p = pi0.long().cpu()
+    cnt = torch.ones(G, dtype=torch.long)
+    f = p[:, 0]
+    cnt += ((f == src) | (f == tgt)).long()
+    for _ in range(step):
+        a = p.gather(1, cnt[:, None]).squeeze(1)
+        cnt += 1 + ((a == src) | (a == tgt)).long()
+    vis = torch.zeros(G, N, dtype=torch.bool)
+    for r in range(G):
+        vis[r, p[r, :cnt[r]]] = True
+    return p.gather(1, (cnt - 1)[:, None]).squeeze(1), vis
+
+
+@pytest.mark.parametrize("mode", ["x3", "fast"])
+@pytest.mark.parametrize("N,G,step", [(200, 200, 0), (200, 200, 131), (100, 37, 40), (20, 20, 5)])
+def test_tcgen05_kernel_intermediates(solvers, sd6, mode, N, G, step):
+    """htsp_decode_debug: the raw glimpse scores S (all heads), the normalised glimpse outputs O and
+    the raw pointer scores U of the tcgen05 rollout kernel at one decode step, against float64
+    arithmetic on the same tables (models.py:404-446 with the hoisted / folded projections)."""
+    s = solvers[mode]
+    g = torch.Generator().manual_seed(N * 7 + G)
+    x = torch.rand(2, N, 2, generator=g).cuda()
+    src = torch.zeros(2, dtype=torch.long)
+    tgt = torch.full((2,), N - 1)
+    first = torch.randperm(N, generator=g)[:G]
+    emb = solvers["fp32"].encode(x)
+    pi_ref, _, _ = solvers["fp32"].rollout(x, emb, src, tgt, first)
+    pi, _, S, O, U = s.rollout_debug(x, emb, src, tgt, first, pi_ref, step)
+    assert torch.equal(pi, pi_ref)
+    W = {k: v.double().cuda() for k, v in sd6.items() if k.startswith("decoder.")}
+    e = emb[0].double()
+    K, V = e @ W["decoder.Wk.weight"].T, e @ W["decoder.Wv.weight"].T
+    QL, QF = e @ W["decoder.Wq_last.weight"].T, e @ W["decoder.Wq_first.weight"].T
+    K2 = e @ W["decoder.multi_head_combine.weight"]
+    qfix = (W["decoder.Wq_graph.weight"] @ e.mean(0) + W["decoder.Wq_source.weight"] @ e[0]
+            + W["decoder.Wq_target.weight"] @ e[N - 1])
+    cur, vis = _replay_state(pi_ref[0], N, G, 0, N - 1, step)
+    cur, vis = cur.cuda(), vis.cuda()
+    log2e = 1.4426950408889634
+    q = (qfix[None] + QF[first.cuda()] + QL[cur]) * (0.25 * log2e)
+    Sref = torch.einsum("ghd,nhd->hgn", q.reshape(G, 8, 16), K.reshape(N, 8, 16))
+    Sgot = torch.cat([S[0], S[1]], dim=1)[:, :G, :N].double()
+    P = torch.softmax((Sref / log2e).masked_fill(vis[None], float("-inf")), dim=-1)
+    Oref = torch.einsum("hgn,nhd->ghd", P, V.reshape(N, 8, 16)).reshape(G, 128)
+    Uref = Oref @ K2.T
+    # scores / outputs are O(1..10): split-fp16 products (x3) keep ~1e-5; `fast` rounds Q and K of the
+    # glimpse scores to single fp16 (2^-11 relative)
+    tol_s = {"x3": 5e-5, "fast": 2e-2}[mode]
+    tol_o = {"x3": 5e-5, "fast": 5e-3}[mode]
+    assert float((Sgot - Sref).abs().max()) <= tol_s
+    assert float((O[:G].double() - Oref).abs().max()) <= tol_o
+    assert float((U[:G, :N].double() - Uref).abs().max()) <= 4 * tol_o
+
+
+@pytest.mark.parametrize("mode", ["x3", "fast"])
+def test_tcgen05_and_mma_kernels_agree(solvers, sd6, mode, monkeypatch):
+    """The two tensor-core rollout kernels (tcgen05/TMEM, and the mma.sync one that still serves
+    N > 208) evaluate the same arithmetic: teacher-forced logits agree to the mode's tolerance and
+    both free-running rollouts pass the tie-aware check."""
+    s = solvers[mode]
+    g = torch.Generator().manual_seed(31)
+    Bp, N, G = 3, 200, 200
+    x = torch.rand(Bp, N, 2, generator=g)
+    src = torch.zeros(Bp, dtype=torch.long)
+    tgt = torch.full((Bp,), N - 1)
+    first = torch.randperm(N, generator=g)[:G]
+    xc = x.cuda()
+    emb = s.encode(xc)
+    pi_tc, rew_tc, _ = s.rollout(xc, emb, src, tgt, first)
+    _, _, lg_tc = s.rollout(xc, emb, src, tgt, first, forced_pi=pi_tc, want_logits=True)
+    monkeypatch.setenv("HTSP_DECODE_IMPL", "mma")
+    pi_mm, rew_mm, _ = s.rollout(xc, emb, src, tgt, first)
+    _, _, lg_mm = s.rollout(xc, emb, src, tgt, first, forced_pi=pi_tc, want_logits=True)
+    monkeypatch.delenv("HTSP_DECODE_IMPL")
+    fin = torch.isfinite(lg_tc)
+    assert torch.equal(fin, torch.isfinite(lg_mm))
+    assert float((lg_tc[fin] - lg_mm[fin]).abs().max()) <= 2 * LOGIT_TOL[mode]
+    with torch.no_grad():
+        for pi in (pi_tc, pi_mm):
+            tie_aware_check(sd6, x[:1], src[:1], tgt[:1], first, pi[:1].cpu().long(), 2 * LOGIT_TOL[mode])
+    same = (pi_tc == pi_mm).all(dim=2).float().mean().item()
+    print(f"[{mode}] rows identical between the tcgen05 and mma.sync kernels: {same:.3f}")
