@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
           const uint32_t d = dS + (X ? K0 : 0);
           if (tc::elect_one()) {
             tc::mma_ss_lo(d, a_hi, b_hi, idK[X], 0);
-            if (!(A.fast & 1)) {
+            if (!A.fast) {
               tc::mma_ss_lo(d, a_hi, b_lo, idK[X], 1);
               tc::mma_ss_lo(d, a_lo, b_hi, idK[X], 1);
             }
@@ -383,10 +383,8 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
               const uint32_t v_hi = vb + (ks >> 2) * 256 + (ks & 3) * 2, v_lo = v_hi + 128;
               const uint32_t p_hi = dS + 16 * ks, p_lo = p_hi + 8;
               tc::mma_ts_lo(dO + 16 * X, p_hi, v_hi, idO, ks != k_lo);
-              if (!(A.fast & 2)) {      // (timing experiment: HTSP_TC_EXPERIMENT=pvhi drops the lo terms)
-                tc::mma_ts_lo(dO + 16 * X, p_hi, v_lo, idO, 1);
-                tc::mma_ts_lo(dO + 16 * X, p_lo, v_hi, idO, 1);
-              }
+              tc::mma_ts_lo(dO + 16 * X, p_hi, v_lo, idO, 1);
+              tc::mma_ts_lo(dO + 16 * X, p_lo, v_hi, idO, 1);
             }
             tc::commit(BAR(TB_OFULL + X));
           }
@@ -941,10 +939,6 @@ int launch_decode_tc(const float* x, const float* proj, const float* qfix, const
   a.src = src; a.tgt = tgt; a.first = first; a.forced_pi = forced_pi;
   a.pi = pi; a.reward = reward; a.logits_out = logits_out; a.dbg = dbg;
   a.N = N; a.NP = NP; a.G = G; a.fast = (mode == HTSP_MODE_TC_FAST) ? 1 : 0; a.dbg_step = dbg_step;
-  {
-    const char* e = getenv("HTSP_TC_EXPERIMENT");
-    if (e != nullptr && strcmp(e, "pvhi") == 0) a.fast |= 2;
-  }
   if (dbg != nullptr) return launch_tcd<false, true>(a, Bp, s);
   if (logits_out != nullptr) return launch_tcd<true, false>(a, Bp, s);
   return launch_tcd<false, false>(a, Bp, s);
