@@ -100,7 +100,10 @@ def test_teacher_forced_logits_match_golden_n200(solvers, golden, mode):
 
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("Bp,N,G", [(2, 20, 20), (3, 50, 7), (1, 200, 33), (2, 100, 100), (1, 500, 12),
-                                    (1, 230, 230)])
+                                    (1, 230, 230),
+                                    # tcgen05 kernel edges: largest N (NP = 208, second row tile of 80 rows),
+                                    # odd chunk counts (NP = 144), smallest NP (32), one row, G = 129
+                                    (1, 208, 208), (2, 130, 130), (3, 17, 17), (2, 64, 1), (1, 150, 129)])
 def test_teacher_forced_logits_match_oracle(solvers, sd6, mode, Bp, N, G):
     s = solvers[mode]
     g = torch.Generator().manual_seed(N + G)
