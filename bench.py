@@ -43,6 +43,15 @@ def algorithmic_flops(N: int, G: int, L: int):
     return enc, reset, dec
 
 
+def k3_dram_traffic(args, B, N, G, L):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one rollout-kernel launch, from the committed
+    `ncu --set full` capture of this very command line (profiles/r01_decode_tc_x3_cfg2_dram_traffic.txt);
+    only quoted for the configuration that capture was taken on, otherwise null."""
+    if (args.mode, B, N, G, L) == ("x3", 4096, 200, 200, 6) and os.environ.get("HTSP_DECODE_IMPL") != "mma":
+        return 3.439671e9 + 0.736127e9
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -308,7 +317,7 @@ def run_b200(args):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "rollout (decode) kernel",
                          "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
-                         "frac": achieved / tc_peak, "traffic": None,
+                         "frac": achieved / tc_peak, "traffic": k3_dram_traffic(args, B, N, G, L),
                          "peak_source": f"bf16_tflops_sustained, {peak_src}",
                          "kernel_ms": kms, "kernel_share_of_step": kms / (total_ms / args.steps),
                          "algorithmic_flops_per_launch": dec_f * B},

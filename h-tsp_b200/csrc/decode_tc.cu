@@ -15,11 +15,13 @@
 // Arithmetic is split-fp16 (x = hi + lo, three MMAs per product, fp32 accumulation; DESIGN.md
 // section 4); HTSP_MODE_TC_FAST drops the lo terms of S only.
 //
-// Warp roles (320 threads): warp 0 = operand producer (cp.async.bulk of pre-swizzled K/V/K2 tiles
-// from the L2-resident per-instance image into a 3-stage ring, shared by both row tiles), warp 1 =
-// MMA issuer (one thread), warps 2-5 / 6-9 = softmax warps of tile 0 / 1 (warp%4 selects the TMEM
-// lane quarter).  All synchronisation is mbarrier based; tcgen05.commit publishes accumulators and
-// releases ring stages.
+// Warp roles (640 threads, setmaxnreg 32 / 112): warp 0 = operand producer (cp.async.bulk of the
+// pre-swizzled K/V/K2 blocks from the L2-resident per-instance image into one 3 x 16 KB ring per row
+// tile), warps 3 and 19 (or 2) = MMA issuers of tile 0 / 1 (elect.sync blocks, uniform operands),
+// warps 4-19 = 2 tiles x 2 key halves x 4 lane quarters of softmax warps (warp%4 selects the TMEM
+// lane quarter; the two warps of a quarter form a split-K pair).  All synchronisation is mbarrier
+// based (plus one named barrier per pair for the arg-max merge); tcgen05.commit publishes
+// accumulators and releases ring stages.
 #include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
@@ -267,53 +269,14 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
   tc::fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // register budget: the role warpgroup (warps 0-3) hands registers to the two softmax warpgroups
-  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
-  else asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
-
-  if (warp == 0) {
-    // ================================================================== operand producer (both row tiles)
-    if (lane == 0) {
-      const size_t szk = tcd_szk(NP), szvh = tcd_szvh(NP), pair = tcd_pair_bytes(NP);
-      const int per_step = 24;                             // ring stages one tile consumes per decode step
-      const uint32_t total = (uint32_t)n_steps * (uint32_t)per_step;
-      uint32_t it[2] = {0, 0};
-      int rem = n_tiles;
-      uint32_t idle = 0;
-      while (rem > 0) {
-        bool pushed = false;
-        for (int t = 0; t < n_tiles; ++t) {
-          if (it[t] >= total) continue;
-          const uint32_t bt = bar0 + 8u * (uint32_t)(t * TB_PER_TILE);
-          const uint32_t s = it[t] % TCD_STAGES, use = it[t] / TCD_STAGES;
-          if (!tc::mbar_test(bt + 8 * (TB_EMPTY + s), (use & 1) ^ 1)) continue;
-          // i-th stage of the step: per head pair p [K_p half A, K_p half B, V 2p, V 2p+1], then the four K2
-          // blocks by key half
-          const int i = (int)(it[t] % (uint32_t)per_step);
-          size_t off;
-          uint32_t bytes;
-          if (i < 16) {
-            const int p = i >> 2, j = i & 3;
-            if (j < 2) { off = (size_t)p * pair + (j ? (size_t)K0 * 128 : 0); bytes = (uint32_t)(j ? K1 : K0) * 128u; }
-            else { off = (size_t)p * pair + szk + (size_t)(j - 2) * szvh; bytes = (uint32_t)szvh; }
-          } else {
-            const int i2 = i - 16, blk = i2 >> 1, gi = i2 & 1;
-            off = 4 * pair + (size_t)blk * szk + (gi ? (size_t)K0 * 128 : 0);
-            bytes = (uint32_t)(gi ? K1 : K0) * 128u;
-          }
-          tc::mbar_expect_tx(bt + 8 * (TB_FULL + s), bytes);
-          tc::bulk_g2s(tc::smem_u32(rings + ((size_t)t * TCD_STAGES + s) * TCD_STAGE), imgb + off, bytes,
-                       bt + 8 * (TB_FULL + s));
-          if (++it[t] == total) --rem;
-          pushed = true;
-        }
-        if (pushed) idle = 0;
-        else if (++idle > (1u << 28)) __trap();
-        else __nanosleep(64);
-      }
-    }
-  } else if (warp < 3) {
-    const int t = warp - 1;                       // warp 1 issues for row tile 0, warp 2 for row tile 1
+  // The issuers sit on scheduler 3 (warp % 4 == 3), the least loaded one: row tile 1 of a 200-row
+  // instance has no rows in lane quarter 3, so its softmax warp 19 is free to be tile 1's issuer
+  // (when tile 1 does use that quarter, warp 2 issues instead).
+  const int iss1_warp = (G - 128 > 96) ? 2 : 19;
+  auto run_issuer = [&](const int t) {
+    // The issuers sit on scheduler 3 (warp % 4 == 3), the least loaded one: row tile 1 of a 200-row
+    // instance has no rows in lane quarter 3, so its softmax warp 19 is free to be tile 1's issuer
+    // (when tile 1 does use that quarter, warp 2 issues instead).
     const uint32_t bt = bar0 + 8u * (uint32_t)(t * TB_PER_TILE);
     auto BAR = [&](int i) { return bt + 8u * (uint32_t)i; };
     const uint32_t ring0 = tc::smem_u32(rings + (size_t)t * TCD_STAGES * TCD_STAGE);
@@ -466,7 +429,51 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
         }
       }
     }
-  } else if (warp >= 4) {
+  };
+
+  auto run_producer = [&]() {
+    // ================================================================== operand producer (both row tiles)
+    if (lane == 0) {
+      const size_t szk = tcd_szk(NP), szvh = tcd_szvh(NP), pair = tcd_pair_bytes(NP);
+      const int per_step = 24;                             // ring stages one tile consumes per decode step
+      const uint32_t total = (uint32_t)n_steps * (uint32_t)per_step;
+      uint32_t it[2] = {0, 0};
+      int rem = n_tiles;
+      uint32_t idle = 0;
+      while (rem > 0) {
+        bool pushed = false;
+        for (int t = 0; t < n_tiles; ++t) {
+          if (it[t] >= total) continue;
+          const uint32_t bt = bar0 + 8u * (uint32_t)(t * TB_PER_TILE);
+          const uint32_t s = it[t] % TCD_STAGES, use = it[t] / TCD_STAGES;
+          if (!tc::mbar_test(bt + 8 * (TB_EMPTY + s), (use & 1) ^ 1)) continue;
+          // i-th stage of the step: per head pair p [K_p half A, K_p half B, V 2p, V 2p+1], then the four K2
+          // blocks by key half
+          const int i = (int)(it[t] % (uint32_t)per_step);
+          size_t off;
+          uint32_t bytes;
+          if (i < 16) {
+            const int p = i >> 2, j = i & 3;
+            if (j < 2) { off = (size_t)p * pair + (j ? (size_t)K0 * 128 : 0); bytes = (uint32_t)(j ? K1 : K0) * 128u; }
+            else { off = (size_t)p * pair + szk + (size_t)(j - 2) * szvh; bytes = (uint32_t)szvh; }
+          } else {
+            const int i2 = i - 16, blk = i2 >> 1, gi = i2 & 1;
+            off = 4 * pair + (size_t)blk * szk + (gi ? (size_t)K0 * 128 : 0);
+            bytes = (uint32_t)(gi ? K1 : K0) * 128u;
+          }
+          tc::mbar_expect_tx(bt + 8 * (TB_FULL + s), bytes);
+          tc::bulk_g2s(tc::smem_u32(rings + ((size_t)t * TCD_STAGES + s) * TCD_STAGE), imgb + off, bytes,
+                       bt + 8 * (TB_FULL + s));
+          if (++it[t] == total) --rem;
+          pushed = true;
+        }
+        if (pushed) idle = 0;
+        else if (++idle > (1u << 28)) __trap();
+        else __nanosleep(64);
+      }
+    }
+  };
+  auto run_softmax = [&]() {
     // ================================================================== softmax / state warps
     // Two warps share every 32-row lane quarter of a tile ("split-K"): the primary (half 0) owns key
     // chunks [0,n0), the secondary (half 1) chunks [n0,nch).  Each runs its own online softmax
@@ -882,7 +889,21 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
         for (int i = 0; i < 6; ++i) dT[i] = (float)tph[i];
       }
     }
+  };
+
+  // register budget: the role warpgroup (warps 0-3) hands registers to the softmax warpgroups; the
+  // role dispatch is repeated inside each branch so that ptxas sees one register budget per path
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
+    if (warp == 0) run_producer();
+    else if (warp == 3) run_issuer(0);
+    else if (warp == 2 && iss1_warp == 2) run_issuer(1);
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
+    if (warp == 19 && iss1_warp == 19) run_issuer(1);
+    else run_softmax();
   }
+
   tc::fence_before();
   __syncthreads();
   if (warp == 1) {
