@@ -15,13 +15,11 @@
 // Arithmetic is split-fp16 (x = hi + lo, three MMAs per product, fp32 accumulation; DESIGN.md
 // section 4); HTSP_MODE_TC_FAST drops the lo terms of S only.
 //
-// Warp roles (640 threads, setmaxnreg 32 / 112): warp 0 = operand producer (cp.async.bulk of the
-// pre-swizzled K/V/K2 blocks from the L2-resident per-instance image into one 3 x 16 KB ring per row
-// tile), warps 3 and 19 (or 2) = MMA issuers of tile 0 / 1 (elect.sync blocks, uniform operands),
-// warps 4-19 = 2 tiles x 2 key halves x 4 lane quarters of softmax warps (warp%4 selects the TMEM
-// lane quarter; the two warps of a quarter form a split-K pair).  All synchronisation is mbarrier
-// based (plus one named barrier per pair for the arg-max merge); tcgen05.commit publishes
-// accumulators and releases ring stages.
+// Warp roles (320 threads): warp 0 = operand producer (cp.async.bulk of pre-swizzled K/V/K2 tiles
+// from the L2-resident per-instance image into a 3-stage ring, shared by both row tiles), warp 1 =
+// MMA issuer (one thread), warps 2-5 / 6-9 = softmax warps of tile 0 / 1 (warp%4 selects the TMEM
+// lane quarter).  All synchronisation is mbarrier based; tcgen05.commit publishes accumulators and
+// releases ring stages.
 #include <stdlib.h>
 #include <string.h>
 #include "common.cuh"

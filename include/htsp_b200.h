@@ -126,6 +126,28 @@ int htsp_finalize_paths(const int64_t* best_pi, const int64_t* fragment, const f
 int htsp_tour_length(const float* coords, const int64_t* tours, const int32_t* tour_len, int E,
                      int Ntot, int Tmax, float* out, void* stream);
 
+/* ---- K6: large-TSP environment state ------------------------
+ * Device-resident replacement of the per-step bookkeeping of Env._step (h_tsp.py:569-603), batched
+ * over E environments (VecEnv.step runs them in a Python loop, h_tsp.py:779-782).
+ * htsp_env_splice = LargeState.move_to's list splice (h_tsp.py:288-320): new_paths [E,P] i64 with
+ * path_len [E] i32 valid entries each; tour_in/tour_out [E,Ntot] i64 (distinct buffers), tour_len [E]
+ * i32 in/out, pos [E,Ntot] i32 in/out = position of every city in its tour or -1; status [E] i32:
+ * 0 ok, 1 an endpoint of the path is not on the tour, 2 both endpoints coincide, 3 duplicate city,
+ * 4 the tour did not grow, 5 index out of range (the reference's asserts, :293-320).
+ * htsp_env_update (after the splice, on the new tour): neighbour coordinates
+ * (rl_utils.update_neighbor_coord_, rl_utils.py:135-159), selected / available masks with the k-NN
+ * lists knn [E,Ntot,k] i64 (LargeState.mask, h_tsp.py:330-340), the closed-tour length
+ * (get_tour_distance over fp32(fp64 cdist x 1000), rl_utils.py:87-102, without the Ntot x Ntot matrix;
+ * cur_len [E] in: old length, out: new length / 1000), reward [E] = old - new (h_tsp.py:599), and the
+ * [E,Ntot,8] state tensor of LargeState.to_tensor (h_tsp.py:396-408; may be NULL).             */
+int htsp_env_splice(const int64_t* new_paths, const int32_t* path_len, int E, int P, int Ntot,
+                    const int64_t* tour_in, int64_t* tour_out, int32_t* tour_len, int32_t* pos,
+                    int32_t* status, void* stream);
+int htsp_env_update(const float* x, const int64_t* tour, const int32_t* tour_len, const int64_t* new_paths,
+                    const int32_t* path_len, const int64_t* knn, int k, int E, int P, int Ntot,
+                    uint8_t* selected, uint8_t* available, float* neighbor_coord, float* state,
+                    float* cur_len, float* reward, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
