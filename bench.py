@@ -145,6 +145,37 @@ def cpu_oracle_throughput(N, G, L, sample_B, threads=None, repeats=1):
     return sample_B / best, torch.get_num_threads(), best
 
 
+def gpu_eager_port_throughput(N, G, L, sample_B=256):
+    """Context for the ">20x the reference's single-GPU PyTorch throughput" target (BASELINE.md): the
+    oracle port -- the reference's op sequence as eager PyTorch / ATen kernels, fp32, TF32 off -- on THIS
+    GPU, on a bounded sample.  The port has no per-step host syncs and no O(t) list growth, so it is an
+    upper bound on what the unmodified reference reaches.  Baseline only; never on the product path."""
+    import torch
+    from htsp_b200.weights import synthetic_state_dict
+    from oracle import path_solver_oracle as po
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = torch.device("cuda")
+    sd = {k: v.to(dev) for k, v in synthetic_state_dict(1234, L).items()}
+    x = make_inputs(sample_B, N, 99).to(dev)
+    src = torch.zeros(sample_B, 1, dtype=torch.long, device=dev)
+    tgt = torch.full((sample_B, 1), N - 1, dtype=torch.long, device=dev)
+    first = torch.randperm(N, generator=torch.Generator().manual_seed(7))[:G].to(dev)
+    best = None
+    with torch.no_grad():
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            po.path_solver_forward(sd, x, src, tgt, first, val_type="noAug_nTraj", return_pi=True)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    del sd, x
+    torch.cuda.empty_cache()
+    return sample_B / best
+
+
 def run_reference(args):
     """--impl reference: rank 0 only; each step = one bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
@@ -302,6 +333,11 @@ def run_b200(args):
         kms = float(kern_ms)
         achieved = dec_f * B / (kms / 1e3) / 1e12
         cpu_val, cores, cpu_dt = cpu_oracle_throughput(N, G, L, args.cpu_sample)
+        try:
+            gpu_port = gpu_eager_port_throughput(N, G, L)
+        except Exception as exc:      # context only: never fail the bench line over it
+            gpu_port = None
+            print(f"[bench] eager-PyTorch GPU baseline skipped: {exc}", file=sys.stderr)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -325,6 +361,10 @@ def run_b200(args):
                              "sample": f"{args.cpu_sample} subproblems (N={N}, G={G}, noAug_nTraj, "
                                        f"L={L}) in {cpu_dt:.1f} s, oracle port, torch CPU fp32",
                              "host_cpus": os.cpu_count()},
+            "gpu_eager_pytorch_port": {"value": gpu_port, "unit": UNIT, "kind": "port",
+                                       "sample": "256 subproblems, oracle port as eager PyTorch fp32 (TF32 off) on "
+                                                 "this GPU: an upper bound on the unmodified reference, which adds "
+                                                 ">= 4 host syncs per decode step"},
         }
         print(json.dumps(line))
     if world > 1:
