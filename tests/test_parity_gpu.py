@@ -514,3 +514,43 @@ def test_tcgen05_and_mma_kernels_agree(solvers, sd6, mode, monkeypatch):
             tie_aware_check(sd6, x[:1], src[:1], tgt[:1], first, pi[:1].cpu().long(), 2 * LOGIT_TOL[mode])
     same = (pi_tc == pi_mm).all(dim=2).float().mean().item()
     print(f"[{mode}] rows identical between the tcgen05 and mma.sync kernels: {same:.3f}")
+
+
+# ---------------------------------------------------------------- multi-GPU: augmentation sharding (8e)
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_aug_sharding_equals_single_gpu_hook(solvers, world):
+    """B < ranks (one TSP-10000 environment step): the 8 augmentations are sharded.  Emulated on one
+    GPU by running every rank's shard in turn: the combined result must be IDENTICAL to the
+    one-GPU hook call (same kernels, same inputs, the reference's first-max reduction)."""
+    from htsp_b200 import B200RLSolver
+    from htsp_b200.sharding import combine_aug_winners, shard_range, solve_aug_shard
+    from htsp_b200 import _abi
+    s = solvers["x3"]
+    hook = B200RLSolver(s, sample_size=10)
+    g = torch.Generator().manual_seed(4)
+    data = torch.rand(2, 700, 2, generator=g).cuda()
+    frag = torch.stack([torch.randperm(700, generator=g)[:64] for _ in range(2)]).cuda()
+    first = torch.randperm(64, generator=g)[:10]
+    s.first_action_override = first
+    try:
+        want_paths, want_len, status, _ = hook.solve_device(data, frag, None)
+    finally:
+        s.first_action_override = None
+    assert bool((status == 0).all())
+    lens, pis = [], []
+    for r in range(world):
+        lo, hi = shard_range(8, r, world)
+        bl, bp, scale, fdev = solve_aug_shard(hook, data, frag, lo, hi, first)
+        lens.append(bl)
+        pis.append(bp)
+    win_len, win_pi = combine_aug_winners(torch.cat(lens), torch.cat(pis))
+    B, N = win_pi.shape
+    paths = torch.empty(B, N, dtype=torch.int64, device="cuda")
+    lengths = torch.empty(B, device="cuda")
+    st = torch.empty(B, dtype=torch.int32, device="cuda")
+    _abi.check(_abi.lib().htsp_finalize_paths(win_pi.contiguous().data_ptr(), fdev.data_ptr(),
+                                              win_len.contiguous().data_ptr(), scale.data_ptr(), B, N,
+                                              paths.data_ptr(), lengths.data_ptr(), st.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream), "finalize")
+    assert bool((st == 0).all())
+    assert torch.equal(paths, want_paths) and torch.equal(lengths, want_len)
