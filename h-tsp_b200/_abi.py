@@ -35,6 +35,9 @@ SIGNATURES = {
     "htsp_select_best": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "htsp_finalize_paths": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "htsp_tour_length": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "htsp_env_knn": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "htsp_env_fragment": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp,
+                               _vp, _vp, _vp]),
     "htsp_env_splice": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "htsp_env_update": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp,
                              _vp, _vp]),

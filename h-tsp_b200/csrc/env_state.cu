@@ -32,6 +32,11 @@ env_splice_kernel(const long long* __restrict__ new_paths, const int32_t* __rest
   int32_t* ps = pos + (size_t)e * Ntot;
   const int T = tour_len[e], L = path_len[e];
   __shared__ int s_bad;
+  if (L == 0) {                       // inactive (finished) environment: the tour carries over unchanged
+    for (int i = tid; i < T; i += ENV_THREADS) tout[i] = tin[i];
+    if (tid == 0) status[e] = ENV_OK;
+    return;
+  }
   if (tid == 0) s_bad = ENV_OK;
   __syncthreads();
   // range check of the path (everything below indexes with it)

@@ -148,6 +148,22 @@ int htsp_env_update(const float* x, const int64_t* tour, const int32_t* tour_len
                     uint8_t* selected, uint8_t* available, float* neighbor_coord, float* state,
                     float* cur_len, float* reward, void* stream);
 
+/* ---- K7: fragment selection ----------------------------------
+ * htsp_env_knn = the k-NN lists of Env.reset (h_tsp.py:443-455): for every city the k nearest
+ * other cities under float32(float64 distance x 1000), ascending, equal distances by city id;
+ * x [E,Ntot,2] f32 -> knn [E,Ntot,k] i64.  No Ntot x Ntot matrix is materialised.
+ * htsp_env_fragment = Env.get_fragment_knn (h_tsp.py:482-542) for E environments: action [E,2] f32
+ * is the policy output after Env.scale_action ([0,1]^2); selected [E,Ntot] u8, tour / tour_len /
+ * pos as in K6; active [E] u8 or NULL.  Outputs: fragment [E,frag_len] i64 (what RLSolver.solve
+ * receives), new_cities [E,frag_len] i64 (-1 padded) with n_new [E], start_city [E] i32 (-1 for an
+ * empty tour), status [E] (1 = one of the reference's fragment-length asserts, h_tsp.py:641,656-658). */
+int htsp_env_knn(const float* x, int E, int Ntot, int k, int64_t* knn, void* stream);
+int htsp_env_fragment(const float* x, const uint8_t* selected, const int64_t* knn, int k,
+                      const int64_t* tour, const int32_t* tour_len, const int32_t* pos,
+                      const float* action, const uint8_t* active, int E, int Ntot, int frag_len,
+                      int max_new_nodes, int64_t* fragment, int64_t* new_cities, int32_t* n_new,
+                      int32_t* start_city, int32_t* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

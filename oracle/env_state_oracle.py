@@ -101,3 +101,74 @@ def env_step(state: LargeStateOracle, new_path: List[int]) -> Tuple[np.ndarray, 
     state.move_to(new_path)
     state.current_tour_len = np.float32(tour_distance(state.x, state.current_tour) / np.float32(DISTANCE_SCALE))
     return state.to_tensor(), np.float32(old_len - state.current_tour_len)
+
+
+# ------------------------------------------------------------------------------------------------
+# fragment selection: Env.reset k-NN (h_tsp.py:443-469),
+# rl_utils.get_nearest_city_idx (rl_utils.py:46-62), Env.get_fragment_knn (h_tsp.py:482-542) with
+# the numba FIFO expansion (h_tsp.py:472-480) and Env._extend_fragment (h_tsp.py:638-661)
+# ------------------------------------------------------------------------------------------------
+def knn_reset(x: np.ndarray, k: int) -> Tuple[np.ndarray, List[int]]:
+    """k nearest neighbours of every city under fp32(fp64 cdist x 1000) with an infinite diagonal,
+    ascending (torch.topk(largest=False)); equal distances are ordered by city index here (torch leaves
+    the order of exact ties unspecified).  Also the initial 2-city tour [0, knn[0][0]] (h_tsp.py:456-459)."""
+    xs = x.astype(np.float64) * DISTANCE_SCALE
+    n = x.shape[0]
+    knn = np.empty((n, k), dtype=np.int64)
+    for i in range(n):
+        d = np.sqrt(((xs - xs[i]) ** 2).sum(axis=1)).astype(np.float32)
+        d[i] = np.inf
+        knn[i] = np.lexsort((np.arange(n), d))[:k]
+    return knn, [0, int(knn[0, 0])]
+
+
+def nearest_city_idx(x: np.ndarray, coord: np.ndarray, mask: np.ndarray) -> int:
+    """rl_utils.get_nearest_city_idx: arg-min over the masked cities of float32(fp64 distance to
+    `coord`), first (lowest) city index among equal distances."""
+    cities = np.nonzero(mask)[0]
+    d = np.sqrt(((x[cities].astype(np.float64) - coord.astype(np.float64)[None]) ** 2).sum(axis=1)).astype(np.float32)
+    return int(cities[int(np.argmin(d))])
+
+
+def extend_fragment(tour: List[int], nearest_city: int, new_cities: List[int], frag_len: int) -> List[int]:
+    nearest_idx = tour.index(nearest_city)
+    total = frag_len - len(new_cities)
+    assert total > 0
+    offset = nearest_idx - total // 2
+    reorder = tour[offset:] + tour[:offset]            # Python slice semantics (negative offset wraps)
+    assert len(reorder) == len(tour)
+    frag = reorder[:total // 2] + list(new_cities) + reorder[total // 2:total]
+    assert len(frag) == frag_len and len(set(frag)) == frag_len
+    return frag
+
+
+def fragment_knn(state: LargeStateOracle, coord: np.ndarray, frag_len: int, max_new_nodes: int):
+    """Env.get_fragment_knn for an environment that is not done: (fragment, new_cities, start_city).
+    `coord` is the scaled action in [0,1]^2 (Env.scale_action has been applied by the caller)."""
+    x = state.x
+    construction_done = state.current_num_cities == state.graph_size
+    if not construction_done:
+        nearest_new = nearest_city_idx(x, coord, ~state.selected_mask)
+        if state.current_num_cities != 0:
+            start_city = nearest_city_idx(x, x[nearest_new], state.selected_mask)
+            new_start = nearest_city_idx(x, x[start_city], ~state.selected_mask)
+        else:
+            start_city, new_start = None, nearest_new
+        max_cities = max(max_new_nodes, frag_len - state.current_num_cities)
+        new_cities, queue, seen = [], [new_start], {new_start}
+        while queue and len(new_cities) < max_cities:
+            node = queue.pop(0)
+            new_cities.append(int(node))
+            for n in state.knn_neighbor[node]:
+                n = int(n)
+                if n not in seen and not state.selected_mask[n]:
+                    queue.append(n)
+                    seen.add(n)
+    else:
+        start_city = nearest_city_idx(x, coord, state.selected_mask)
+        new_cities = []
+    if state.current_num_cities != 0:
+        fragment = extend_fragment(state.current_tour, start_city, new_cities, frag_len)
+    else:
+        fragment = list(new_cities)
+    return fragment, new_cities, start_city

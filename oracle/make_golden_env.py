@@ -46,6 +46,7 @@ def main():
         out[f"{tag}_init_len"] = np.float32(st.current_tour_len)
         out[f"{tag}_init_state"] = st.to_tensor().numpy()
         paths, tours, tour_lens, lens, rewards, states, wrap = [], [], [], [], [], [], []
+        acts, frags, newc, starts = [], [], [], []
         solver = NNPathSolver()
         orig_step = env._step
 
@@ -65,12 +66,30 @@ def main():
             return res
 
         env._step = rec_step
+        orig_frag = env.get_fragment_knn
+
+        def rec_frag(a, _orig=orig_frag):
+            res = _orig(a)
+            acts.append(a.numpy().astype(np.float32).copy())          # the SCALED action in [0,1]^2
+            frags.append(res[0].numpy().astype(np.int64))
+            nc = np.full(frag_len, -1, dtype=np.int64)
+            nc[:len(res[1])] = res[1].numpy()
+            newc.append(nc)
+            starts.append(res[2].numpy().astype(np.float32))
+            return res
+
+        env.get_fragment_knn = rec_frag
         while not venv.done:
             venv.step(venv.random_action(), solver)
         L = max(len(p) for p in paths)
         pp = np.full((len(paths), L), -1, dtype=np.int64)
         for i, p in enumerate(paths):
             pp[i, :len(p)] = p
+        out[f"{tag}_actions"] = np.stack(acts)
+        out[f"{tag}_fragments"] = np.stack(frags)
+        out[f"{tag}_new_cities"] = np.stack(newc)
+        out[f"{tag}_start_coord"] = np.stack(starts)
+        out[f"{tag}_cfg"] = np.array([frag_len, max_new, k], dtype=np.int32)
         out[f"{tag}_paths"] = pp
         out[f"{tag}_path_len"] = np.array([len(p) for p in paths], dtype=np.int32)
         out[f"{tag}_tours"] = np.stack(tours)

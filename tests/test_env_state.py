@@ -222,3 +222,91 @@ def test_b200_state_tsp10000_properties(built_lib):
         assert abs(float(total[0]) - want) <= 1e-4 * want      # rewards telescope to the tour length
         sel = v.selected[0].cpu().numpy().astype(bool)
         assert sel.sum() == len(t) and sel[t].all()
+
+
+# ------------------------------------------------------------------------------------ fragment selection (8f-2)
+@pytest.mark.parametrize("tag", ["n300", "n1000"])
+def test_fragment_oracle_matches_reference_golden(egold, tag):
+    """Env.reset k-NN and Env.get_fragment_knn / _extend_fragment of the oracle against what the
+    unmodified reference produced on the recorded episodes (every step, exact integer equality)."""
+    x = egold[f"{tag}_x"]
+    frag_len, max_new, k = [int(v) for v in egold[f"{tag}_cfg"]]
+    knn, init = eo.knn_reset(x, k)
+    assert np.array_equal(knn, egold[f"{tag}_knn"]) and init == egold[f"{tag}_init_tour"].tolist()
+    st = eo.LargeStateOracle(x, knn, init)
+    for i in range(egold[f"{tag}_paths"].shape[0]):
+        frag, new_cities, start = eo.fragment_knn(st, egold[f"{tag}_actions"][i], frag_len, max_new)
+        assert frag == egold[f"{tag}_fragments"][i].tolist()
+        want_new = egold[f"{tag}_new_cities"][i]
+        assert new_cities == want_new[want_new >= 0].tolist()
+        assert np.array_equal(x[start] * 2 - 1, egold[f"{tag}_start_coord"][i])     # Env.unscale_action
+        eo.env_step(st, egold[f"{tag}_paths"][i, :egold[f"{tag}_path_len"][i]].tolist())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["n300", "n1000"])
+def test_b200_knn_and_fragments_match_reference_golden(built_lib, egold, tag):
+    """K7 against the unmodified reference's recorded episodes: the k-NN lists of Env.reset and, step
+    by step, the fragment / new cities / start city of Env.get_fragment_knn -- exact integers."""
+    from htsp_b200.vec_env import B200VecEnv
+    x = torch.from_numpy(egold[f"{tag}_x"]).cuda()
+    frag_len, max_new, k = [int(v) for v in egold[f"{tag}_cfg"]]
+    env = B200VecEnv(k=k, frag_len=frag_len, max_new_nodes=max_new, max_improvement_step=2)
+    env.reset(x[None])
+    assert np.array_equal(env.knn[0].cpu().numpy(), egold[f"{tag}_knn"])
+    assert env.state.current_tour(0) == egold[f"{tag}_init_tour"].tolist()
+    for i in range(egold[f"{tag}_paths"].shape[0]):
+        act = torch.from_numpy(egold[f"{tag}_actions"][i])[None].cuda()
+        frag, newc, n_new, start = env.fragments(act, scaled=True)
+        assert int(env._fstatus[0]) == 0
+        assert frag[0].cpu().tolist() == egold[f"{tag}_fragments"][i].tolist()
+        want_new = egold[f"{tag}_new_cities"][i]
+        assert int(n_new[0]) == int((want_new >= 0).sum())
+        assert newc[0].cpu().numpy()[: int(n_new[0])].tolist() == want_new[want_new >= 0].tolist()
+        got_start = egold[f"{tag}_x"][int(start[0])] * 2 - 1
+        assert np.array_equal(got_start, egold[f"{tag}_start_coord"][i])
+        env.state.step([egold[f"{tag}_paths"][i, :egold[f"{tag}_path_len"][i]].tolist()])
+
+
+@pytest.mark.gpu
+def test_b200_vec_env_full_loop_against_oracle(built_lib, sd6):
+    """The whole device-resident construction loop (fragment selection -> path solver hook -> scoring)
+    for 3 environments, mirrored step by step by the oracle driven with the SAME paths: fragments,
+    tours, state tensors identical; the episode ends with complete, duplicate-free tours."""
+    from htsp_b200 import B200PathSolver, B200RLSolver
+    from htsp_b200.vec_env import B200VecEnv
+    N, k, FL, MAXNEW = 260, 8, 40, 30
+    g = torch.Generator().manual_seed(21)
+    x = torch.rand(3, N, 2, generator=g)
+    model = B200PathSolver(state_dict=sd6, mode="x3", device="cuda", graph_size=FL)
+    hook = B200RLSolver(model, sample_size=8)
+    env = B200VecEnv(k=k, frag_len=FL, max_new_nodes=MAXNEW, max_improvement_step=1)
+    env.reset(x.cuda())
+    oracles = []
+    for e in range(3):
+        knn, init = eo.knn_reset(x[e].numpy(), k)
+        assert np.array_equal(knn, env.knn[e].cpu().numpy())
+        oracles.append(eo.LargeStateOracle(x[e].numpy(), knn, init))
+    steps = 0
+    while not env.done:
+        act = env.random_action()
+        active = (~env.dones).cpu().tolist()
+        frag, _, _, _ = env.fragments(act, ~env.dones)
+        scaled = (act * 0.5 + 0.5).cpu().numpy()
+        for e in range(3):
+            if active[e]:
+                want, _, _ = eo.fragment_knn(oracles[e], scaled[e], FL, MAXNEW)
+                assert frag[e].cpu().tolist() == want
+        states, rewards, dones = env.step(act, hook)
+        for e in range(3):
+            if active[e]:
+                path = env.state._paths[e].cpu().tolist()
+                st, r = eo.env_step(oracles[e], path)
+                assert env.state.current_tour(e) == oracles[e].current_tour
+                assert np.array_equal(states[e].cpu().numpy(), st)
+                assert abs(float(rewards[e]) - float(r)) <= 2e-5 * float(oracles[e].current_tour_len)
+        steps += 1
+        assert steps < 100
+    for e in range(3):
+        t = env.state.current_tour(e)
+        assert sorted(t) == list(range(N))
