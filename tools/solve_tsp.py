@@ -1,0 +1,103 @@
+#!/usr/bin/env python
+"""End-to-end large-TSP construction on the device-resident pipeline (BASELINE configs 3 / 4 shape):
+B200VecEnv (k-NN reset, fragment selection, scoring) + B200RLSolver (the path-solver hot path), with
+the reference's evaluate.py settings (k=40, frag_len=200, max_new_nodes=190, max_improvement_step=0,
+x8Aug, 200 POMO starts, bsz 16).  The upper-level PPO policy is out of scope: actions
+are the reference's random stand-in (VecEnv.random_action), and the lower-level weights are random
+init unless --ckpt gives a reference state_dict -- so the printed GAP IS NOT the paper's number; the
+solve TIME and the per-step breakdown are what this tool measures.
+
+  python tools/solve_tsp.py [--cities 10000] [--envs 16] [--mode x3] [--ckpt path_solver.ckpt]"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import htsp_b200  # noqa: E402,F401
+from htsp_b200 import B200PathSolver, B200RLSolver  # noqa: E402
+from htsp_b200.vec_env import B200VecEnv  # noqa: E402
+from htsp_b200.weights import synthetic_state_dict  # noqa: E402
+
+OPTIMA = {1000: 23.1182, 10000: 71.7778}      # rl4cop/eval.py:116 (mean optimal length, uniform instances)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cities", type=int, default=10000)
+    ap.add_argument("--envs", type=int, default=16)
+    ap.add_argument("--mode", default="x3")
+    ap.add_argument("--group", type=int, default=200)
+    ap.add_argument("--ckpt", default=None)
+    ap.add_argument("--seed", type=int, default=1234)
+    a = ap.parse_args()
+    dev = torch.device("cuda")
+    if a.ckpt:
+        sd = torch.load(a.ckpt, map_location="cpu")
+        sd = sd.get("state_dict", sd)
+    else:
+        sd = synthetic_state_dict(1234, 6)
+    model = B200PathSolver(state_dict=sd, mode=a.mode, device=dev, graph_size=200)
+    hook = B200RLSolver(model, sample_size=a.group)
+    g = torch.Generator().manual_seed(a.seed)
+    x = torch.rand(a.envs, a.cities, 2, generator=g).to(dev)
+    env = B200VecEnv(k=40, frag_len=200, max_new_nodes=190, max_improvement_step=0)
+    torch.manual_seed(a.seed)
+    # warm-up on a small instance (library load, workspace allocation, first-launch overheads)
+    w = B200VecEnv(k=40, frag_len=200, max_new_nodes=190, max_improvement_step=0)
+    w.reset(torch.rand(2, 600, 2, generator=g).to(dev))
+    while not w.done:
+        w.step(w.random_action(), hook)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    env.reset(x)
+    torch.cuda.synchronize()
+    t_reset = time.perf_counter() - t0
+    steps = 0
+    t_frag = t_solve = t_score = 0.0
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    while not env.done:
+        act = env.random_action()
+        ev[0].record()
+        active = ~env.dones
+        idx = torch.nonzero(active).squeeze(1)
+        frag, _, _, _ = env.fragments(act, active)
+        ev[1].record()
+        paths, _, status, _ = hook.solve_device(env.x.index_select(0, idx), frag.index_select(0, idx), None)
+        ev[2].record()
+        s = env.state
+        s._paths.zero_(); s._path_len.zero_()
+        s._paths.index_copy_(0, idx, paths)
+        s._path_len.index_fill_(0, idx, env.frag_len)
+        s.step_device(check=True)
+        ev[3].record()
+        torch.cuda.synchronize()
+        assert bool((status == 0).all())
+        t_frag += ev[0].elapsed_time(ev[1]); t_solve += ev[1].elapsed_time(ev[2]); t_score += ev[2].elapsed_time(ev[3])
+        steps += 1
+    total = time.perf_counter() - t0
+    lens = env.state.cur_len.cpu()
+    for e in range(a.envs):
+        t = env.state.current_tour(e)
+        assert len(t) == a.cities and len(set(t)) == a.cities
+    opt = OPTIMA.get(a.cities)
+    print(json.dumps({
+        "metric": f"TSP-{a.cities} end-to-end construction time (device-resident H-TSP loop)", "unit": "s",
+        "value": total, "higher_is_better": False, "n_instances": a.envs, "env_steps": steps,
+        "seconds_per_instance": total / a.envs,
+        "breakdown_ms": {"knn_reset": t_reset * 1e3, "fragment_selection": t_frag, "path_solver_hook": t_solve,
+                         "scoring": t_score},
+        "mean_tour_length": float(lens.mean()),
+        "gap_vs_rl4cop_eval_optimum": None if opt is None else float(lens.mean() / opt - 1),
+        "caveat": "random upper-level actions and " + ("checkpoint" if a.ckpt else "random-init") +
+                  " lower-level weights: the gap is not the paper's; time and breakdown are the measurement",
+        "config": {"k": 40, "frag_len": 200, "max_new_nodes": 190, "val_type": "x8Aug_2Traj", "pomo_starts": a.group,
+                   "arith": a.mode}}))
+
+
+if __name__ == "__main__":
+    main()
