@@ -808,8 +808,8 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
 #pragma unroll
               for (int jj = 0; jj < 4; ++jj) {
                 const int j = 4 * j4 + jj;
-                float z = (__uint_as_float(u[j]) + ca[jj]) * kTcdInvSqrtH;
-                if (EXACT) z = clip_tanh10(z);
+                float z = __uint_as_float(u[j]) + ca[jj];          // EXACT: 10 tanh(z / sqrt(128)); else the
+                if (EXACT) z = clip_tanh10(z * kTcdInvSqrtH);       // monotone pre-activation itself
                 if ((bits >> j) & 1u) z = -INFINITY;
                 if (LOGITS && lo_out != nullptr && valid && 16 * c + j < N) lo_out[16 * c + j] = z;
                 if (z > bj[j]) { bj[j] = z; cj[j] = c; }
@@ -828,8 +828,8 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
           pass(std::true_type{});
         } else {
           pass(std::false_type{});
-          if (__any_sync(0xffffffffu, valid && best > 3.0f)) pass(std::true_type{});
-          else best = (best == -INFINITY) ? best : clip_tanh10(best);    // candidates are exchanged as clipped logits
+          if (__any_sync(0xffffffffu, valid && best * kTcdInvSqrtH > 3.0f)) pass(std::true_type{});
+          else best = (best == -INFINITY) ? best : clip_tanh10(best * kTcdInvSqrtH);   // candidates are exchanged as clipped logits
         }
         tick(4);
         int a;
