@@ -8,7 +8,9 @@
 //              of the four operand tiles per k-block into a 3-stage shared-memory ring
 //   warp 1   : MMA issuer    -- tcgen05.mma.cta_group::1.kind::f16, M=128, N=128, K=16, three MMAs
 //              per k16 step (hi*hi, hi*lo, lo*hi) into one of two TMEM accumulators (128 columns each)
-//   warps 2-5: epilogue      -- tcgen05.ld (32 lanes x 32 columns per warp), bias / ReLU / residual /
+//   warps 2-9: epilogue      -- two warps per TMEM lane quarter (64 of the tile's 128 columns each):
+//              tcgen05.ld (32 lanes x 32 columns), transpose through shared memory so that every global
+//              load / store covers whole 128-byte lines, bias / ReLU / residual /
 //              eval-BatchNorm affine in registers, stores fp32 and/or the fp16 hi/lo split that the
 //              next layer's TMA reads; overlaps with the next tile's MMAs through the second accumulator.
 // Synchronisation is mbarrier-only (full/empty per stage, tmem_full/tmem_empty per accumulator);
@@ -21,9 +23,10 @@ namespace htsp {
 constexpr int GT_BM = 128, GT_BN = 128, GT_BK = 64, GT_STAGES = 3;
 constexpr int GT_TILE_BYTES = GT_BM * GT_BK * 2;            // 16 KB, one operand tile
 constexpr int GT_STAGE_BYTES = 4 * GT_TILE_BYTES;           // A_hi, A_lo, B_hi, B_lo
-constexpr int GT_THREADS = 192;
+constexpr int GT_THREADS = 320;          // TMA producer, MMA issuer, 8 epilogue warps
 constexpr uint32_t GT_TMEM_COLS = 256;
-constexpr size_t GT_SMEM_BYTES = (size_t)GT_STAGES * GT_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int GT_EPI_BYTES = 8 * 32 * 33 * 4;               // four 32 x 32 (+1 pad) fp32 transpose tiles
+constexpr size_t GT_SMEM_BYTES = (size_t)GT_STAGES * GT_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + GT_EPI_BYTES;
 
 struct GemmEpi {
   const float* bias;       // [Nout] or null
@@ -116,6 +119,7 @@ gemm_x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   unsigned char* smem = (unsigned char*)(((uintptr_t)gt_smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + (size_t)GT_STAGES * GT_STAGE_BYTES);
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * GT_STAGES + 4);
+  float* epi_smem = (float*)(smem + (size_t)GT_STAGES * GT_STAGE_BYTES + 256);
   const uint32_t full0 = gt_smem_u32(bars), empty0 = gt_smem_u32(bars + GT_STAGES);
   const uint32_t tfull0 = gt_smem_u32(bars + 2 * GT_STAGES), tempty0 = gt_smem_u32(bars + 2 * GT_STAGES + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -125,7 +129,7 @@ gemm_x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < GT_STAGES; ++s) { gt_mbar_init(full0 + 8 * s, 1); gt_mbar_init(empty0 + 8 * s, 1); }
-    for (int a = 0; a < 2; ++a) { gt_mbar_init(tfull0 + 8 * a, 1); gt_mbar_init(tempty0 + 8 * a, 4); }
+    for (int a = 0; a < 2; ++a) { gt_mbar_init(tfull0 + 8 * a, 1); gt_mbar_init(tempty0 + 8 * a, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -199,45 +203,53 @@ gemm_x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       const uint32_t acc = local & 1, acc_use = local >> 1;
       gt_mbar_wait(tfull0 + 8 * acc, acc_use & 1);
       gt_fence_after();
-      const int row = m_blk * GT_BM + q * 32 + lane;
-      const bool ok = row < E.M;
+      float* tr = epi_smem + (warp - 2) * (32 * 33);       // this warp's 32 x 32 transpose tile (row stride 33)
+      const int rsub = lane >> 3, csub = (lane & 7) * 4;   // store phase: 4 rows x 8 column quads per pass
 #pragma unroll 1
-      for (int c = 0; c < GT_BN / 32; ++c) {
+      for (int c = 2 * ((warp - 2) >> 2); c < 2 * ((warp - 2) >> 2) + 2; ++c) {
         uint32_t r[32];
         gt_tmem_ld32(tmem_base + acc * GT_BN + c * 32 + ((uint32_t)(q * 32) << 16), r);
         const int col0 = n_blk * GT_BN + c * 32;
-        if (ok) {
-          const size_t off = (size_t)row * E.Nout + col0;
+        // TMEM hands every lane one ROW (32 columns); global memory wants lanes along the columns:
+        // transpose through shared memory so that loads / stores cover whole 128-byte lines
+        __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float v[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                          __uint_as_float(r[j + 3])};
-            if (E.bias != nullptr) {
-              const float4 b = __ldg((const float4*)(E.bias + col0 + j));
-              v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-            }
+        for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = __uint_as_float(r[j]);
+        __syncwarp();
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), al4 = make_float4(1.f, 1.f, 1.f, 1.f), be4 = b4;
+        if (E.bias != nullptr) b4 = __ldg((const float4*)(E.bias + col0 + csub));
+        if (E.bn_alpha != nullptr) {
+          al4 = __ldg((const float4*)(E.bn_alpha + col0 + csub));
+          be4 = __ldg((const float4*)(E.bn_beta + col0 + csub));
+        }
+#pragma unroll
+        for (int rr = 0; rr < 32; rr += 4) {
+          const int rl = rr + rsub;
+          const int row = m_blk * GT_BM + q * 32 + rl;
+          float v[4] = {tr[rl * 33 + csub], tr[rl * 33 + csub + 1], tr[rl * 33 + csub + 2], tr[rl * 33 + csub + 3]};
+          if (row < E.M) {
+            const size_t off = (size_t)row * E.Nout + col0 + csub;
+            v[0] += b4.x; v[1] += b4.y; v[2] += b4.z; v[3] += b4.w;
             if (E.relu) {
 #pragma unroll
               for (int t = 0; t < 4; ++t) v[t] = fmaxf(v[t], 0.f);
             }
             if (E.residual != nullptr) {
-              const float4 x = __ldg((const float4*)(E.residual + off + j));
+              const float4 x = __ldg((const float4*)(E.residual + off));
               v[0] = x.x + v[0]; v[1] = x.y + v[1]; v[2] = x.z + v[2]; v[3] = x.w + v[3];
             }
             if (E.bn_alpha != nullptr) {
-              const float4 al = __ldg((const float4*)(E.bn_alpha + col0 + j));
-              const float4 be = __ldg((const float4*)(E.bn_beta + col0 + j));
-              v[0] = fmaf(v[0], al.x, be.x); v[1] = fmaf(v[1], al.y, be.y);
-              v[2] = fmaf(v[2], al.z, be.z); v[3] = fmaf(v[3], al.w, be.w);
+              v[0] = fmaf(v[0], al4.x, be4.x); v[1] = fmaf(v[1], al4.y, be4.y);
+              v[2] = fmaf(v[2], al4.z, be4.z); v[3] = fmaf(v[3], al4.w, be4.w);
             }
-            if (E.y32 != nullptr) *(float4*)(E.y32 + off + j) = make_float4(v[0], v[1], v[2], v[3]);
+            if (E.y32 != nullptr) *(float4*)(E.y32 + off) = make_float4(v[0], v[1], v[2], v[3]);
             if (E.yhi != nullptr) {
               __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
               const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
               __half2 l0 = __floats2half2_rn(v[0] - f0.x, v[1] - f0.y);
               __half2 l1 = __floats2half2_rn(v[2] - f1.x, v[3] - f1.y);
-              *(uint2*)(E.yhi + off + j) = make_uint2(*(uint32_t*)&h0, *(uint32_t*)&h1);
-              *(uint2*)(E.ylo + off + j) = make_uint2(*(uint32_t*)&l0, *(uint32_t*)&l1);
+              *(uint2*)(E.yhi + off) = make_uint2(*(uint32_t*)&h0, *(uint32_t*)&h1);
+              *(uint2*)(E.ylo + off) = make_uint2(*(uint32_t*)&l0, *(uint32_t*)&l1);
             }
           }
         }
