@@ -64,6 +64,19 @@ __device__ __forceinline__ void tcd_split8(const float* v, uint4& hi, uint4& lo)
   lo = *reinterpret_cast<uint4*>(l);
 }
 
+// same split with the residual as one packed FFMA2 per pair (exact: x - hi is representable)
+__device__ __forceinline__ void tcd_split8_packed(const float* v, uint4& hi, uint4& lo) {
+  __half2 h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    const float2 r = __ffma2_rn(__half22float2(h[i]), make_float2(-1.f, -1.f), make_float2(v[2 * i], v[2 * i + 1]));
+    l[i] = __floats2half2_rn(r.x, r.y);
+  }
+  hi = *reinterpret_cast<uint4*>(h);
+  lo = *reinterpret_cast<uint4*>(l);
+}
+
 // proj fp32 [Bp*N, 640] (K | V | QL | QF | K2) -> operand image
 __global__ void __launch_bounds__(256)
 decode_tc_pack_kernel(const float* __restrict__ proj, int Bp, int N, int NP, unsigned char* __restrict__ img) {
@@ -713,7 +726,8 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
         // a half without a finite score has l = 0 and contributes nothing
         const float sa = (la > 0.f) ? ex2_approx(ma - M) : 0.f;
         const float sb = (lb > 0.f) ? ex2_approx(mb - M) : 0.f;
-        const float inv = 1.f / (la * sa + lb * sb);
+        float inv;         // MUFU reciprocal (1 ulp): the normalisation error is far below the fp16x2 split
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(la * sa + lb * sb));
         const float wa = sa * inv, wb = sb * inv;
         float v[16];
 #pragma unroll
@@ -727,8 +741,8 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
           for (int j = 0; j < 16; ++j) dO[j] = v[j];
         }
         uint4 h0, l0, h1, l1;
-        tcd_split8(v, h0, l0);
-        tcd_split8(v + 8, h1, l1);
+        tcd_split8_packed(v, h0, l0);
+        tcd_split8_packed(v + 8, h1, l1);
         unsigned char* p = stg + (h >> 2) * 16384;
         const uint32_t c = (uint32_t)(h & 3) * 2;
         *(uint4*)(p + tc::sw128_off((uint32_t)row, c)) = h0;
