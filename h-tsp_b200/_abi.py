@@ -39,6 +39,11 @@ SIGNATURES = {
     "htsp_env_fragment": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp,
                                _vp, _vp, _vp]),
     "htsp_env_splice": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "htsp_policy_n_tensors": (_i, []),
+    "htsp_policy_blob_bytes": (_sz, [_i, _i, _i]),
+    "htsp_policy_pack_weights": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _vp, _vp]),
+    "htsp_policy_workspace_bytes": (_sz, [_i, _i, _i]),
+    "htsp_policy_forward": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "htsp_env_update": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp,
                              _vp, _vp]),
 }

@@ -1,4 +1,4 @@
-// K3, Blackwell-native variant (HTSP_MODE_TC_X3 / HTSP_MODE_TC_FAST, N <= 224): persistent POMO
+// K3, Blackwell-native variant (HTSP_MODE_TC_X3 / HTSP_MODE_TC_FAST, 17 <= N <= 208): persistent POMO
 // rollout kernel on tcgen05 tensor cores with TMEM accumulators.
 //
 // One CTA owns one instance (all G <= 256 POMO starts, two M = 128 row tiles) for all N-2 decode
@@ -15,10 +15,12 @@
 // Arithmetic is split-fp16 (x = hi + lo, three MMAs per product, fp32 accumulation; DESIGN.md
 // section 4); HTSP_MODE_TC_FAST drops the lo terms of S only.
 //
-// Warp roles (320 threads): warp 0 = operand producer (cp.async.bulk of pre-swizzled K/V/K2 tiles
-// from the L2-resident per-instance image into a 3-stage ring, shared by both row tiles), warp 1 =
-// MMA issuer (one thread), warps 2-5 / 6-9 = softmax warps of tile 0 / 1 (warp%4 selects the TMEM
-// lane quarter).  All synchronisation is mbarrier based; tcgen05.commit publishes accumulators and
+// Warp roles (640 threads = 20 warps; dispatch at the end of the kernel): warp 0 = operand producer
+// (cp.async.bulk of pre-swizzled K/V/K2 blocks from the L2-resident per-instance image into one 3-stage
+// ring per row tile); warp 3 = MMA issuer of tile 0, warp 19 (or 2) = issuer of tile 1 (one elected
+// lane issues); warps 4-19 = softmax / state warps: tile t, key half X, lane quarter q = warp % 4 --
+// two warps share every 32-row lane quarter and split the keys between them ("split-K").  All
+// synchronisation is mbarrier or named-barrier based; tcgen05.commit publishes accumulators and
 // releases ring stages.
 #include <stdlib.h>
 #include <string.h>

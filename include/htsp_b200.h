@@ -164,6 +164,28 @@ int htsp_env_fragment(const float* x, const uint8_t* selected, const int64_t* kn
                       int max_new_nodes, int64_t* fragment, int64_t* new_cities, int32_t* n_new,
                       int32_t* start_city, int32_t* status, void* stream);
 
+/* ---- K8: upper-level policy forward ---------------------------
+ * HTSP_PPO.forward (h_tsp.py:1272-1276): ActorPPO.forward (rl_models.py:329-336) o IMPALAEncoder.forward
+ * (rl_models.py:187-273) o IMPALACNN.forward (rl_models.py:117-133) with the reference's default geometry
+ * (input_dim 8, bev grid 100 x 100 over [0,1]^2, depths [16,32,32]); embed = cfg.embedding_dim (128),
+ * mid = cfg.acotr_mid_dim (128), adim = cfg.nb_actions (2).
+ * htsp_policy_pack_weights: host fp32 tensors in the order of HTSP_PPO.state_dict() restricted to
+ *   encoder.input_transform.{0.weight,1.weight,1.bias}; per block i = 0..2: encoder.cnn.feat_convs.i.0,
+ *   resnet1.i.1, resnet1.i.3, resnet2.i.1, resnet2.i.3 (weight, bias each); encoder.cnn.fc;
+ *   actor.net.0.0, actor.net.0.2, actor.net.1, actor.net.3 (weight, bias each)  -> device blob.
+ * htsp_policy_forward: state [E,Ntot,8] f32 (the tensor htsp_env_update writes) -> feat [E,embed]
+ *   (graph_feat) and action [E,adim] = tanh(actor.net(feat)); image_out (may be NULL) receives the pseudo
+ *   image [E,embed/2,100,100] the reference hands to its CNN.  Pillar ids must stay exact in fp32
+ *   (E * 10^4 < 2^24, rl_models.py:207-211).                                                     */
+int htsp_policy_n_tensors(void);
+size_t htsp_policy_blob_bytes(int embed, int mid, int adim);
+int htsp_policy_pack_weights(const float* const* host_tensors, int n_tensors, int embed, int mid,
+                             int adim, void* dev_blob, void* stream);
+size_t htsp_policy_workspace_bytes(int E, int Ntot, int embed);
+int htsp_policy_forward(const void* blob, int embed, int mid, int adim, const float* state, int E,
+                        int Ntot, float* feat, float* action, float* image_out, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

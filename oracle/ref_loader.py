@@ -88,9 +88,31 @@ def _install_stubs() -> None:
     if not _have("omegaconf"):
         _stub("omegaconf", DictConfig=dict, OmegaConf=_Dummy)
     for name in ("dgl", "dgl.function", "torch_geometric", "torch_geometric.nn",
-                 "torch_scatter", "tsplib95", "lkh", "fast_pytorch_kmeans", "mistree"):
+                 "tsplib95", "lkh", "fast_pytorch_kmeans", "mistree"):
         if not _have(name):
             _stub(name)
+    if not _have("torch_scatter"):
+        # pytorch-scatter 2.0.9 (requirements.txt:159) is absent.  The upper policy calls exactly two of its
+        # functions (rl_models.py:217,230), both with dim=0 and a dense 0..G-1 index from torch.unique; their
+        # published semantics, restated with stock torch ops:
+        #   scatter_mean(src, index, dim=0): out[g] = sum(src[index == g]) / max(count(index == g), 1)
+        #   scatter_max(src, index, dim=0):  (out, argmax), out[g] = max(src[index == g])
+        def scatter_mean(src, index, dim=0):
+            assert dim == 0 and index.ndim == 1
+            n = int(index.max()) + 1
+            out = torch.zeros((n,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device).index_add_(0, index, src)
+            cnt = torch.zeros(n, dtype=src.dtype, device=src.device).index_add_(
+                0, index, torch.ones(index.shape[0], dtype=src.dtype, device=src.device))
+            return out / cnt.clamp(min=1).view((n,) + (1,) * (src.ndim - 1))
+
+        def scatter_max(src, index, dim=0):
+            assert dim == 0 and index.ndim == 1 and src.ndim == 2
+            n = int(index.max()) + 1
+            out = torch.zeros(n, src.shape[1], dtype=src.dtype, device=src.device)
+            out.scatter_reduce_(0, index[:, None].expand_as(src), src, "amax", include_self=False)
+            return out, None
+
+        _stub("torch_scatter", scatter_mean=scatter_mean, scatter_max=scatter_max)
     if not _have("matplotlib"):
         _stub("matplotlib", use=lambda *a, **k: None)
         _stub("matplotlib.pyplot")
@@ -126,6 +148,15 @@ def load_h_tsp_module():
     h_tsp = importlib.import_module("h_tsp")
     _loaded["h_tsp"] = h_tsp
     return h_tsp
+
+
+def load_rl_models_module():
+    """Returns the reference module ``rl_models`` (IMPALAEncoder, ActorPPO: the upper-level policy)."""
+    if "rl_models" in _loaded:
+        return _loaded["rl_models"]
+    load_path_solver_module()
+    _loaded["rl_models"] = importlib.import_module("rl_models")
+    return _loaded["rl_models"]
 
 
 def make_cfg(n_layers: int = 6, graph_size: int = 200, group_size: int = 200,

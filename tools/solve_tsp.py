@@ -2,12 +2,14 @@
 """End-to-end large-TSP construction on the device-resident pipeline (BASELINE configs 3 / 4 shape):
 B200VecEnv (k-NN reset, fragment selection, scoring) + B200RLSolver (the path-solver hot path), with
 the reference's evaluate.py settings (k=40, frag_len=200, max_new_nodes=190, max_improvement_step=0,
-x8Aug, 200 POMO starts, bsz 16).  The upper-level PPO policy is out of scope: actions
-are the reference's random stand-in (VecEnv.random_action), and the lower-level weights are random
-init unless --ckpt gives a reference state_dict -- so the printed GAP IS NOT the paper's number; the
-solve TIME and the per-step breakdown are what this tool measures.
+x8Aug, 200 POMO starts, bsz 16).  --policy upper runs the upper-level policy forward on the device too
+(B200UpperPolicy, evaluate.py:84); --policy random uses the reference's random stand-in
+(VecEnv.random_action, evaluate.py:86).  Trained checkpoints are not available offline: upper and
+lower weights are random init unless --ckpt / --upper-ckpt give reference state_dicts -- so the printed
+GAP IS NOT the paper's number; the solve TIME and the per-step breakdown are what this tool measures.
 
-  python tools/solve_tsp.py [--cities 10000] [--envs 16] [--mode x3] [--ckpt path_solver.ckpt]"""
+  python tools/solve_tsp.py [--cities 10000] [--envs 16] [--mode x3] [--policy upper|random]
+                            [--ckpt path_solver.ckpt] [--upper-ckpt htsp_ppo.ckpt]"""
 import argparse
 import json
 import os
@@ -22,6 +24,7 @@ import htsp_b200  # noqa: E402,F401
 from htsp_b200 import B200PathSolver, B200RLSolver  # noqa: E402
 from htsp_b200.vec_env import B200VecEnv  # noqa: E402
 from htsp_b200.weights import synthetic_state_dict  # noqa: E402
+from htsp_b200.upper_policy import B200UpperPolicy, synthetic_policy_state_dict  # noqa: E402
 
 OPTIMA = {1000: 23.1182, 10000: 71.7778}      # rl4cop/eval.py:116 (mean optimal length, uniform instances)
 
@@ -34,6 +37,8 @@ def main():
     ap.add_argument("--group", type=int, default=200)
     ap.add_argument("--ckpt", default=None)
     ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--policy", choices=("upper", "random"), default="upper")
+    ap.add_argument("--upper-ckpt", default=None)
     a = ap.parse_args()
     dev = torch.device("cuda")
     if a.ckpt:
@@ -43,6 +48,15 @@ def main():
         sd = synthetic_state_dict(1234, 6)
     model = B200PathSolver(state_dict=sd, mode=a.mode, device=dev, graph_size=200)
     hook = B200RLSolver(model, sample_size=a.group)
+    policy = None
+    if a.policy == "upper":
+        if a.upper_ckpt:
+            usd = torch.load(a.upper_ckpt, map_location="cpu")
+            usd = usd.get("state_dict", usd)
+        else:
+            usd = synthetic_policy_state_dict(a.seed)
+        policy = B200UpperPolicy(usd, dev, embedding_dim=usd["encoder.cnn.fc.weight"].shape[0],
+                                 mid_dim=usd["actor.net.0.0.weight"].shape[0])
     g = torch.Generator().manual_seed(a.seed)
     x = torch.rand(a.envs, a.cities, 2, generator=g).to(dev)
     env = B200VecEnv(k=40, frag_len=200, max_new_nodes=190, max_improvement_step=0)
@@ -50,18 +64,20 @@ def main():
     # warm-up on a small instance (library load, workspace allocation, first-launch overheads)
     w = B200VecEnv(k=40, frag_len=200, max_new_nodes=190, max_improvement_step=0)
     w.reset(torch.rand(2, 600, 2, generator=g).to(dev))
+    ws = w.state.state
     while not w.done:
-        w.step(w.random_action(), hook)
+        ws, _, _ = w.step(w.random_action() if policy is None else policy(ws), hook)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    env.reset(x)
+    state = env.reset(x)
     torch.cuda.synchronize()
     t_reset = time.perf_counter() - t0
     steps = 0
-    t_frag = t_solve = t_score = 0.0
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    t_pol = t_frag = t_solve = t_score = 0.0
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     while not env.done:
-        act = env.random_action()
+        ev[4].record()
+        act = env.random_action() if policy is None else policy(state)
         ev[0].record()
         active = ~env.dones
         idx = torch.nonzero(active).squeeze(1)
@@ -73,10 +89,11 @@ def main():
         s._paths.zero_(); s._path_len.zero_()
         s._paths.index_copy_(0, idx, paths)
         s._path_len.index_fill_(0, idx, env.frag_len)
-        s.step_device(check=True)
+        state, _ = s.step_device(check=True)
         ev[3].record()
         torch.cuda.synchronize()
         assert bool((status == 0).all())
+        t_pol += ev[4].elapsed_time(ev[0])
         t_frag += ev[0].elapsed_time(ev[1]); t_solve += ev[1].elapsed_time(ev[2]); t_score += ev[2].elapsed_time(ev[3])
         steps += 1
     total = time.perf_counter() - t0
@@ -89,11 +106,14 @@ def main():
         "metric": f"TSP-{a.cities} end-to-end construction time (device-resident H-TSP loop)", "unit": "s",
         "value": total, "higher_is_better": False, "n_instances": a.envs, "env_steps": steps,
         "seconds_per_instance": total / a.envs,
-        "breakdown_ms": {"knn_reset": t_reset * 1e3, "fragment_selection": t_frag, "path_solver_hook": t_solve,
+        "breakdown_ms": {"knn_reset": t_reset * 1e3, "upper_policy": t_pol, "fragment_selection": t_frag, "path_solver_hook": t_solve,
                          "scoring": t_score},
         "mean_tour_length": float(lens.mean()),
         "gap_vs_rl4cop_eval_optimum": None if opt is None else float(lens.mean() / opt - 1),
-        "caveat": "random upper-level actions and " + ("checkpoint" if a.ckpt else "random-init") +
+        "upper_policy": a.policy if a.policy == "random" else ("checkpoint" if a.upper_ckpt else "random-init weights"),
+        "caveat": ("random upper-level actions" if policy is None else
+                   ("checkpoint" if a.upper_ckpt else "random-init") + " upper-level policy") + " and " +
+                  ("checkpoint" if a.ckpt else "random-init") +
                   " lower-level weights: the gap is not the paper's; time and breakdown are the measurement",
         "config": {"k": 40, "frag_len": 200, "max_new_nodes": 190, "val_type": "x8Aug_2Traj", "pomo_starts": a.group,
                    "arith": a.mode}}))
