@@ -70,7 +70,12 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
-        self.gpu, self.lines, self.proc = gpu_index, [], None
+        self.gpu, self.lines, self.proc, self.skip = gpu_index, [], None, 0
+
+    def mark(self):
+        """Start of the timed region: samples taken before (nvidia-smi attaching to the driver can stall
+        launches for ~100 ms, so the process is started during the warm-up) are dropped."""
+        self.skip = len(self.lines)
 
     def start(self):
         try:
@@ -94,7 +99,7 @@ class ClockSampler:
         except Exception:
             pass
         sm, mx, reasons, power = [], [], set(), []
-        for ln in self.lines:
+        for ln in self.lines[self.skip:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -268,7 +273,10 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput (value) ------------------------------------------------
+    sampler = ClockSampler(local)
     for i in range(args.warmup):
+        if rank == 0 and i == args.warmup - 1:
+            sampler.start()           # attach nvidia-smi during the last warm-up step, not inside the timed region
         step(i)
     barrier()
     timers = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -276,9 +284,10 @@ def run_b200(args):
     for a, b in timers:       # materialise the cudaEvent_t handles; the library re-records them
         a.record(); b.record()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        if sampler.proc is None:
+            sampler.start()
+        sampler.mark()
     launches0 = lib.htsp_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -327,6 +336,29 @@ def run_b200(args):
     h2d = B * N * 2 * 4 + 2 * B * 8
     d2h = B * N * 8 + B * 4
 
+    # ---- the same device-resident steps in the fp16-class mode (config 2 is quoted "bf16", logits <= 1e-3) ----
+    fast_value = fast_ms = None
+    if args.mode == "x3":
+        fmodel = B200PathSolver(state_dict=synthetic_state_dict(1234, L), mode="fast", device=dev)
+        fmodel.first_action_override = model.first_action_override
+        for i in range(2):
+            fmodel(xs_dev[i % n_in], src, tgt, val_type="noAug_nTraj", return_pi=True, group_size=G)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for i in range(args.steps):
+            fl, fp = fmodel(xs_dev[(2 + i) % n_in], src, tgt, val_type="noAug_nTraj", return_pi=True, group_size=G)
+            if world > 1:
+                fp, fl = gather_tours(fp, fl, total)
+        f1.record()
+        barrier()
+        fms = torch.tensor([f0.elapsed_time(f1)], device=dev)
+        if world > 1:
+            dist.all_reduce(fms, op=dist.ReduceOp.MAX)
+        fast_ms = float(fms) / args.steps
+        fast_value = total / (fast_ms / 1e3)
+        del fmodel
+
     if rank == 0:
         tc_peak, hbm_peak, peak_src = load_peaks()
         enc_f, reset_f, dec_f = algorithmic_flops(N, G, L)
@@ -343,7 +375,7 @@ def run_b200(args):
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32": "f32", "x3": "f16x3 (split-fp32 on fp16 tensor cores, f32 accumulate)",
-                      "fast": "f16x3/f16"}[args.mode],
+                      "fast": "f16x3 with single-fp16 softmax probabilities"}[args.mode],
             "data": "synthetic uniform coords, random-init weights (seed 1234)",
             "config": workload_config(args),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
@@ -361,6 +393,10 @@ def run_b200(args):
                              "sample": f"{args.cpu_sample} subproblems (N={N}, G={G}, noAug_nTraj, "
                                        f"L={L}) in {cpu_dt:.1f} s, oracle port, torch CPU fp32",
                              "host_cpus": os.cpu_count()},
+            "fast_mode": {"value": fast_value, "unit": UNIT, "ms_per_step": fast_ms,
+                          "arith": "softmax probabilities stored as single fp16 (row sums from the rounded values); "
+                                   "scores, values and pointer logits keep the split: logits within 1e-3 of the fp32 "
+                                   "reference (measured ~2.5e-4) instead of ~3e-5"},
             "gpu_eager_pytorch_port": {"value": gpu_port, "unit": UNIT, "kind": "port",
                                        "sample": "256 subproblems, oracle port as eager PyTorch fp32 (TF32 off) on "
                                                  "this GPU: an upper bound on the unmodified reference, which adds "

@@ -13,7 +13,8 @@
 //   U     = O K2^T               tcgen05.mma (multi_head_combine folded into the keys, K2 = emb Wc)
 //   argmax_j 10 tanh((U + c0)/sqrt(128)) over unvisited j, state update, next query gather.
 // Arithmetic is split-fp16 (x = hi + lo, three MMAs per product, fp32 accumulation; DESIGN.md
-// section 4); HTSP_MODE_TC_FAST drops the lo terms of S only.
+// section 4); HTSP_MODE_TC_FAST stores the softmax probabilities P as a single fp16 (S, V and the logits keep
+// the split).
 //
 // Warp roles (640 threads = 20 warps; dispatch at the end of the kernel): warp 0 = operand producer
 // (cp.async.bulk of pre-swizzled K/V/K2 blocks from the L2-resident per-instance image into one 3-stage
@@ -66,17 +67,35 @@ __device__ __forceinline__ void tcd_split8(const float* v, uint4& hi, uint4& lo)
   lo = *reinterpret_cast<uint4*>(l);
 }
 
-// same split with the residual as one packed FFMA2 per pair (exact: x - hi is representable)
+// sm_100 mixed-precision add (one FHADD: fp16 operand read straight from a packed register half)
+__device__ __forceinline__ float tcd_sub_h_f(uint32_t pair, int hi_half, float x) {   // half - x
+  float r;
+  const unsigned short h = hi_half ? (unsigned short)(pair >> 16) : (unsigned short)(pair & 0xffffu);
+  asm("sub.rn.f32.f16 %0, %1, %2;" : "=f"(r) : "h"(h), "f"(x));
+  return r;
+}
+__device__ __forceinline__ float tcd_add_h_f(uint32_t pair, int hi_half, float acc) {   // half + acc
+  float r;
+  const unsigned short h = hi_half ? (unsigned short)(pair >> 16) : (unsigned short)(pair & 0xffffu);
+  asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(r) : "h"(h), "f"(acc));
+  return r;
+}
+// x = hi + lo for a pair: hi = RN_fp16(x); x - hi is exact in fp32 (<= 13 significant bits), lo = RN_fp16(x - hi).
+// The residual is one packed FFMA2 after unpacking hi (2 HADD2.F32); the 2-FHADD form (tcd_sub_h_f) has
+// fewer instructions but measured 1.8 % slower on the whole rollout.
+__device__ __forceinline__ void tcd_split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 hh = __floats2half2_rn(x0, x1);
+  hi = *reinterpret_cast<const uint32_t*>(&hh);
+  const float2 r = __ffma2_rn(__half22float2(hh), make_float2(-1.f, -1.f), make_float2(x0, x1));
+  const __half2 ll = __floats2half2_rn(r.x, r.y);
+  lo = *reinterpret_cast<const uint32_t*>(&ll);
+}
 __device__ __forceinline__ void tcd_split8_packed(const float* v, uint4& hi, uint4& lo) {
-  __half2 h[4], l[4];
+  uint32_t h[4], l[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-    const float2 r = __ffma2_rn(__half22float2(h[i]), make_float2(-1.f, -1.f), make_float2(v[2 * i], v[2 * i + 1]));
-    l[i] = __floats2half2_rn(r.x, r.y);
-  }
-  hi = *reinterpret_cast<uint4*>(h);
-  lo = *reinterpret_cast<uint4*>(l);
+  for (int i = 0; i < 4; ++i) tcd_split_pair(v[2 * i], v[2 * i + 1], h[i], l[i]);
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 // proj fp32 [Bp*N, 640] (K | V | QL | QF | K2) -> operand image
@@ -206,7 +225,11 @@ __device__ __forceinline__ void tld_wait16(uint32_t (&r)[32]) {
 }
 template <int W>
 __device__ __forceinline__ void tst(uint32_t taddr, const uint32_t (&r)[32]) {
-  if (W == 32) {
+  if (W == 8) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr),
+                 "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+  } else if (W == 32) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
         "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
@@ -226,7 +249,10 @@ __device__ __forceinline__ void tst(uint32_t taddr, const uint32_t (&r)[32]) {
   }
 }
 
-template <bool LOGITS, bool DEBUG>
+// PSINGLE (HTSP_MODE_TC_FAST): the softmax probabilities are stored as one fp16 (no lo part), the row
+// sum is taken from the ROUNDED values so that the normalisation stays consistent; S, V and the pointer
+// logits keep the full split.  Logit error ~2.5e-4 (bound 1e-3) instead of ~3e-5.
+template <bool LOGITS, bool DEBUG, bool PSINGLE>
 __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs A) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31;
@@ -341,10 +367,8 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
           const uint32_t d = dS + (X ? K0 : 0);
           if (tc::elect_one()) {
             tc::mma_ss_lo(d, a_hi, b_hi, idK[X], 0);
-            if (!A.fast) {
-              tc::mma_ss_lo(d, a_hi, b_lo, idK[X], 1);
-              tc::mma_ss_lo(d, a_lo, b_hi, idK[X], 1);
-            }
+            tc::mma_ss_lo(d, a_hi, b_lo, idK[X], 1);
+            tc::mma_ss_lo(d, a_lo, b_hi, idK[X], 1);
             tc::commit(BAR(TB_SFULL + X));
           }
           __syncwarp();
@@ -360,7 +384,7 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
               const uint32_t p_hi = dS + 16 * ks, p_lo = p_hi + 8;
               tc::mma_ts_lo(dO + 16 * X, p_hi, v_hi, idO, ks != k_lo);
               tc::mma_ts_lo(dO + 16 * X, p_hi, v_lo, idO, 1);
-              tc::mma_ts_lo(dO + 16 * X, p_lo, v_hi, idO, 1);
+              if (!PSINGLE) tc::mma_ts_lo(dO + 16 * X, p_lo, v_hi, idO, 1);
             }
             tc::commit(BAR(TB_OFULL + X));
           }
@@ -570,22 +594,43 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
 #pragma unroll
           for (int j = 0; j < 16; ++j) tv[j] = ((bits >> j) & 1u) ? -INFINITY : __uint_as_float(s[j]);
           float csum;
+          uint32_t out[32];
           auto expo = [&]() {
-            float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
             const float2 nm = make_float2(-m, -m);
+            if (!PSINGLE) {
+              float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float2 d0 = __fadd2_rn(make_float2(tv[j], tv[j + 1]), nm);
-              const float2 d1 = __fadd2_rn(make_float2(tv[j + 2], tv[j + 3]), nm);
-              p[j] = ex2_approx(d0.x);
-              p[j + 1] = ex2_approx(d0.y);
-              p[j + 2] = ex2_approx(d1.x);
-              p[j + 3] = ex2_approx(d1.y);
-              acc0 = __fadd2_rn(acc0, make_float2(p[j], p[j + 1]));
-              acc1 = __fadd2_rn(acc1, make_float2(p[j + 2], p[j + 3]));
+              for (int j = 0; j < 16; j += 4) {
+                const float2 d0 = __fadd2_rn(make_float2(tv[j], tv[j + 1]), nm);
+                const float2 d1 = __fadd2_rn(make_float2(tv[j + 2], tv[j + 3]), nm);
+                p[j] = ex2_approx(d0.x);
+                p[j + 1] = ex2_approx(d0.y);
+                p[j + 2] = ex2_approx(d1.x);
+                p[j + 3] = ex2_approx(d1.y);
+                acc0 = __fadd2_rn(acc0, make_float2(p[j], p[j + 1]));
+                acc1 = __fadd2_rn(acc1, make_float2(p[j + 2], p[j + 3]));
+              }
+              acc0 = __fadd2_rn(acc0, acc1);
+              csum = acc0.x + acc0.y;
+            } else {
+              // single fp16 P: pack first, then sum the rounded halves (one FHADD each, four chains)
+              float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float2 d0 = __fadd2_rn(make_float2(tv[j], tv[j + 1]), nm);
+                const float2 d1 = __fadd2_rn(make_float2(tv[j + 2], tv[j + 3]), nm);
+                const __half2 h0 = __floats2half2_rn(ex2_approx(d0.x), ex2_approx(d0.y));
+                const __half2 h1 = __floats2half2_rn(ex2_approx(d1.x), ex2_approx(d1.y));
+                const uint32_t u0 = *reinterpret_cast<const uint32_t*>(&h0), u1 = *reinterpret_cast<const uint32_t*>(&h1);
+                out[j >> 1] = u0;
+                out[(j >> 1) + 1] = u1;
+                a0 = tcd_add_h_f(u0, 0, a0);
+                a1 = tcd_add_h_f(u0, 1, a1);
+                a2 = tcd_add_h_f(u1, 0, a2);
+                a3 = tcd_add_h_f(u1, 1, a3);
+              }
+              csum = (a0 + a1) + (a2 + a3);
             }
-            acc0 = __fadd2_rn(acc0, acc1);
-            csum = acc0.x + acc0.y;
           };
           // rows that have not seen a finite score yet (always the case in the first chunk) take their
           // shift from this chunk's maximum up front instead of tripping the overflow path below
@@ -608,7 +653,7 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
               tc::st_wait();
               for (int cc = 16 * c_lo; cc < c0; cc += 16) {
                 uint32_t r[16];
-                tc::ld16(tS + cc, r);
+                tc::ld16(tS + cc, r);      // PSINGLE: columns 8-15 are stale scores, rescaled but never read
                 tc::ld16_wait(r);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
@@ -624,16 +669,14 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
             expo();
           }
           l += csum;
-          uint32_t out[32];
+          if (!PSINGLE) {
 #pragma unroll
-          for (int j = 0; j < 16; j += 2) {     // x = hi + lo; the residual is one packed FFMA2 (exact)
-            const __half2 hh = __floats2half2_rn(p[j], p[j + 1]);
-            const float2 r = __ffma2_rn(__half22float2(hh), make_float2(-1.f, -1.f), make_float2(p[j], p[j + 1]));
-            const __half2 ll = __floats2half2_rn(r.x, r.y);
-            out[j >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
-            out[8 + (j >> 1)] = *reinterpret_cast<const uint32_t*>(&ll);
+            for (int j = 0; j < 16; j += 2)       // x = hi + lo; the residual hi - x is one exact FHADD per element
+              tcd_split_pair(p[j], p[j + 1], out[j >> 1], out[8 + (j >> 1)]);
+            tst<16>(tS + c0, out);
+          } else {
+            tst<8>(tS + c0, out);
           }
-          tst<16>(tS + c0, out);
         };
         // 16-key chunks, two per 32-bit word of the visited mask; four warps per scheduler hide the
         // TMEM load latency
@@ -938,7 +981,7 @@ size_t decode_tc_dbg_floats(int N) {
   return (size_t)2 * 8 * 128 * NP + (size_t)256 * 128 + (size_t)256 * NP + 256;
 }
 
-template <bool LOGITS, bool DEBUG>
+template <bool LOGITS, bool DEBUG, bool PSINGLE>
 static int launch_tcd(const TcdArgs& a, int Bp, cudaStream_t s) {
   const size_t smem = (size_t)2 * TCD_TILE_STAGING + (size_t)2 * TCD_STAGES * TCD_STAGE +
                       (size_t)a.NP * 4 + 2 * TB_PER_TILE * 8 + 16;   // 224 KB + c0 + barriers
@@ -946,10 +989,10 @@ static int launch_tcd(const TcdArgs& a, int Bp, cudaStream_t s) {
     set_error("decode_tc: N=%d needs %zu bytes of shared memory", a.N, smem);
     return HTSP_ERR_UNSUPPORTED;
   }
-  HTSP_CHECK_CUDA(cudaFuncSetAttribute(decode_tc_kernel<LOGITS, DEBUG>,
+  HTSP_CHECK_CUDA(cudaFuncSetAttribute(decode_tc_kernel<LOGITS, DEBUG, PSINGLE>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kernel_timer_begin(s);
-  decode_tc_kernel<LOGITS, DEBUG><<<Bp, TCD_THREADS, smem, s>>>(a);
+  decode_tc_kernel<LOGITS, DEBUG, PSINGLE><<<Bp, TCD_THREADS, smem, s>>>(a);
   kernel_timer_end(s);
   HTSP_CHECK_LAUNCH();
   return HTSP_OK;
@@ -974,9 +1017,14 @@ int launch_decode_tc(const float* x, const float* proj, const float* qfix, const
   a.src = src; a.tgt = tgt; a.first = first; a.forced_pi = forced_pi;
   a.pi = pi; a.reward = reward; a.logits_out = logits_out; a.dbg = dbg;
   a.N = N; a.NP = NP; a.G = G; a.fast = (mode == HTSP_MODE_TC_FAST) ? 1 : 0; a.dbg_step = dbg_step;
-  if (dbg != nullptr) return launch_tcd<false, true>(a, Bp, s);
-  if (logits_out != nullptr) return launch_tcd<true, false>(a, Bp, s);
-  return launch_tcd<false, false>(a, Bp, s);
+  if (a.fast) {
+    if (dbg != nullptr) return launch_tcd<false, true, true>(a, Bp, s);
+    if (logits_out != nullptr) return launch_tcd<true, false, true>(a, Bp, s);
+    return launch_tcd<false, false, true>(a, Bp, s);
+  }
+  if (dbg != nullptr) return launch_tcd<false, true, false>(a, Bp, s);
+  if (logits_out != nullptr) return launch_tcd<true, false, false>(a, Bp, s);
+  return launch_tcd<false, false, false>(a, Bp, s);
 }
 
 }  // namespace htsp

@@ -253,65 +253,118 @@ pol_scatter_kernel(const float* __restrict__ state, const int* __restrict__ pix,
 }
 
 // ---- CNN ----------------------------------------------------------------------------------------------
-// direct 3x3 convolution, padding 1: one CTA = 16 x 16 output pixels x CT output channels; input channels
-// in chunks of 8 through shared memory; weights pre-arranged [Cin][9][Cout]
-template <int CT>
-__global__ void __launch_bounds__(256)
+// direct 3x3 convolution, padding 1.  One CTA = a (TXN*PW) x TYN tile of output pixels x CT output channels;
+// a thread owns PW horizontally adjacent pixels x CT channels (PW*CT accumulators), so every weight vector
+// read from shared memory feeds PW*CT FMAs and every input row segment 3*PW*CT.  Input channels go through
+// shared memory in chunks of CK (all loads of a chunk are issued before the first use); weights are
+// pre-arranged [Cin][9][Cout].  Tiles are chosen per layer so that rows are whole (100 = 25 threads x 4,
+// 50 = 25 x 2, 25, 13): no wasted lanes along x, 400/200/100/52-byte coalesced rows.
+template <int PW, int CT>
+__global__ void __launch_bounds__(256, 3)
 pol_conv3x3_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
                    const float* __restrict__ res, float* __restrict__ out, int Cin, int Cout, int Hh, int Ww,
-                   int relu_in) {
-  constexpr int CK = 8, TS = 16;
-  __shared__ float s_in[CK][TS + 2][TS + 3];
-  __shared__ __align__(16) float s_w[CK][9][CT];
-  const int tiles_x = (Ww + TS - 1) / TS;
-  const int ty0 = (blockIdx.x / tiles_x) * TS, tx0 = (blockIdx.x % tiles_x) * TS;
+                   int relu_in, int TXN, int TYN, int CK) {
+  extern __shared__ __align__(16) float pol_smem[];
+  const int TW = TXN * PW, SW = (TW + 2 + 3) & ~3, SH = TYN + 2;      // smem row pitch: multiple of 4 floats
+  float* s_in = pol_smem;                                             // [CK][SH][SW]
+  float* s_w = pol_smem + (size_t)CK * SH * SW;                       // [CK][9][CT]
+  const int tiles_x = (Ww + TW - 1) / TW;
+  const int ty0 = (blockIdx.x / tiles_x) * TYN, tx0 = (blockIdx.x % tiles_x) * TW;
   const int co0 = blockIdx.y * CT, b = blockIdx.z;
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  float acc[CT];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int tx = tid % TXN, ty = tid / TXN;
+  float acc[PW][CT];
 #pragma unroll
-  for (int j = 0; j < CT; ++j) acc[j] = bias[co0 + j];
+  for (int j = 0; j < CT; ++j) {
+    const float bj = bias[co0 + j];
+#pragma unroll
+    for (int px = 0; px < PW; ++px) acc[px][j] = bj;
+  }
   const float* inb = in + (size_t)b * Cin * Hh * Ww;
+  const int per_ch = SH * SW;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
   for (int c0 = 0; c0 < Cin; c0 += CK) {
     __syncthreads();
-    for (int i = tid; i < CK * (TS + 2) * (TS + 2); i += 256) {
-      const int ci = i / ((TS + 2) * (TS + 2)), r = i - ci * (TS + 2) * (TS + 2);
-      const int yy = r / (TS + 2), xx = r - yy * (TS + 2);
-      const int gy = ty0 + yy - 1, gx = tx0 + xx - 1;
-      float v = 0.f;
-      if (c0 + ci < Cin && gy >= 0 && gy < Hh && gx >= 0 && gx < Ww) {
-        v = inb[((size_t)(c0 + ci) * Hh + gy) * Ww + gx];
-        if (relu_in) v = fmaxf(v, 0.f);
+    // asynchronous 4-byte copies (zero-filled outside the image): one warp per (channel, row), every copy of
+    // the chunk is in flight before the first wait
+    for (int row = warp; row < CK * SH; row += nwarps) {
+      const int ci = row / SH, yy = row - ci * SH;
+      const int gy = ty0 + yy - 1;
+      const bool row_ok = (c0 + ci < Cin) && gy >= 0 && gy < Hh;
+      const float* src_row = inb + ((size_t)(row_ok ? c0 + ci : 0) * Hh + (row_ok ? gy : 0)) * Ww;
+      const uint32_t dst_row = (uint32_t)__cvta_generic_to_shared(s_in + (size_t)row * SW);
+      for (int xx = lane; xx < SW; xx += 32) {
+        const int gx = tx0 + xx - 1;
+        const bool ok = row_ok && xx < TW + 2 && gx >= 0 && gx < Ww;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst_row + 4u * xx), "l"(src_row + (ok ? gx : 0)),
+                     "r"(ok ? 4 : 0)
+                     : "memory");
       }
-      s_in[ci][yy][xx] = v;
     }
-    for (int i = tid; i < CK * 9 * CT; i += 256) {
-      const int ci = i / (9 * CT), r = i - ci * 9 * CT;
-      (&s_w[0][0][0])[i] = (c0 + ci < Cin) ? w[((size_t)(c0 + ci) * 9 + r / CT) * Cout + co0 + (r % CT)] : 0.f;
+    for (int i = tid; i < CK * 9 * (CT / 4); i += nthr) {        // 16-byte weight copies: [ci][tap][CT]
+      const int q = i % (CT / 4), ct = i / (CT / 4);             // ct = ci * 9 + tap
+      const bool ok = c0 + ct / 9 < Cin;
+      const float* src = w + ((size_t)(ok ? c0 * 9 + ct : 0)) * Cout + co0 + 4 * q;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(s_w + 4 * i)),
+                   "l"(src), "r"(ok ? 16 : 0)
+                   : "memory");
     }
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    if (ty < TYN) {
 #pragma unroll 2
-    for (int ci = 0; ci < CK; ++ci) {
+      for (int ci = 0; ci < CK; ++ci) {
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const float v = s_in[ci][ty + tap / 3][tx + tap % 3];
-        const float4* wp = (const float4*)&s_w[ci][tap][0];
+        for (int dy = 0; dy < 3; ++dy) {
+          const float* row = s_in + (size_t)ci * per_ch + (ty + dy) * SW + tx * PW;
+          float seg[PW + 2];
+          if (PW == 4) {
+            const float4 a = *(const float4*)row;
+            const float2 c = *(const float2*)(row + 4);
+            seg[0] = a.x; seg[1] = a.y; seg[2] = a.z; seg[3] = a.w; seg[PW] = c.x; seg[PW + 1] = c.y;
+          } else if (PW == 2) {
+            const float2 a = *(const float2*)row, c = *(const float2*)(row + 2);
+            seg[0] = a.x; seg[1] = a.y; seg[PW] = c.x; seg[PW + 1] = c.y;
+          } else {
 #pragma unroll
-        for (int j4 = 0; j4 < CT / 4; ++j4) {
-          const float4 ww = wp[j4];
-          acc[4 * j4 + 0] = fmaf(v, ww.x, acc[4 * j4 + 0]);
-          acc[4 * j4 + 1] = fmaf(v, ww.y, acc[4 * j4 + 1]);
-          acc[4 * j4 + 2] = fmaf(v, ww.z, acc[4 * j4 + 2]);
-          acc[4 * j4 + 3] = fmaf(v, ww.w, acc[4 * j4 + 3]);
+            for (int k = 0; k < PW + 2; ++k) seg[k] = row[k];
+          }
+          if (relu_in) {
+#pragma unroll
+            for (int k = 0; k < PW + 2; ++k) seg[k] = fmaxf(seg[k], 0.f);
+          }
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const float4* wp = (const float4*)(s_w + ((size_t)ci * 9 + dy * 3 + dx) * CT);
+#pragma unroll
+            for (int j4 = 0; j4 < CT / 4; ++j4) {
+              const float4 ww = wp[j4];
+#pragma unroll
+              for (int px = 0; px < PW; ++px) {
+                const float v = seg[px + dx];
+                acc[px][4 * j4 + 0] = fmaf(v, ww.x, acc[px][4 * j4 + 0]);
+                acc[px][4 * j4 + 1] = fmaf(v, ww.y, acc[px][4 * j4 + 1]);
+                acc[px][4 * j4 + 2] = fmaf(v, ww.z, acc[px][4 * j4 + 2]);
+                acc[px][4 * j4 + 3] = fmaf(v, ww.w, acc[px][4 * j4 + 3]);
+              }
+            }
+          }
         }
       }
     }
   }
-  const int gy = ty0 + ty, gx = tx0 + tx;
-  if (gy < Hh && gx < Ww) {
+  const int gy = ty0 + ty;
+  if (ty < TYN && gy < Hh) {
 #pragma unroll
     for (int j = 0; j < CT; ++j) {
-      const size_t o = (((size_t)b * Cout + co0 + j) * Hh + gy) * Ww + gx;
-      out[o] = res ? acc[j] + res[o] : acc[j];
+#pragma unroll
+      for (int px = 0; px < PW; ++px) {
+        const int gx = tx0 + tx * PW + px;
+        if (gx < Ww) {
+          const size_t o = (((size_t)b * Cout + co0 + j) * Hh + gy) * Ww + gx;
+          out[o] = res ? acc[px][j] + res[o] : acc[px][j];
+        }
+      }
     }
   }
 }
@@ -338,41 +391,50 @@ pol_maxpool_kernel(const float* __restrict__ in, float* __restrict__ out, size_t
   out[i] = m;
 }
 
-// ReLU(flatten) -> fc -> ReLU = graph_feat (rl_models.py:130-131), then ActorPPO.net and tanh; one CTA
-// per instance
+// ReLU(flatten) -> fc -> ReLU = graph_feat (rl_models.py:130-131): one warp per (instance, output), the
+// 5408-long dot product with four 16-byte weight loads in flight per lane; grid (E/8, instances)
 __global__ void __launch_bounds__(256)
-pol_head_kernel(const float* __restrict__ x3, const float* __restrict__ fc_w, const float* __restrict__ fc_b,
-                const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
-                const float* __restrict__ b2, const float* __restrict__ w3, const float* __restrict__ b3,
-                const float* __restrict__ w4, const float* __restrict__ b4, int E, int mid, int adim,
-                float* __restrict__ feat, float* __restrict__ action) {
-  __shared__ __align__(16) float xin[PFLAT];
-  __shared__ float h0[256], h1[256];
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < PFLAT; i += 256) xin[i] = fmaxf(x3[(size_t)b * PFLAT + i], 0.f);
-  __syncthreads();
-  for (int o = warp; o < E; o += 8) {
-    const float* wr = fc_w + (size_t)o * PFLAT;
-    float acc = 0.f;
-    for (int k = 4 * lane; k < PFLAT; k += 128) {
-      const float4 ww = *(const float4*)(wr + k), xx = *(const float4*)(xin + k);
-      acc = fmaf(xx.x, ww.x, acc);
-      acc = fmaf(xx.y, ww.y, acc);
-      acc = fmaf(xx.z, ww.z, acc);
-      acc = fmaf(xx.w, ww.w, acc);
-    }
+pol_fc_kernel(const float* __restrict__ x3, const float* __restrict__ fc_w, const float* __restrict__ fc_b, int E,
+              float* __restrict__ feat) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31, o = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (o >= E) return;
+  const float4* wr = (const float4*)(fc_w + (size_t)o * PFLAT);
+  const float4* xr = (const float4*)(x3 + (size_t)b * PFLAT);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  constexpr int NV = PFLAT / 4;                       // 1352 float4 per row
+  for (int k0 = 0; k0 < NV; k0 += 128) {
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-    if (lane == 0) {
-      const float v = fmaxf(acc + fc_b[o], 0.f);
-      h0[o] = v;
-      feat[(size_t)b * E + o] = v;
+    for (int u = 0; u < 4; ++u) {
+      const int k = k0 + u * 32 + lane;
+      if (k < NV) {
+        const float4 ww = __ldg(wr + k), xx = __ldg(xr + k);
+        acc[u] = fmaf(fmaxf(xx.x, 0.f), ww.x, acc[u]);
+        acc[u] = fmaf(fmaxf(xx.y, 0.f), ww.y, acc[u]);
+        acc[u] = fmaf(fmaxf(xx.z, 0.f), ww.z, acc[u]);
+        acc[u] = fmaf(fmaxf(xx.w, 0.f), ww.w, acc[u]);
+      }
     }
   }
+  float a = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
+  if (lane == 0) feat[(size_t)b * E + o] = fmaxf(a + fc_b[o], 0.f);
+}
+
+// ActorPPO.net and tanh (rl_models.py:287-301, 329-336); one CTA per instance, weights [in][out]
+__global__ void __launch_bounds__(256)
+pol_actor_kernel(const float* __restrict__ feat, const float* __restrict__ w1, const float* __restrict__ b1,
+                 const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ w3,
+                 const float* __restrict__ b3, const float* __restrict__ w4, const float* __restrict__ b4, int E,
+                 int mid, int adim, float* __restrict__ action) {
+  __shared__ float h0[256], h1[256];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  if (tid < E) h0[tid] = feat[(size_t)b * E + tid];
   __syncthreads();
   auto dense = [&](const float* hin, int nin, const float* wt, const float* bb, int nout, int j) {
     float acc = bb[j];
-    for (int i = 0; i < nin; ++i) acc = fmaf(hin[i], wt[(size_t)i * nout + j], acc);
+#pragma unroll 16
+    for (int i = 0; i < nin; ++i) acc = fmaf(hin[i], __ldg(wt + (size_t)i * nout + j), acc);
     return acc;
   };
   if (tid < mid) h1[tid] = fmaxf(dense(h0, E, w1, b1, mid, tid), 0.f);
@@ -485,10 +547,30 @@ extern "C" int htsp_policy_forward(const void* blob, int embed, int mid, int adi
   if (image_out)
     HTSP_CHECK_CUDA(cudaMemcpyAsync(image_out, img, (size_t)B * g.C0 * PS * 4, cudaMemcpyDeviceToDevice, s));
 
+  // tiles per layer size: 100 -> 25 threads x 4 px by 10 rows, 50 -> 25 x 2 px by 10 rows, <= 25 -> whole rows
   auto conv = [&](int j, const float* in, const float* res, float* out, int hw, int relu_in) -> int {
-    const int tiles = ((hw + 15) / 16) * ((hw + 15) / 16);
-    pol_conv3x3_kernel<16><<<dim3(tiles, g.cout[j] / 16, B), 256, 0, s>>>(in, wb + o.conv_w[j], wb + o.conv_b[j], res,
-                                                                          out, g.cin[j], g.cout[j], hw, hw, relu_in);
+    const int pw = hw >= 100 ? 4 : (hw >= 50 ? 2 : 1);
+    const int txn = (hw + pw - 1) / pw > 25 ? 25 : (hw + pw - 1) / pw;
+    int tyn = 256 / txn;
+    if (tyn > 10 && hw > 13) tyn = 10;
+    if (tyn > hw) tyn = hw;
+    const int cin = g.cin[j], ck = cin > 32 ? 8 : (pw == 1 ? cin : (cin < 16 ? cin : 16));
+    const int tw = txn * pw, sw = (tw + 2 + 3) & ~3;
+    const size_t smem = ((size_t)ck * (tyn + 2) * sw + (size_t)ck * 9 * 8) * sizeof(float);
+    const int tiles = ((hw + tw - 1) / tw) * ((hw + tyn - 1) / tyn);
+    const dim3 grid(tiles, g.cout[j] / 8, B);
+    const int threads = (txn * tyn + 31) / 32 * 32;
+#define POL_LAUNCH_CONV(PWV)                                                                                         \
+    do {                                                                                                             \
+      HTSP_CHECK_CUDA(cudaFuncSetAttribute(pol_conv3x3_kernel<PWV, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                           (int)smem));                                                              \
+      pol_conv3x3_kernel<PWV, 8><<<grid, threads, smem, s>>>(in, wb + o.conv_w[j], wb + o.conv_b[j], res, out, cin,   \
+                                                            g.cout[j], hw, hw, relu_in, txn, tyn, ck);              \
+    } while (0)
+    if (pw == 4) POL_LAUNCH_CONV(4);
+    else if (pw == 2) POL_LAUNCH_CONV(2);
+    else POL_LAUNCH_CONV(1);
+#undef POL_LAUNCH_CONV
     HTSP_CHECK_LAUNCH();
     return HTSP_OK;
   };
@@ -510,9 +592,10 @@ extern "C" int htsp_policy_forward(const void* blob, int embed, int mid, int adi
     x = xa;
   }
   HTSP_REQUIRE(hw * hw * 32 == PFLAT, "flatten dimension");
-  pol_head_kernel<<<B, 256, 0, s>>>(xa, wb + o.fc_w, wb + o.fc_b, wb + o.a_w[0], wb + o.a_b[0], wb + o.a_w[1],
-                                    wb + o.a_b[1], wb + o.a_w[2], wb + o.a_b[2], wb + o.a_w[3], wb + o.a_b[3], g.E,
-                                    g.mid, g.adim, feat, action);
+  pol_fc_kernel<<<dim3((g.E + 7) / 8, B), 256, 0, s>>>(xa, wb + o.fc_w, wb + o.fc_b, g.E, feat);
+  HTSP_CHECK_LAUNCH();
+  pol_actor_kernel<<<B, 256, 0, s>>>(feat, wb + o.a_w[0], wb + o.a_b[0], wb + o.a_w[1], wb + o.a_b[1], wb + o.a_w[2],
+                                     wb + o.a_b[2], wb + o.a_w[3], wb + o.a_b[3], g.E, g.mid, g.adim, action);
   HTSP_CHECK_LAUNCH();
   return HTSP_OK;
 }
