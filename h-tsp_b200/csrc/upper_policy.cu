@@ -283,22 +283,38 @@ pol_conv3x3_kernel(const float* __restrict__ in, const float* __restrict__ w, co
   const float* inb = in + (size_t)b * Cin * Hh * Ww;
   const int per_ch = SH * SW;
   const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+  const uint32_t s_in_addr = (uint32_t)__cvta_generic_to_shared(s_in);
+  bool col_ok[4];
+  int col_gx[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {                      // smem row pitch <= 128 floats (TW <= 100)
+    const int xx = lane + 32 * k, gx = tx0 + xx - 1;
+    col_ok[k] = xx < TW + 2 && gx >= 0 && gx < Ww;
+    col_gx[k] = gx;
+  }
   for (int c0 = 0; c0 < Cin; c0 += CK) {
     __syncthreads();
     // asynchronous 4-byte copies (zero-filled outside the image): one warp per (channel, row), every copy of
-    // the chunk is in flight before the first wait
-    for (int row = warp; row < CK * SH; row += nwarps) {
-      const int ci = row / SH, yy = row - ci * SH;
-      const int gy = ty0 + yy - 1;
-      const bool row_ok = (c0 + ci < Cin) && gy >= 0 && gy < Hh;
-      const float* src_row = inb + ((size_t)(row_ok ? c0 + ci : 0) * Hh + (row_ok ? gy : 0)) * Ww;
-      const uint32_t dst_row = (uint32_t)__cvta_generic_to_shared(s_in + (size_t)row * SW);
-      for (int xx = lane; xx < SW; xx += 32) {
-        const int gx = tx0 + xx - 1;
-        const bool ok = row_ok && xx < TW + 2 && gx >= 0 && gx < Ww;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst_row + 4u * xx), "l"(src_row + (ok ? gx : 0)),
-                     "r"(ok ? 4 : 0)
-                     : "memory");
+    // the chunk is in flight before the first wait; column offsets / predicates are per-lane constants
+    {
+      int ci = warp / SH, yy = warp - ci * SH;
+      for (int row = warp; row < CK * SH; row += nwarps) {
+        const int gy = ty0 + yy - 1;
+        const bool row_ok = (c0 + ci < Cin) && gy >= 0 && gy < Hh;
+        const float* src_row = inb + ((size_t)(row_ok ? c0 + ci : 0) * Hh + (row_ok ? gy : 0)) * Ww;
+        const uint32_t dst_row = s_in_addr + 4u * (uint32_t)(row * SW);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k * 32 < SW) {
+            const bool ok = row_ok && col_ok[k];
+            if (lane + 32 * k < SW)
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst_row + 4u * (uint32_t)(lane + 32 * k)),
+                           "l"(src_row + (ok ? col_gx[k] : 0)), "r"(ok ? 4 : 0)
+                           : "memory");
+          }
+        }
+        yy += nwarps;
+        while (yy >= SH) { yy -= SH; ++ci; }
       }
     }
     for (int i = tid; i < CK * 9 * (CT / 4); i += nthr) {        // 16-byte weight copies: [ci][tap][CT]

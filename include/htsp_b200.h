@@ -42,7 +42,8 @@ typedef enum {
 typedef enum {
   HTSP_MODE_FP32 = 0,   /* fp32 FMA on CUDA cores, reference op order (parity anchor)        */
   HTSP_MODE_TC_X3 = 1,  /* tensor cores, split-fp16 operands (hi+lo, 3 MMAs), fp32 accumulate */
-  HTSP_MODE_TC_FAST = 2 /* as X3 but glimpse QK^T with single fp16 operands                   */
+  HTSP_MODE_TC_FAST = 2 /* as X3 with one single-fp16 operand in the glimpse (tcgen05 kernel: the
+                           softmax probabilities; mma.sync kernel: QK^T); logits within 1e-3     */
 } htsp_mode;
 
 int htsp_abi_version(void);
