@@ -78,6 +78,21 @@ class ClockSampler:
         self.skip = len(self.lines)
 
     def start(self):
+        """In-process NVML polling (one thread, 10 Hz).  A looping `nvidia-smi` child disturbed the timed
+        region by tens of ms per step on some boxes; it remains the fallback when pynvml is unavailable."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
+            self.nv = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys))
+            self.proc = "nvml"
+            self._stop = threading.Event()
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
@@ -86,6 +101,28 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll_nvml(self):
+        nv, h = self.nv
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown")
+                else nv.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown",
+                                               getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0)),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown",
+                                               getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0)),
+                "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap",
+                                        getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0))}
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                flags = ["Active" if (rs & b) else "Not Active" for b in bits.values()]
+                self.lines.append(f"{self.gpu}, {sm}, {mx}, {pw}, {rs}, " + ", ".join(flags))
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
@@ -93,11 +130,15 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            pass
+        if self.proc == "nvml":
+            self._stop.set()
+            self.thread.join(timeout=2)
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
         sm, mx, reasons, power = [], [], set(), []
         for ln in self.lines[self.skip:]:
             f = [x.strip() for x in ln.split(",")]
@@ -114,7 +155,8 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(power) if power else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons),
+                "source": "nvml (in-process)" if self.proc == "nvml" else "nvidia-smi -lms 100"}
 
 
 def make_inputs(B, N, seed, device=None, pin=False):
