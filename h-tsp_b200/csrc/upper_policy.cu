@@ -253,26 +253,29 @@ pol_scatter_kernel(const float* __restrict__ state, const int* __restrict__ pix,
 }
 
 // ---- CNN ----------------------------------------------------------------------------------------------
-// direct 3x3 convolution, padding 1.  One CTA = a (TXN*PW) x TYN tile of output pixels x CT output channels;
-// a thread owns PW horizontally adjacent pixels x CT channels (PW*CT accumulators), so every weight vector
-// read from shared memory feeds PW*CT FMAs and every input row segment 3*PW*CT.  Input channels go through
-// shared memory in chunks of CK (all loads of a chunk are issued before the first use); weights are
-// pre-arranged [Cin][9][Cout].  Tiles are chosen per layer so that rows are whole (100 = 25 threads x 4,
-// 50 = 25 x 2, 25, 13): no wasted lanes along x, 400/200/100/52-byte coalesced rows.
-template <int PW, int CT>
-__global__ void __launch_bounds__(256, 3)
+// direct 3x3 convolution, padding 1.  One CTA = TYN whole rows of output pixels x CT output channels; a
+// thread owns PW horizontally adjacent pixels x CT channels.  Shared memory delivers one weight per clock
+// and SM (a broadcast LDS.128 occupies the pipe for 4 clocks), so a weight vector must feed >= 32 FMAs
+// per lane to keep the FMA pipes busy: PW = 10 / 5 / 5 / 7 pixels for 100 / 50 / 25 / 13-pixel rows with
+// CT = 4 channels (40 / 20 / 20 / 28 accumulators per thread).  Rows are whole, so the left/right halo columns
+// and the rows outside the image are always zero: shared memory is cleared once and only the interior is
+// copied, one VEC*4-byte cp.async per lane and row (16 bytes for the 100-pixel rows); every copy of a
+// chunk of CK input channels is in flight before the first wait.  Row layout in shared memory:
+// [3 pad | 0 | Ww pixels | 0 | pad], the interior 16-byte aligned.  Weights are pre-arranged [Cin][9][Cout].
+template <int PW, int CT, int VEC>
+__global__ void __launch_bounds__(256, 2)
 pol_conv3x3_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
                    const float* __restrict__ res, float* __restrict__ out, int Cin, int Cout, int Hh, int Ww,
                    int relu_in, int TXN, int TYN, int CK) {
   extern __shared__ __align__(16) float pol_smem[];
-  const int TW = TXN * PW, SW = (TW + 2 + 3) & ~3, SH = TYN + 2;      // smem row pitch: multiple of 4 floats
+  const int SW = (Ww + 8 + PW + 3) & ~3, SH = TYN + 2;                // smem row pitch: multiple of 4 floats
   float* s_in = pol_smem;                                             // [CK][SH][SW]
   float* s_w = pol_smem + (size_t)CK * SH * SW;                       // [CK][9][CT]
-  const int tiles_x = (Ww + TW - 1) / TW;
-  const int ty0 = (blockIdx.x / tiles_x) * TYN, tx0 = (blockIdx.x % tiles_x) * TW;
+  const int ty0 = blockIdx.x * TYN;
   const int co0 = blockIdx.y * CT, b = blockIdx.z;
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int tx = tid % TXN, ty = tid / TXN;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
   float acc[PW][CT];
 #pragma unroll
   for (int j = 0; j < CT; ++j) {
@@ -280,75 +283,48 @@ pol_conv3x3_kernel(const float* __restrict__ in, const float* __restrict__ w, co
 #pragma unroll
     for (int px = 0; px < PW; ++px) acc[px][j] = bj;
   }
-  const float* inb = in + (size_t)b * Cin * Hh * Ww;
   const int per_ch = SH * SW;
-  const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+  for (int i = tid; i < CK * per_ch / 4; i += nthr) ((float4*)s_in)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* inb = in + (size_t)b * Cin * Hh * Ww;
   const uint32_t s_in_addr = (uint32_t)__cvta_generic_to_shared(s_in);
-  bool col_ok[4];
-  int col_gx[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {                      // smem row pitch <= 128 floats (TW <= 100)
-    const int xx = lane + 32 * k, gx = tx0 + xx - 1;
-    col_ok[k] = xx < TW + 2 && gx >= 0 && gx < Ww;
-    col_gx[k] = gx;
-  }
+  const int nvec = Ww / VEC;                                           // copy lanes per row (<= 32)
   for (int c0 = 0; c0 < Cin; c0 += CK) {
     __syncthreads();
-    // asynchronous 4-byte copies (zero-filled outside the image): one warp per (channel, row), every copy of
-    // the chunk is in flight before the first wait; column offsets / predicates are per-lane constants
-    {
-      int ci = warp / SH, yy = warp - ci * SH;
-      for (int row = warp; row < CK * SH; row += nwarps) {
-        const int gy = ty0 + yy - 1;
-        const bool row_ok = (c0 + ci < Cin) && gy >= 0 && gy < Hh;
-        const float* src_row = inb + ((size_t)(row_ok ? c0 + ci : 0) * Hh + (row_ok ? gy : 0)) * Ww;
-        const uint32_t dst_row = s_in_addr + 4u * (uint32_t)(row * SW);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (k * 32 < SW) {
-            const bool ok = row_ok && col_ok[k];
-            if (lane + 32 * k < SW)
-              asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst_row + 4u * (uint32_t)(lane + 32 * k)),
-                           "l"(src_row + (ok ? col_gx[k] : 0)), "r"(ok ? 4 : 0)
-                           : "memory");
+    if (lane < nvec) {
+      for (int ci = warp; ci < CK; ci += nwarps) {                 // one warp per input channel of the chunk
+        const float* src = inb + ((ptrdiff_t)(c0 + ci) * Hh + (ty0 - 1)) * Ww + lane * VEC;   // row yy = 0
+        const uint32_t dst = s_in_addr + 4u * (uint32_t)(ci * per_ch + 4 + lane * VEC);
+#pragma unroll 4
+        for (int yy = 0; yy < SH; ++yy) {
+          const int gy = ty0 + yy - 1;
+          if (gy >= 0 && gy < Hh) {
+            const float* sp = src + (ptrdiff_t)yy * Ww;
+            const uint32_t dp = dst + 4u * (uint32_t)(yy * SW);
+            if (VEC == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dp), "l"(sp) : "memory");
+            else if (VEC == 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dp), "l"(sp) : "memory");
+            else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dp), "l"(sp) : "memory");
           }
         }
-        yy += nwarps;
-        while (yy >= SH) { yy -= SH; ++ci; }
       }
     }
     for (int i = tid; i < CK * 9 * (CT / 4); i += nthr) {        // 16-byte weight copies: [ci][tap][CT]
       const int q = i % (CT / 4), ct = i / (CT / 4);             // ct = ci * 9 + tap
-      const bool ok = c0 + ct / 9 < Cin;
-      const float* src = w + ((size_t)(ok ? c0 * 9 + ct : 0)) * Cout + co0 + 4 * q;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(s_w + 4 * i)),
-                   "l"(src), "r"(ok ? 16 : 0)
+      const float* src = w + ((size_t)c0 * 9 + ct) * Cout + co0 + 4 * q;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(s_w + 4 * i)),
+                   "l"(src)
                    : "memory");
     }
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     if (ty < TYN) {
-#pragma unroll 2
+#pragma unroll 1
       for (int ci = 0; ci < CK; ++ci) {
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
-          const float* row = s_in + (size_t)ci * per_ch + (ty + dy) * SW + tx * PW;
+          const float* row = s_in + (size_t)ci * per_ch + (ty + dy) * SW + 3 + tx * PW;   // pixel tx*PW - 1 of the row
           float seg[PW + 2];
-          if (PW == 4) {
-            const float4 a = *(const float4*)row;
-            const float2 c = *(const float2*)(row + 4);
-            seg[0] = a.x; seg[1] = a.y; seg[2] = a.z; seg[3] = a.w; seg[PW] = c.x; seg[PW + 1] = c.y;
-          } else if (PW == 2) {
-            const float2 a = *(const float2*)row, c = *(const float2*)(row + 2);
-            seg[0] = a.x; seg[1] = a.y; seg[PW] = c.x; seg[PW + 1] = c.y;
-          } else {
 #pragma unroll
-            for (int k = 0; k < PW + 2; ++k) seg[k] = row[k];
-          }
-          if (relu_in) {
-#pragma unroll
-            for (int k = 0; k < PW + 2; ++k) seg[k] = fmaxf(seg[k], 0.f);
-          }
+          for (int k = 0; k < PW + 2; ++k) seg[k] = relu_in ? fmaxf(row[k], 0.f) : row[k];
 #pragma unroll
           for (int dx = 0; dx < 3; ++dx) {
             const float4* wp = (const float4*)(s_w + ((size_t)ci * 9 + dy * 3 + dx) * CT);
@@ -373,14 +349,10 @@ pol_conv3x3_kernel(const float* __restrict__ in, const float* __restrict__ w, co
   if (ty < TYN && gy < Hh) {
 #pragma unroll
     for (int j = 0; j < CT; ++j) {
+      const size_t o = (((size_t)b * Cout + co0 + j) * Hh + gy) * Ww + tx * PW;
 #pragma unroll
-      for (int px = 0; px < PW; ++px) {
-        const int gx = tx0 + tx * PW + px;
-        if (gx < Ww) {
-          const size_t o = (((size_t)b * Cout + co0 + j) * Hh + gy) * Ww + gx;
-          out[o] = res ? acc[px][j] + res[o] : acc[px][j];
-        }
-      }
+      for (int px = 0; px < PW; ++px)
+        if (tx * PW + px < Ww) out[o + px] = res ? acc[px][j] + res[o + px] : acc[px][j];
     }
   }
 }
@@ -408,7 +380,7 @@ pol_maxpool_kernel(const float* __restrict__ in, float* __restrict__ out, size_t
 }
 
 // ReLU(flatten) -> fc -> ReLU = graph_feat (rl_models.py:130-131): one warp per (instance, output), the
-// 5408-long dot product with four 16-byte weight loads in flight per lane; grid (E/8, instances)
+// 5408-long dot product with eight 16-byte weight loads in flight per lane; grid (E/8, instances)
 __global__ void __launch_bounds__(256)
 pol_fc_kernel(const float* __restrict__ x3, const float* __restrict__ fc_w, const float* __restrict__ fc_b, int E,
               float* __restrict__ feat) {
@@ -416,11 +388,11 @@ pol_fc_kernel(const float* __restrict__ x3, const float* __restrict__ fc_w, cons
   if (o >= E) return;
   const float4* wr = (const float4*)(fc_w + (size_t)o * PFLAT);
   const float4* xr = (const float4*)(x3 + (size_t)b * PFLAT);
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   constexpr int NV = PFLAT / 4;                       // 1352 float4 per row
-  for (int k0 = 0; k0 < NV; k0 += 128) {
+  for (int k0 = 0; k0 < NV; k0 += 256) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       const int k = k0 + u * 32 + lane;
       if (k < NV) {
         const float4 ww = __ldg(wr + k), xx = __ldg(xr + k);
@@ -431,7 +403,7 @@ pol_fc_kernel(const float* __restrict__ x3, const float* __restrict__ fc_w, cons
       }
     }
   }
-  float a = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  float a = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
   if (lane == 0) feat[(size_t)b * E + o] = fmaxf(a + fc_b[o], 0.f);
@@ -449,7 +421,7 @@ pol_actor_kernel(const float* __restrict__ feat, const float* __restrict__ w1, c
   __syncthreads();
   auto dense = [&](const float* hin, int nin, const float* wt, const float* bb, int nout, int j) {
     float acc = bb[j];
-#pragma unroll 16
+#pragma unroll 32
     for (int i = 0; i < nin; ++i) acc = fmaf(hin[i], __ldg(wt + (size_t)i * nout + j), acc);
     return acc;
   };
@@ -563,29 +535,33 @@ extern "C" int htsp_policy_forward(const void* blob, int embed, int mid, int adi
   if (image_out)
     HTSP_CHECK_CUDA(cudaMemcpyAsync(image_out, img, (size_t)B * g.C0 * PS * 4, cudaMemcpyDeviceToDevice, s));
 
-  // tiles per layer size: 100 -> 25 threads x 4 px by 10 rows, 50 -> 25 x 2 px by 10 rows, <= 25 -> whole rows
+  // per layer size: pixels per thread PW, copy vector VEC, rows per CTA TYN, input channels per chunk CK
   auto conv = [&](int j, const float* in, const float* res, float* out, int hw, int relu_in) -> int {
-    const int pw = hw >= 100 ? 4 : (hw >= 50 ? 2 : 1);
-    const int txn = (hw + pw - 1) / pw > 25 ? 25 : (hw + pw - 1) / pw;
+    const int pw = hw == 100 ? 10 : (hw == 13 ? 7 : 5);
+    HTSP_REQUIRE(hw == 100 || hw == 50 || hw == 25 || hw == 13, "image size of the default IMPALA geometry");
+    const int txn = (hw + pw - 1) / pw;
     int tyn = 256 / txn;
-    if (tyn > 10 && hw > 13) tyn = 10;
+    if (tyn > 25) tyn = 25;
     if (tyn > hw) tyn = hw;
-    const int cin = g.cin[j], ck = cin > 32 ? 8 : (pw == 1 ? cin : (cin < 16 ? cin : 16));
-    const int tw = txn * pw, sw = (tw + 2 + 3) & ~3;
-    const size_t smem = ((size_t)ck * (tyn + 2) * sw + (size_t)ck * 9 * 8) * sizeof(float);
-    const int tiles = ((hw + tw - 1) / tw) * ((hw + tyn - 1) / tyn);
-    const dim3 grid(tiles, g.cout[j] / 8, B);
-    const int threads = (txn * tyn + 31) / 32 * 32;
-#define POL_LAUNCH_CONV(PWV)                                                                                         \
+    const int cin = g.cin[j], ck = hw == 100 ? 8 : (hw == 50 ? 16 : cin);
+    HTSP_REQUIRE(cin % ck == 0, "input channels per chunk");
+    const int sw = (hw + 8 + pw + 3) & ~3, ct = 4;
+    const size_t smem = ((size_t)ck * (tyn + 2) * sw + (size_t)ck * 9 * ct) * sizeof(float);
+    const int tiles = (hw + tyn - 1) / tyn;
+    const dim3 grid(tiles, g.cout[j] / ct, B);
+    int threads = (txn * tyn + 31) / 32 * 32;
+    if (threads < 128) threads = 128;              // the copy phase wants a few warps
+#define POL_LAUNCH_CONV(PWV, VECV)                                                                                   \
     do {                                                                                                             \
-      HTSP_CHECK_CUDA(cudaFuncSetAttribute(pol_conv3x3_kernel<PWV, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                           (int)smem));                                                              \
-      pol_conv3x3_kernel<PWV, 8><<<grid, threads, smem, s>>>(in, wb + o.conv_w[j], wb + o.conv_b[j], res, out, cin,   \
-                                                            g.cout[j], hw, hw, relu_in, txn, tyn, ck);              \
+      HTSP_CHECK_CUDA(cudaFuncSetAttribute(pol_conv3x3_kernel<PWV, 4, VECV>,                                          \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+      pol_conv3x3_kernel<PWV, 4, VECV><<<grid, threads, smem, s>>>(in, wb + o.conv_w[j], wb + o.conv_b[j], res, out,  \
+                                                                  cin, g.cout[j], hw, hw, relu_in, txn, tyn, ck);   \
     } while (0)
-    if (pw == 4) POL_LAUNCH_CONV(4);
-    else if (pw == 2) POL_LAUNCH_CONV(2);
-    else POL_LAUNCH_CONV(1);
+    if (hw == 100) POL_LAUNCH_CONV(10, 4);
+    else if (hw == 50) POL_LAUNCH_CONV(5, 2);
+    else if (hw == 25) POL_LAUNCH_CONV(5, 1);
+    else POL_LAUNCH_CONV(7, 1);
 #undef POL_LAUNCH_CONV
     HTSP_CHECK_LAUNCH();
     return HTSP_OK;

@@ -9,7 +9,12 @@ lower weights are random init unless --ckpt / --upper-ckpt give reference state_
 GAP IS NOT the paper's number; the solve TIME and the per-step breakdown are what this tool measures.
 
   python tools/solve_tsp.py [--cities 10000] [--envs 16] [--mode x3] [--policy upper|random]
-                            [--ckpt path_solver.ckpt] [--upper-ckpt htsp_ppo.ckpt]"""
+                            [--ckpt path_solver.ckpt] [--upper-ckpt htsp_ppo.ckpt]
+
+Under torchrun (one rank per GPU, BASELINE config 4) every rank constructs its own --envs instances
+(instances are independent: no data-path collective); the ranks meet at a barrier before and after, the
+reported time is the maximum over ranks and the tour lengths are all-gathered for the mean:
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/solve_tsp.py"""
 import argparse
 import json
 import os
@@ -40,7 +45,14 @@ def main():
     ap.add_argument("--policy", choices=("upper", "random"), default="upper")
     ap.add_argument("--upper-ckpt", default=None)
     a = ap.parse_args()
-    dev = torch.device("cuda")
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
     if a.ckpt:
         sd = torch.load(a.ckpt, map_location="cpu")
         sd = sd.get("state_dict", sd)
@@ -57,7 +69,7 @@ def main():
             usd = synthetic_policy_state_dict(a.seed)
         policy = B200UpperPolicy(usd, dev, embedding_dim=usd["encoder.cnn.fc.weight"].shape[0],
                                  mid_dim=usd["actor.net.0.0.weight"].shape[0])
-    g = torch.Generator().manual_seed(a.seed)
+    g = torch.Generator().manual_seed(a.seed + 7919 * rank)           # different instances on every rank
     x = torch.rand(a.envs, a.cities, 2, generator=g).to(dev)
     env = B200VecEnv(k=40, frag_len=200, max_new_nodes=190, max_improvement_step=0)
     torch.manual_seed(a.seed)
@@ -68,6 +80,8 @@ def main():
     while not w.done:
         ws, _, _ = w.step(w.random_action() if policy is None else policy(ws), hook)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     state = env.reset(x)
     torch.cuda.synchronize()
@@ -97,15 +111,30 @@ def main():
         t_frag += ev[0].elapsed_time(ev[1]); t_solve += ev[1].elapsed_time(ev[2]); t_score += ev[2].elapsed_time(ev[3])
         steps += 1
     total = time.perf_counter() - t0
-    lens = env.state.cur_len.cpu()
+    lens = env.state.cur_len
+    if world > 1:
+        tt = torch.tensor([total], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total = float(tt)
+        all_lens = torch.empty(world * a.envs, device=dev, dtype=lens.dtype)
+        dist.all_gather_into_tensor(all_lens, lens.contiguous())
+        lens = all_lens
+    lens = lens.cpu()
     for e in range(a.envs):
         t = env.state.current_tour(e)
         assert len(t) == a.cities and len(set(t)) == a.cities
     opt = OPTIMA.get(a.cities)
+    n_total = a.envs * world
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
     print(json.dumps({
         "metric": f"TSP-{a.cities} end-to-end construction time (device-resident H-TSP loop)", "unit": "s",
-        "value": total, "higher_is_better": False, "n_instances": a.envs, "env_steps": steps,
-        "seconds_per_instance": total / a.envs,
+        "value": total, "higher_is_better": False, "n_gpus": world, "n_instances": n_total, "env_steps": steps,
+        "seconds_per_instance": total / n_total,
         "breakdown_ms": {"knn_reset": t_reset * 1e3, "upper_policy": t_pol, "fragment_selection": t_frag, "path_solver_hook": t_solve,
                          "scoring": t_score},
         "mean_tour_length": float(lens.mean()),
@@ -117,6 +146,8 @@ def main():
                   " lower-level weights: the gap is not the paper's; time and breakdown are the measurement",
         "config": {"k": 40, "frag_len": 200, "max_new_nodes": 190, "val_type": "x8Aug_2Traj", "pomo_starts": a.group,
                    "arith": a.mode}}))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
