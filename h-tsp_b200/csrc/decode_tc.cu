@@ -171,6 +171,7 @@ struct TcdArgs {
   float* logits_out;
   float* dbg;            // DEBUG builds: [S raw 2*8*128*NP | O 256*128 | U raw 256*NP | phase cycles] of instance 0
   int N, NP, G, fast, dbg_step;
+  int split, rows_per_cta;   // CTAs per instance and POMO rows per CTA (split == 1: rows_per_cta >= G)
 };
 
 // barrier slots of one row tile
@@ -257,8 +258,11 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler too
-  const int b = blockIdx.x;
-  const int N = A.N, NP = A.NP, G = A.G;
+  // Low-occupancy launches (fewer instances than SMs, e.g. one environment step of a few large-TSP
+  // instances) split the POMO rows of an instance over several CTAs: rows are independent, the operand
+  // image is shared, and a CTA with fewer softmax warps finishes its decode steps sooner.
+  const int b = blockIdx.x / A.split, r0 = (blockIdx.x - b * A.split) * A.rows_per_cta;
+  const int N = A.N, NP = A.NP, GT = A.G, G = min(A.rows_per_cta, GT - r0);   // G: rows of this CTA, from row r0
   const int n_steps = N - 2;
   const int n_tiles = G > 128 ? 2 : 1;
   const int K0 = tcd_k0(NP), K1 = NP - K0;     // key halves A = [0,K0), B = [K0,NP): one softmax warp each
@@ -534,8 +538,8 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
       const uint32_t tX = tmem_base + lane_addr + (uint32_t)(TCD_XCOL + 16 * t);
       unsigned char* stg = staging + t * TCD_TILE_STAGING;
       const int src = A.src[b], tgt = A.tgt[b];
-      const int first = A.first[gc];
-      int32_t* pirow = A.pi + ((size_t)b * G + gc) * N;
+      const int first = A.first[r0 + gc];
+      int32_t* pirow = A.pi + ((size_t)b * GT + r0 + gc) * N;
       const int nch = NP >> 4, n0 = nch >> 1;
       const int c_lo = half ? n0 : 0, c_hi = half ? nch : n0;
 
@@ -836,7 +840,7 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
         int idx = 0x7fffffff;
         float* lo_out = nullptr;
         if (LOGITS && A.logits_out != nullptr)
-          lo_out = A.logits_out + (((size_t)b * G + gc) * n_steps + step) * N;
+          lo_out = A.logits_out + (((size_t)b * GT + r0 + gc) * n_steps + step) * N;
         // pass(EXACT): EXACT compares the clipped logits 10*tanh(.) themselves (models.py:438-440);
         // otherwise the monotone pre-activation is compared, which picks the same key except when two
         // clipped logits round to the same float (handled by re-running EXACT near the clip).
@@ -913,7 +917,7 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
           asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(bz), "+r"(bi)::"memory");
           if (__uint_as_float(bz) > best) idx = (int)bi;     // ties keep the primary's (lower) key
           // ---- state update (train_path_solver.py:45-72); the chosen node goes to the secondary warp
-          a = A.forced_pi ? A.forced_pi[((size_t)b * G + gc) * N + cnt] : idx;
+          a = A.forced_pi ? A.forced_pi[((size_t)b * GT + r0 + gc) * N + cnt] : idx;
           asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tX + 8), "r"((uint32_t)a) : "memory");
           tc::st_wait();
           tc::fence_before();
@@ -939,7 +943,7 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
         const float2 ps = __ldg(&xb[src]), pt = __ldg(&xb[tgt]);
         const float dx = ps.x - pt.x, dy = ps.y - pt.y;
         const float fixed = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
-        A.reward[(size_t)b * G + g] = -(len - fixed);
+        A.reward[(size_t)b * GT + r0 + g] = -(len - fixed);
       }
       if (DEBUG && b == 0 && lane == 0) {
         float* dT = A.dbg + (size_t)2 * 8 * 128 * NP + (size_t)256 * 128 + (size_t)256 * NP + sw * 8;
@@ -981,6 +985,35 @@ size_t decode_tc_dbg_floats(int N) {
   return (size_t)2 * 8 * 128 * NP + (size_t)256 * 128 + (size_t)256 * NP + 256;
 }
 
+// CTAs per instance: 1 unless the launch would leave most SMs idle; then the rows are cut into 128-, 64- or
+// 32-row parts as long as all CTAs still fit in one wave (HTSP_DECODE_SPLIT = 1 | 2 | 4 | 8 overrides: the
+// requested number of parts, rounded to whole 32-row warps).
+static void tcd_choose_split(int Bp, int G, bool debug, int& split, int& rows_per_cta) {
+  split = 1;
+  rows_per_cta = G;
+  if (debug || G <= 32) return;
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0)
+      n_sm = 148;
+  }
+  const char* env = getenv("HTSP_DECODE_SPLIT");
+  const int forced = env ? atoi(env) : 0;
+  for (int want = 8; want >= 2; want >>= 1) {
+    if (forced > 0 && want != forced) continue;
+    const int rpc = ((G + want - 1) / want + 31) / 32 * 32;
+    const int parts = (G + rpc - 1) / rpc;
+    if (parts < 2) continue;
+    if (forced > 0 || (long long)Bp * parts <= n_sm) {
+      split = parts;
+      rows_per_cta = rpc;
+      return;
+    }
+  }
+}
+
 template <bool LOGITS, bool DEBUG, bool PSINGLE>
 static int launch_tcd(const TcdArgs& a, int Bp, cudaStream_t s) {
   const size_t smem = (size_t)2 * TCD_TILE_STAGING + (size_t)2 * TCD_STAGES * TCD_STAGE +
@@ -992,7 +1025,7 @@ static int launch_tcd(const TcdArgs& a, int Bp, cudaStream_t s) {
   HTSP_CHECK_CUDA(cudaFuncSetAttribute(decode_tc_kernel<LOGITS, DEBUG, PSINGLE>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kernel_timer_begin(s);
-  decode_tc_kernel<LOGITS, DEBUG, PSINGLE><<<Bp, TCD_THREADS, smem, s>>>(a);
+  decode_tc_kernel<LOGITS, DEBUG, PSINGLE><<<Bp * a.split, TCD_THREADS, smem, s>>>(a);
   kernel_timer_end(s);
   HTSP_CHECK_LAUNCH();
   return HTSP_OK;
@@ -1017,6 +1050,7 @@ int launch_decode_tc(const float* x, const float* proj, const float* qfix, const
   a.src = src; a.tgt = tgt; a.first = first; a.forced_pi = forced_pi;
   a.pi = pi; a.reward = reward; a.logits_out = logits_out; a.dbg = dbg;
   a.N = N; a.NP = NP; a.G = G; a.fast = (mode == HTSP_MODE_TC_FAST) ? 1 : 0; a.dbg_step = dbg_step;
+  tcd_choose_split(Bp, G, dbg != nullptr, a.split, a.rows_per_cta);
   if (a.fast) {
     if (dbg != nullptr) return launch_tcd<false, true, true>(a, Bp, s);
     if (logits_out != nullptr) return launch_tcd<true, false, true>(a, Bp, s);

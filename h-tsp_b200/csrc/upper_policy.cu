@@ -421,7 +421,7 @@ pol_actor_kernel(const float* __restrict__ feat, const float* __restrict__ w1, c
   __syncthreads();
   auto dense = [&](const float* hin, int nin, const float* wt, const float* bb, int nout, int j) {
     float acc = bb[j];
-#pragma unroll 32
+#pragma unroll 16
     for (int i = 0; i < nin; ++i) acc = fmaf(hin[i], __ldg(wt + (size_t)i * nout + j), acc);
     return acc;
   };

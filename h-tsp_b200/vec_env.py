@@ -90,10 +90,14 @@ class B200VecEnv:
 
     # -- VecEnv.step (h_tsp.py:724-827) without auto-reset ----------------------------------------------
     @torch.no_grad()
-    def step(self, actions: torch.Tensor, hook, check: bool = True) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    def step(self, actions: torch.Tensor, hook, check: bool = True, shard_solver: bool = False
+             ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """One environment step for every environment that is not done: fragment selection, the
         lower-level path solver (`hook.solve_device`, B200RLSolver) and the scoring step.
-        Returns (states [E,Ntot,8], rewards [E], dones [E])."""
+        Returns (states [E,Ntot,8], rewards [E], dones [E]).
+        shard_solver (under torch.distributed, every rank holding the SAME environments and actions): the
+        subproblems of the step are solved by `sharding.solve_sharded` -- each rank rolls out its block, one NCCL
+        all-gather of the paths -- and every rank applies the identical scoring step."""
         active = ~self.dones
         idx = torch.nonzero(active).squeeze(1)
         s = self.state
@@ -103,9 +107,13 @@ class B200VecEnv:
         if check:
             fs = self._fstatus.cpu()
             assert bool((fs == 0).all()), f"fragment length asserts failed: {fs.tolist()}"   # h_tsp.py:641,656-658
-        paths, _, status, _ = hook.solve_device(self.x.index_select(0, idx), frag.index_select(0, idx), None)
-        if check:
-            assert bool((status == 0).all()), "invalid path(s) returned by the rollout"
+        if shard_solver:
+            from . import sharding
+            paths, _ = sharding.solve_sharded(hook, self.x.index_select(0, idx), frag.index_select(0, idx))
+        else:
+            paths, _, status, _ = hook.solve_device(self.x.index_select(0, idx), frag.index_select(0, idx), None)
+            if check:
+                assert bool((status == 0).all()), "invalid path(s) returned by the rollout"
         was_done = self.construction_done.clone()
         s._paths.zero_()
         s._path_len.zero_()

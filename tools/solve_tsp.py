@@ -26,7 +26,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import htsp_b200  # noqa: E402,F401
-from htsp_b200 import B200PathSolver, B200RLSolver  # noqa: E402
+from htsp_b200 import B200PathSolver, B200RLSolver, sharding  # noqa: E402
 from htsp_b200.vec_env import B200VecEnv  # noqa: E402
 from htsp_b200.weights import synthetic_state_dict  # noqa: E402
 from htsp_b200.upper_policy import B200UpperPolicy, synthetic_policy_state_dict  # noqa: E402
@@ -44,6 +44,9 @@ def main():
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--policy", choices=("upper", "random"), default="upper")
     ap.add_argument("--upper-ckpt", default=None)
+    ap.add_argument("--shard-solver", action="store_true",
+                    help="under torchrun: all ranks construct the SAME --envs instances, the subproblems of every "
+                         "environment step are sharded over the ranks (latency of one batch instead of throughput)")
     a = ap.parse_args()
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -69,7 +72,8 @@ def main():
             usd = synthetic_policy_state_dict(a.seed)
         policy = B200UpperPolicy(usd, dev, embedding_dim=usd["encoder.cnn.fc.weight"].shape[0],
                                  mid_dim=usd["actor.net.0.0.weight"].shape[0])
-    g = torch.Generator().manual_seed(a.seed + 7919 * rank)           # different instances on every rank
+    shard = a.shard_solver and world > 1
+    g = torch.Generator().manual_seed(a.seed + (0 if shard else 7919 * rank))   # own instances per rank unless sharded
     x = torch.rand(a.envs, a.cities, 2, generator=g).to(dev)
     env = B200VecEnv(k=40, frag_len=200, max_new_nodes=190, max_improvement_step=0)
     torch.manual_seed(a.seed)
@@ -97,7 +101,11 @@ def main():
         idx = torch.nonzero(active).squeeze(1)
         frag, _, _, _ = env.fragments(act, active)
         ev[1].record()
-        paths, _, status, _ = hook.solve_device(env.x.index_select(0, idx), frag.index_select(0, idx), None)
+        if shard:
+            paths, _ = sharding.solve_sharded(hook, env.x.index_select(0, idx), frag.index_select(0, idx))
+            status = torch.zeros(1, dtype=torch.int32, device=dev)
+        else:
+            paths, _, status, _ = hook.solve_device(env.x.index_select(0, idx), frag.index_select(0, idx), None)
         ev[2].record()
         s = env.state
         s._paths.zero_(); s._path_len.zero_()
@@ -116,15 +124,16 @@ def main():
         tt = torch.tensor([total], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         total = float(tt)
-        all_lens = torch.empty(world * a.envs, device=dev, dtype=lens.dtype)
-        dist.all_gather_into_tensor(all_lens, lens.contiguous())
-        lens = all_lens
+        if not shard:
+            all_lens = torch.empty(world * a.envs, device=dev, dtype=lens.dtype)
+            dist.all_gather_into_tensor(all_lens, lens.contiguous())
+            lens = all_lens
     lens = lens.cpu()
     for e in range(a.envs):
         t = env.state.current_tour(e)
         assert len(t) == a.cities and len(set(t)) == a.cities
     opt = OPTIMA.get(a.cities)
-    n_total = a.envs * world
+    n_total = a.envs if shard else a.envs * world
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -133,7 +142,9 @@ def main():
         return
     print(json.dumps({
         "metric": f"TSP-{a.cities} end-to-end construction time (device-resident H-TSP loop)", "unit": "s",
-        "value": total, "higher_is_better": False, "n_gpus": world, "n_instances": n_total, "env_steps": steps,
+        "value": total, "higher_is_better": False, "n_gpus": world,
+        "multi_gpu": None if world == 1 else ("subproblems of every step sharded over the ranks (same instances)"
+                                              if shard else "independent instances per rank"), "n_instances": n_total, "env_steps": steps,
         "seconds_per_instance": total / n_total,
         "breakdown_ms": {"knn_reset": t_reset * 1e3, "upper_policy": t_pol, "fragment_selection": t_frag, "path_solver_hook": t_solve,
                          "scoring": t_score},
