@@ -171,7 +171,6 @@ struct TcdArgs {
   float* logits_out;
   float* dbg;            // DEBUG builds: [S raw 2*8*128*NP | O 256*128 | U raw 256*NP | phase cycles] of instance 0
   int N, NP, G, fast, dbg_step;
-  int split, rows_per_cta;   // CTAs per instance and POMO rows per CTA (split == 1: rows_per_cta >= G)
 };
 
 // barrier slots of one row tile
@@ -253,7 +252,7 @@ __device__ __forceinline__ void tst(uint32_t taddr, const uint32_t (&r)[32]) {
 // PSINGLE (HTSP_MODE_TC_FAST): the softmax probabilities are stored as one fp16 (no lo part), the row
 // sum is taken from the ROUNDED values so that the normalisation stays consistent; S, V and the pointer
 // logits keep the full split.  Logit error ~2.5e-4 (bound 1e-3) instead of ~3e-5.
-template <bool LOGITS, bool DEBUG, bool PSINGLE>
+template <bool LOGITS, bool DEBUG, bool PSINGLE, bool SPLIT>
 __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs A) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31;
@@ -261,8 +260,14 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
   // Low-occupancy launches (fewer instances than SMs, e.g. one environment step of a few large-TSP
   // instances) split the POMO rows of an instance over several CTAs: rows are independent, the operand
   // image is shared, and a CTA with fewer softmax warps finishes its decode steps sooner.
-  const int b = blockIdx.x / A.split, r0 = (blockIdx.x - b * A.split) * A.rows_per_cta;
-  const int N = A.N, NP = A.NP, GT = A.G, G = min(A.rows_per_cta, GT - r0);   // G: rows of this CTA, from row r0
+  // TcdArgs must not grow (8 more bytes of kernel parameters cost 7 % of the full-occupancy throughput) and the
+  // unsplit kernel must not change: the split kernels are separate instantiations that find their rows per CTA
+  // in A.dbg_step (unused outside DEBUG builds).
+  const int n_parts = SPLIT ? (A.G + A.dbg_step - 1) / A.dbg_step : 1;
+  const int b = SPLIT ? blockIdx.x / n_parts : blockIdx.x;
+  const int r0 = SPLIT ? (blockIdx.x - b * n_parts) * A.dbg_step : 0;
+  const int N = A.N, NP = A.NP, GT = A.G;
+  const int G = SPLIT ? min(A.dbg_step, GT - r0) : A.G;   // rows of this CTA, from row r0 of the instance
   const int n_steps = N - 2;
   const int n_tiles = G > 128 ? 2 : 1;
   const int K0 = tcd_k0(NP), K1 = NP - K0;     // key halves A = [0,K0), B = [K0,NP): one softmax warp each
@@ -891,8 +896,11 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
           pass(std::true_type{});
         } else {
           pass(std::false_type{});
-          if (__any_sync(0xffffffffu, valid && best * kTcdInvSqrtH > 3.0f)) pass(std::true_type{});
-          else best = (best == -INFINITY) ? best : clip_tanh10(best * kTcdInvSqrtH);   // candidates are exchanged as clipped logits
+          if (__any_sync(0xffffffffu, valid && best * kTcdInvSqrtH > 3.0f)) {
+            pass(std::true_type{});
+          } else {
+            best = (best == -INFINITY) ? best : clip_tanh10(best * kTcdInvSqrtH);   // candidates are exchanged as clipped logits
+          }
         }
         tick(4);
         int a;
@@ -1014,7 +1022,7 @@ static void tcd_choose_split(int Bp, int G, bool debug, int& split, int& rows_pe
   }
 }
 
-template <bool LOGITS, bool DEBUG, bool PSINGLE>
+template <bool LOGITS, bool DEBUG, bool PSINGLE, bool SPLIT>
 static int launch_tcd(const TcdArgs& a, int Bp, cudaStream_t s) {
   const size_t smem = (size_t)2 * TCD_TILE_STAGING + (size_t)2 * TCD_STAGES * TCD_STAGE +
                       (size_t)a.NP * 4 + 2 * TB_PER_TILE * 8 + 16;   // 224 KB + c0 + barriers
@@ -1022,10 +1030,10 @@ static int launch_tcd(const TcdArgs& a, int Bp, cudaStream_t s) {
     set_error("decode_tc: N=%d needs %zu bytes of shared memory", a.N, smem);
     return HTSP_ERR_UNSUPPORTED;
   }
-  HTSP_CHECK_CUDA(cudaFuncSetAttribute(decode_tc_kernel<LOGITS, DEBUG, PSINGLE>,
+  HTSP_CHECK_CUDA(cudaFuncSetAttribute(decode_tc_kernel<LOGITS, DEBUG, PSINGLE, SPLIT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kernel_timer_begin(s);
-  decode_tc_kernel<LOGITS, DEBUG, PSINGLE><<<Bp * a.split, TCD_THREADS, smem, s>>>(a);
+  decode_tc_kernel<LOGITS, DEBUG, PSINGLE, SPLIT><<<SPLIT ? Bp * ((a.G + a.dbg_step - 1) / a.dbg_step) : Bp, TCD_THREADS, smem, s>>>(a);
   kernel_timer_end(s);
   HTSP_CHECK_LAUNCH();
   return HTSP_OK;
@@ -1050,15 +1058,17 @@ int launch_decode_tc(const float* x, const float* proj, const float* qfix, const
   a.src = src; a.tgt = tgt; a.first = first; a.forced_pi = forced_pi;
   a.pi = pi; a.reward = reward; a.logits_out = logits_out; a.dbg = dbg;
   a.N = N; a.NP = NP; a.G = G; a.fast = (mode == HTSP_MODE_TC_FAST) ? 1 : 0; a.dbg_step = dbg_step;
-  tcd_choose_split(Bp, G, dbg != nullptr, a.split, a.rows_per_cta);
-  if (a.fast) {
-    if (dbg != nullptr) return launch_tcd<false, true, true>(a, Bp, s);
-    if (logits_out != nullptr) return launch_tcd<true, false, true>(a, Bp, s);
-    return launch_tcd<false, false, true>(a, Bp, s);
+  int n_split = 1, rows_per_cta = G;
+  tcd_choose_split(Bp, G, dbg != nullptr, n_split, rows_per_cta);
+  const bool split = n_split > 1;
+  if (split) a.dbg_step = rows_per_cta;
+  if (dbg != nullptr) return a.fast ? launch_tcd<false, true, true, false>(a, Bp, s) : launch_tcd<false, true, false, false>(a, Bp, s);
+  if (logits_out != nullptr) {
+    if (a.fast) return split ? launch_tcd<true, false, true, true>(a, Bp, s) : launch_tcd<true, false, true, false>(a, Bp, s);
+    return split ? launch_tcd<true, false, false, true>(a, Bp, s) : launch_tcd<true, false, false, false>(a, Bp, s);
   }
-  if (dbg != nullptr) return launch_tcd<false, true, false>(a, Bp, s);
-  if (logits_out != nullptr) return launch_tcd<true, false, false>(a, Bp, s);
-  return launch_tcd<false, false, false>(a, Bp, s);
+  if (a.fast) return split ? launch_tcd<false, false, true, true>(a, Bp, s) : launch_tcd<false, false, true, false>(a, Bp, s);
+  return split ? launch_tcd<false, false, false, true>(a, Bp, s) : launch_tcd<false, false, false, false>(a, Bp, s);
 }
 
 }  // namespace htsp

@@ -516,6 +516,34 @@ def test_tcgen05_and_mma_kernels_agree(solvers, sd6, mode, monkeypatch):
     print(f"[{mode}] rows identical between the tcgen05 and mma.sync kernels: {same:.3f}")
 
 
+@pytest.mark.parametrize("mode", ["x3", "fast"])
+@pytest.mark.parametrize("Bp,N,G", [(3, 200, 200), (2, 130, 130), (5, 64, 40), (1, 200, 33)])
+def test_row_split_launch_is_bit_identical(solvers, monkeypatch, mode, Bp, N, G):
+    """Low-occupancy launches cut the POMO rows of an instance into 128/64/32-row parts, one CTA each
+    (csrc/decode_tc.cu, tcd_choose_split).  Rows are independent: tours, rewards and the teacher-forced logits
+    must not change by a bit, for every forced number of parts and for the automatic choice."""
+    s = solvers[mode]
+    g = torch.Generator().manual_seed(77 + Bp + N)
+    x = torch.rand(Bp, N, 2, generator=g)
+    src = torch.randint(0, N, (Bp,), generator=g)
+    tgt = (src + 1 + torch.randint(0, N - 1, (Bp,), generator=g)) % N
+    first = torch.randperm(N, generator=g)[:G]
+    xc = x.cuda()
+    emb = s.encode(xc)
+    monkeypatch.setenv("HTSP_DECODE_SPLIT", "1")
+    pi0, rew0, _ = s.rollout(xc, emb, src, tgt, first)
+    _, _, lg0 = s.rollout(xc, emb, src, tgt, first, forced_pi=pi0, want_logits=True)
+    for parts in ("2", "4", "8", None):
+        if parts is None:
+            monkeypatch.delenv("HTSP_DECODE_SPLIT")
+        else:
+            monkeypatch.setenv("HTSP_DECODE_SPLIT", parts)
+        pi1, rew1, _ = s.rollout(xc, emb, src, tgt, first)
+        _, _, lg1 = s.rollout(xc, emb, src, tgt, first, forced_pi=pi0, want_logits=True)
+        assert torch.equal(pi0, pi1) and torch.equal(rew0, rew1), f"parts={parts}"
+        assert torch.equal(torch.nan_to_num(lg0, neginf=-1e30), torch.nan_to_num(lg1, neginf=-1e30)), f"parts={parts}"
+
+
 # ---------------------------------------------------------------- multi-GPU: augmentation sharding (8e)
 @pytest.mark.parametrize("world", [2, 3, 8])
 def test_aug_sharding_equals_single_gpu_hook(solvers, world):
