@@ -176,7 +176,8 @@ static int decode_impl(const void* blob, int n_layers, const float* x, const flo
                        const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp,
                        int N, int G, int mode, const int32_t* forced_pi, int32_t* pi,
                        float* reward, float* logits_out, void* workspace,
-                       size_t workspace_bytes, float* dbg, int dbg_step, void* stream) {
+                       size_t workspace_bytes, float* dbg, int dbg_step, void* stream,
+                       const uint64_t* sample_seed = nullptr) {
   HTSP_REQUIRE(blob && x && emb && src && tgt && first && pi && reward, "null pointer");
   HTSP_REQUIRE(Bp >= 0 && N >= 3 && G >= 1 && G <= N && n_layers >= 0, "bad shape");
   HTSP_REQUIRE(mode >= HTSP_MODE_FP32 && mode <= HTSP_MODE_TC_FAST, "bad mode");
@@ -196,12 +197,17 @@ static int decode_impl(const void* blob, int n_layers, const float* x, const flo
   void* prep_ws = tc ? (void*)(w + dec_pack_bytes(Bp, N, G)) : nullptr;
   int rc = launch_decode_prep(blob, n_layers, emb, src, tgt, Bp, N, proj, qfix, c0, tc, prep_ws, s);
   if (rc) return rc;
+  if (sample_seed != nullptr && (mode == HTSP_MODE_FP32 || !use_tc_kernel(N, G))) {
+    set_error("htsp_decode_sample: sampling rollouts are served by the tcgen05 kernel only (tensor-core mode, "
+              "17 <= N <= 208, G <= 256); got mode %d, N %d, G %d", mode, N, G);
+    return HTSP_ERR_UNSUPPORTED;
+  }
   if (mode == HTSP_MODE_FP32)
     return launch_decode_f32((const float*)blob, n_layers, x, emb, proj, qfix, src, tgt, first, Bp,
                              N, G, forced_pi, pi, reward, logits_out, s);
   if (use_tc_kernel(N, G))
     return launch_decode_tc(x, proj, qfix, c0, src, tgt, first, Bp, N, G, mode, forced_pi, pi, reward,
-                            logits_out, pack_ws, dbg, dbg_step, s);
+                            logits_out, pack_ws, dbg, dbg_step, sample_seed, s);
   HTSP_REQUIRE(dbg == nullptr, "debug dump needs the tcgen05 kernel");
   return launch_decode_mma(x, proj, qfix, c0, src, tgt, first, Bp, N, G, mode, forced_pi, pi, reward,
                            logits_out, pack_ws, s);
@@ -214,6 +220,14 @@ extern "C" int htsp_decode(const void* blob, int n_layers, const float* x, const
                            size_t workspace_bytes, void* stream) {
   return decode_impl(blob, n_layers, x, emb, src, tgt, first, Bp, N, G, mode, forced_pi, pi, reward,
                      logits_out, workspace, workspace_bytes, nullptr, 0, stream);
+}
+
+extern "C" int htsp_decode_sample(const void* blob, int n_layers, const float* x, const float* emb,
+                                  const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp,
+                                  int N, int G, int mode, uint64_t seed, int32_t* pi, float* reward,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  return decode_impl(blob, n_layers, x, emb, src, tgt, first, Bp, N, G, mode, nullptr, pi, reward, nullptr,
+                     workspace, workspace_bytes, nullptr, 0, stream, &seed);
 }
 
 extern "C" size_t htsp_decode_debug_floats(int N) { return decode_tc_dbg_floats(N); }

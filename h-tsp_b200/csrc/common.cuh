@@ -167,6 +167,7 @@ size_t decode_tc_dbg_floats(int N);
 int launch_decode_tc(const float* x, const float* proj, const float* qfix, const float* c0,
                      const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp, int N,
                      int G, int mode, const int32_t* forced_pi, int32_t* pi, float* reward,
-                     float* logits_out, void* pack_ws, float* dbg, int dbg_step, cudaStream_t s);
+                     float* logits_out, void* pack_ws, float* dbg, int dbg_step, const uint64_t* sample_seed,
+                     cudaStream_t s);
 
 }  // namespace htsp

@@ -249,10 +249,31 @@ __device__ __forceinline__ void tst(uint32_t taddr, const uint32_t (&r)[32]) {
   }
 }
 
+// Philox4x32-10 (counter-based: the noise of (instance, row, step, key quad) does not depend on the launch geometry)
+__device__ __forceinline__ uint4 tcd_philox(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+// standard Gumbel noise -ln(-ln u), u uniform in (0,1) from 24 random bits
+__device__ __forceinline__ float tcd_gumbel(uint32_t bits) {
+  const float u = ((float)(bits >> 8) + 0.5f) * 5.9604644775390625e-08f;
+  return -__logf(-__logf(u));
+}
+
+// SAMPLE (htsp_decode_sample): instead of the arg-max every row draws its next node from softmax(logits)
+// (train_path_solver.py:266-271, probs.multinomial(1)) by the Gumbel-max rule arg-max_j (z_j + g_j); the 64-bit
+// seed travels in A.dbg (unused outside DEBUG builds: TcdArgs must not grow).
 // PSINGLE (HTSP_MODE_TC_FAST): the softmax probabilities are stored as one fp16 (no lo part), the row
 // sum is taken from the ROUNDED values so that the normalisation stays consistent; S, V and the pointer
 // logits keep the full split.  Logit error ~2.5e-4 (bound 1e-3) instead of ~3e-5.
-template <bool LOGITS, bool DEBUG, bool PSINGLE, bool SPLIT>
+template <bool LOGITS, bool DEBUG, bool PSINGLE, bool SPLIT, bool SAMPLE>
 __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs A) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31;
@@ -268,6 +289,7 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
   const int r0 = SPLIT ? (blockIdx.x - b * n_parts) * A.dbg_step : 0;
   const int N = A.N, NP = A.NP, GT = A.G;
   const int G = SPLIT ? min(A.dbg_step, GT - r0) : A.G;   // rows of this CTA, from row r0 of the instance
+  const unsigned long long sample_seed = SAMPLE ? (unsigned long long)(uintptr_t)A.dbg : 0ull;
   const int n_steps = N - 2;
   const int n_tiles = G > 128 ? 2 : 1;
   const int K0 = tcd_k0(NP), K1 = NP - K0;     // key halves A = [0,K0), B = [K0,NP): one softmax warp each
@@ -873,11 +895,17 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
             for (int j4 = 0; j4 < 4; ++j4) {
               const float4 cc = cc4[j4];
               const float ca[4] = {cc.x, cc.y, cc.z, cc.w};
+              uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
+              if (SAMPLE)
+                rnd = tcd_philox(make_uint4((uint32_t)(4 * c + j4), (uint32_t)step, (uint32_t)(r0 + gc), (uint32_t)b),
+                                 make_uint2((uint32_t)sample_seed, (uint32_t)(sample_seed >> 32)));
+              const uint32_t ra[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
               for (int jj = 0; jj < 4; ++jj) {
                 const int j = 4 * j4 + jj;
                 float z = __uint_as_float(u[j]) + ca[jj];          // EXACT: 10 tanh(z / sqrt(128)); else the
                 if (EXACT) z = clip_tanh10(z * kTcdInvSqrtH);       // monotone pre-activation itself
+                if (SAMPLE) z += tcd_gumbel(ra[jj]);
                 if ((bits >> j) & 1u) z = -INFINITY;
                 if (LOGITS && lo_out != nullptr && valid && 16 * c + j < N) lo_out[16 * c + j] = z;
                 if (z > bj[j]) { bj[j] = z; cj[j] = c; }
@@ -892,7 +920,7 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
             if (bj[j] > best || (bj[j] == best && key < idx)) { best = bj[j]; idx = key; }
           }
         };
-        if (LOGITS) {
+        if (LOGITS || SAMPLE) {
           pass(std::true_type{});
         } else {
           pass(std::false_type{});
@@ -1022,7 +1050,7 @@ static void tcd_choose_split(int Bp, int G, bool debug, int& split, int& rows_pe
   }
 }
 
-template <bool LOGITS, bool DEBUG, bool PSINGLE, bool SPLIT>
+template <bool LOGITS, bool DEBUG, bool PSINGLE, bool SPLIT, bool SAMPLE = false>
 static int launch_tcd(const TcdArgs& a, int Bp, cudaStream_t s) {
   const size_t smem = (size_t)2 * TCD_TILE_STAGING + (size_t)2 * TCD_STAGES * TCD_STAGE +
                       (size_t)a.NP * 4 + 2 * TB_PER_TILE * 8 + 16;   // 224 KB + c0 + barriers
@@ -1030,10 +1058,10 @@ static int launch_tcd(const TcdArgs& a, int Bp, cudaStream_t s) {
     set_error("decode_tc: N=%d needs %zu bytes of shared memory", a.N, smem);
     return HTSP_ERR_UNSUPPORTED;
   }
-  HTSP_CHECK_CUDA(cudaFuncSetAttribute(decode_tc_kernel<LOGITS, DEBUG, PSINGLE, SPLIT>,
+  HTSP_CHECK_CUDA(cudaFuncSetAttribute(decode_tc_kernel<LOGITS, DEBUG, PSINGLE, SPLIT, SAMPLE>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kernel_timer_begin(s);
-  decode_tc_kernel<LOGITS, DEBUG, PSINGLE, SPLIT><<<SPLIT ? Bp * ((a.G + a.dbg_step - 1) / a.dbg_step) : Bp, TCD_THREADS, smem, s>>>(a);
+  decode_tc_kernel<LOGITS, DEBUG, PSINGLE, SPLIT, SAMPLE><<<SPLIT ? Bp * ((a.G + a.dbg_step - 1) / a.dbg_step) : Bp, TCD_THREADS, smem, s>>>(a);
   kernel_timer_end(s);
   HTSP_CHECK_LAUNCH();
   return HTSP_OK;
@@ -1042,8 +1070,11 @@ static int launch_tcd(const TcdArgs& a, int Bp, cudaStream_t s) {
 int launch_decode_tc(const float* x, const float* proj, const float* qfix, const float* c0,
                      const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp, int N,
                      int G, int mode, const int32_t* forced_pi, int32_t* pi, float* reward,
-                     float* logits_out, void* pack_ws, float* dbg, int dbg_step, cudaStream_t s) {
+                     float* logits_out, void* pack_ws, float* dbg, int dbg_step, const uint64_t* sample_seed,
+                     cudaStream_t s) {
   HTSP_REQUIRE(decode_tc_supported(N, G), "decode_tc shape");
+  HTSP_REQUIRE(sample_seed == nullptr || (dbg == nullptr && logits_out == nullptr && forced_pi == nullptr),
+               "sampling rollouts take no teacher forcing, logit capture or debug dump");
   const int NP = tcd_np_of(N);
   unsigned char* img = (unsigned char*)(((uintptr_t)pack_ws + 1023) & ~(uintptr_t)1023);
   {
@@ -1062,6 +1093,11 @@ int launch_decode_tc(const float* x, const float* proj, const float* qfix, const
   tcd_choose_split(Bp, G, dbg != nullptr, n_split, rows_per_cta);
   const bool split = n_split > 1;
   if (split) a.dbg_step = rows_per_cta;
+  if (sample_seed != nullptr) {
+    a.dbg = (float*)(uintptr_t)(*sample_seed);      // see SAMPLE above
+    if (a.fast) return split ? launch_tcd<false, false, true, true, true>(a, Bp, s) : launch_tcd<false, false, true, false, true>(a, Bp, s);
+    return split ? launch_tcd<false, false, false, true, true>(a, Bp, s) : launch_tcd<false, false, false, false, true>(a, Bp, s);
+  }
   if (dbg != nullptr) return a.fast ? launch_tcd<false, true, true, false>(a, Bp, s) : launch_tcd<false, true, false, false>(a, Bp, s);
   if (logits_out != nullptr) {
     if (a.fast) return split ? launch_tcd<true, false, true, true>(a, Bp, s) : launch_tcd<true, false, true, false>(a, Bp, s);

@@ -143,8 +143,9 @@ class B200PathSolver(torch.nn.Module):
 
     def rollout(self, x: torch.Tensor, emb: torch.Tensor, src: torch.Tensor, tgt: torch.Tensor,
                 first: torch.Tensor, forced_pi: Optional[torch.Tensor] = None,
-                want_logits: bool = False):
-        """Greedy POMO rollout -> (pi [Bp,G,N] i32, reward [Bp,G] f32, logits or None)."""
+                want_logits: bool = False, sample_seed: Optional[int] = None):
+        """POMO rollout -> (pi [Bp,G,N] i32, reward [Bp,G] f32, logits or None): greedy, or (sample_seed
+        given) every row samples its next node from the policy (htsp_decode_sample)."""
         lib = _abi.lib()
         Bp, N, _ = x.shape
         G = first.numel()
@@ -163,6 +164,15 @@ class B200PathSolver(torch.nn.Module):
                   if want_logits else None)
         nbytes = lib.htsp_decode_workspace_bytes(Bp, N, G, mode)
         ws = self._ws.get("dec", nbytes, dev)
+        if sample_seed is not None:
+            assert forced_pi is None and not want_logits
+            with torch.cuda.device(dev):
+                _abi.check(lib.htsp_decode_sample(self._packed_weights().data_ptr(), self.cfg.n_layers,
+                                                  x.data_ptr(), emb.data_ptr(), src.data_ptr(), tgt.data_ptr(),
+                                                  first.data_ptr(), Bp, N, G, mode, int(sample_seed) & (2**64 - 1),
+                                                  pi.data_ptr(), reward.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                  self._stream()), "htsp_decode_sample")
+            return pi, reward, None
         with torch.cuda.device(dev):
             _abi.check(lib.htsp_decode(self._packed_weights().data_ptr(), self.cfg.n_layers,
                                        x.data_ptr(), emb.data_ptr(), src.data_ptr(),
@@ -234,9 +244,13 @@ class B200PathSolver(torch.nn.Module):
     @torch.no_grad()
     def forward(self, batch, source_nodes, target_nodes, val_type="x8Aug_2Traj", return_pi=False,
                 group_size=2, greedy=True):
-        if not greedy:
-            raise NotImplementedError("sampling rollouts (greedy=False) are outside the B200 hot "
-                                      "path (SURVEY.md section 8f rank 4); use the reference module")
+        # greedy=False (train_path_solver.py:266-271): rows sample their next node in the kernel; the seed
+        # is drawn from torch's global generator, so torch.manual_seed controls it (the reference consumes the
+        # same generator through multinomial: equal in distribution, not bit-wise)
+        if not greedy and (self.mode == "fp32" or not 17 <= batch.shape[1] <= 208 or int(group_size) > 256):
+            raise NotImplementedError("sampling rollouts (greedy=False) are served by the tcgen05 kernel only: "
+                                      "tensor-core mode, 17 <= N <= 208, group_size <= 256")
+        sample_seed = None if greedy else int(torch.randint(0, 2**62, (1,)).item())
         lib = _abi.lib()
         val_type = val_type or self.cfg.val_type
         dev = self.device
@@ -260,7 +274,7 @@ class B200PathSolver(torch.nn.Module):
         else:
             x = batch
         first = self.draw_first_action(N, G)
-        pi, reward = self._rollout_chunked(x, src, tgt, first, n_aug)
+        pi, reward = self._rollout_chunked(x, src, tgt, first, n_aug, sample_seed)
         if val_type == "noAug_1Traj":
             max_reward, best_pi = reward, pi.to(torch.int64)
         else:
@@ -271,18 +285,19 @@ class B200PathSolver(torch.nn.Module):
             return -max_reward, best_pi.squeeze()
         return -max_reward
 
-    def _rollout_chunked(self, x, src, tgt, first, n_aug):
+    def _rollout_chunked(self, x, src, tgt, first, n_aug, sample_seed=None):
         Bp = x.shape[0]
         cap = self.max_instances_per_launch
         if Bp <= cap:
             emb = self.encode(x)
-            pi, reward, _ = self.rollout(x, emb, src, tgt, first)
+            pi, reward, _ = self.rollout(x, emb, src, tgt, first, sample_seed=sample_seed)
             return pi, reward
         pis, rs = [], []
         for s in range(0, Bp, cap):
             xs = x[s:s + cap]
             emb = self.encode(xs)
-            p, r, _ = self.rollout(xs, emb, src[s:s + cap], tgt[s:s + cap], first)
+            seed_s = None if sample_seed is None else sample_seed + 0x9E3779B97F4A7C15 * (s // cap)   # own stream per chunk
+            p, r, _ = self.rollout(xs, emb, src[s:s + cap], tgt[s:s + cap], first, sample_seed=seed_s)
             pis.append(p)
             rs.append(r)
         return torch.cat(pis), torch.cat(rs)

@@ -97,6 +97,17 @@ int htsp_decode(const void* blob, int n_layers, const float* x, const float* emb
                 const int32_t* forced_pi, int32_t* pi, float* reward, float* logits_out,
                 void* workspace, size_t workspace_bytes, void* stream);
 
+/* Sampling rollout (forward only): PathSolver.forward(greedy=False),
+ * train_path_solver.py:266-271 -- every row draws its next node from softmax(masked 10*tanh logits)
+ * (`probs.multinomial(1)`) instead of the arg-max.  Drawn in the kernel by the Gumbel-max rule with
+ * Philox4x32-10 noise keyed by (seed; instance, row, step, key): the tours depend on `seed` only, not on the
+ * launch geometry; they match the reference in distribution, never bit-wise (different generator).
+ * Served by the tcgen05 kernel only (tensor-core mode, 17 <= N <= 208, G <= 256), else HTSP_ERR_UNSUPPORTED. */
+int htsp_decode_sample(const void* blob, int n_layers, const float* x, const float* emb,
+                       const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp, int N,
+                       int G, int mode, uint64_t seed, int32_t* pi, float* reward, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 /* Test hook (tests/test_parity_gpu.py): as htsp_decode in a tensor-core mode on the tcgen05 kernel
  * (N <= 224, G <= 256), additionally dumping the intermediates of instance 0 at decode step
  * `dbg_step` into dbg [htsp_decode_debug_floats(N)] f32: raw glimpse scores S [2,8,128,NP]

@@ -200,15 +200,104 @@ def test_peaked_policies(built_lib, mode, seed, n_layers):
     assert torch.equal(torch.isinf(got), torch.isinf(want))
     err = float((got[fin] - want[fin]).abs().max())
     # operand magnitudes are 3-5x the seed-1234/6-layer case and the fp32-class bounds scale with them
-    # (measured: fp32 6.5e-5, x3 1.1e-4 / 3.1e-4).  `fast` keeps the glimpse scores in single fp16, whose
-    # error grows with |q||k|: 6e-3 / 9e-3 here -- outside the 1e-3 budget, which is why x3 is the default.
-    tol = {"fp32": 2.5e-4, "x3": 5e-4, "fast": 2e-2}[mode]
+    # (measured: fp32 6.5e-5, x3 1.1e-4 / 3.4e-4).  `fast` on the tcgen05 kernel (single-fp16 softmax
+    # probabilities) measures 7.8e-4 / 9.6e-4 here: inside the 1e-3 budget but close to it, which is why x3 is
+    # the default (the mma.sync kernel's `fast`, single-fp16 glimpse scores, reaches 6e-3 / 9e-3 on these weights).
+    tol = {"fp32": 2.5e-4, "x3": 5e-4, "fast": 2e-3}[mode]
     print(f"[{mode}] seed {seed} L={n_layers}: max |z| {float(want[fin].abs().max()):.3f}, max |dz| = {err:.2e}")
     assert err <= tol
     pi2, reward2, _ = s.rollout(xc, emb, src, tgt, first)
     with torch.no_grad():
         _, _, forced = tie_aware_check(sd, x, src, tgt, first, pi2.cpu().long(), 2 * tol)
     assert rel_err(reward2, forced.reward) <= 1e-5
+
+
+# ---------------------------------------------------------------- sampling rollouts (8f-4, forward only)
+@pytest.mark.parametrize("mode", ["x3", "fast"])
+def test_sampling_rollout_validity_and_distribution(built_lib, monkeypatch, mode):
+    """greedy=False (train_path_solver.py:266-271): rows draw the next node from softmax(logits).  In-kernel
+    Gumbel-max sampling can only match `multinomial` in distribution: 512 replicas of one instance give 512
+    independent draws per row; the first sampled node of every row is chi-square tested against the ORACLE's
+    probabilities (and must be far from uniform: the test has power).  Tours must be valid rollouts, rewards
+    the length of the sampled tour, and the draws a function of the seed only (not of the launch geometry)."""
+    from htsp_b200 import B200PathSolver
+    from htsp_b200.weights import synthetic_state_dict
+    sd = synthetic_state_dict(4321, 6)                      # peaked policy: probabilities far from uniform
+    s = B200PathSolver(state_dict=sd, mode=mode, device="cuda")
+    g = torch.Generator().manual_seed(5)
+    N, G, R = 40, 30, 512
+    x1 = torch.rand(1, N, 2, generator=g)
+    x = x1.expand(R, N, 2).contiguous()
+    src = torch.zeros(R, dtype=torch.long)
+    tgt = torch.full((R,), N - 1)
+    first = 1 + torch.randperm(N - 2, generator=g)[:G]      # never an endpoint: the first draw sits at tour index 1
+    xc = x.cuda()
+    emb = s.encode(xc)
+    pi, rew, _ = s.rollout(xc, emb, src, tgt, first, sample_seed=12345)
+    pic = pi.cpu().long()
+    assert bool((pic.sort(dim=-1).values == torch.arange(N)).all()) and bool((pic[:, :, 0] == first).all())
+    with torch.no_grad():                                   # valid under the reference state machine + reward
+        forced = po.rollout(sd, x[:4], src[:4], tgt[:4], first, forced_pi=pic[:4])
+    assert torch.equal(forced.pi, pic[:4])
+    assert rel_err(rew[:4], forced.reward) <= 1e-5
+    # the draws depend on the seed only
+    pi_same, _, _ = s.rollout(xc, emb, src, tgt, first, sample_seed=12345)
+    pi_other, _, _ = s.rollout(xc, emb, src, tgt, first, sample_seed=12346)
+    assert torch.equal(pi, pi_same) and not torch.equal(pi, pi_other)
+    monkeypatch.setenv("HTSP_DECODE_SPLIT", "4")
+    pi_split, rew_split, _ = s.rollout(xc, emb, src, tgt, first, sample_seed=12345)
+    monkeypatch.delenv("HTSP_DECODE_SPLIT")
+    assert torch.equal(pi, pi_split) and torch.equal(rew, rew_split)
+    assert len({tuple(t) for t in pic[:, 0].tolist()}) > R // 2          # replicas really differ
+    # distribution of the first draw
+    with torch.no_grad():
+        ref = po.rollout(sd, x1, src[:1], tgt[:1], first, forced_pi=pic[:1], capture_logits=True)
+    p = torch.softmax(ref.logits[0][0].double(), dim=-1)                   # [G,N], zeros at visited nodes
+    counts = torch.zeros(G, N, dtype=torch.double)
+    counts.scatter_add_(1, pic[:, :, 1].t().contiguous(), torch.ones(G, R, dtype=torch.double))
+
+    def chi2(prob):
+        stat, df = 0.0, 0
+        for r in range(G):
+            e = prob[r] * R
+            big = e >= 5
+            obs = torch.cat([counts[r][big], counts[r][~big].sum()[None]])
+            exp = torch.cat([e[big], e[~big].sum()[None]])
+            keep = exp > 0
+            stat += float(((obs[keep] - exp[keep]) ** 2 / exp[keep]).sum())
+            df += int(keep.sum()) - 1
+        return stat, df
+
+    stat, df = chi2(p)
+    unvisited = (p > 0).double()
+    stat_u, df_u = chi2(unvisited / unvisited.sum(dim=1, keepdim=True))
+    print(f"[{mode}] sampling: chi2 {stat:.0f} on {df} dof (uniform alternative: {stat_u:.0f} on {df_u})")
+    assert stat <= df + 5 * (2 * df) ** 0.5
+    assert stat_u >= df_u + 50 * (2 * df_u) ** 0.5
+
+
+def test_forward_sampling_surface(solvers):
+    """PathSolver.forward(greedy=False): same return shapes as the greedy call, reproducible under
+    torch.manual_seed (the seed of the in-kernel generator is drawn from torch's), valid tours."""
+    s = solvers["x3"]
+    g = torch.Generator().manual_seed(8)
+    B, N, G = 3, 50, 20
+    x = torch.rand(B, N, 2, generator=g)
+    src = torch.zeros(B, 1, dtype=torch.long)
+    tgt = torch.full((B, 1), N - 1, dtype=torch.long)
+    s.first_action_override = torch.randperm(N, generator=g)[:G]
+    try:
+        torch.manual_seed(3)
+        l1, p1 = s(x, src, tgt, val_type="x8Aug_nTraj", return_pi=True, group_size=G, greedy=False)
+        torch.manual_seed(3)
+        l2, p2 = s(x, src, tgt, val_type="x8Aug_nTraj", return_pi=True, group_size=G, greedy=False)
+        l3, p3 = s(x, src, tgt, val_type="x8Aug_nTraj", return_pi=True, group_size=G, greedy=False)
+        lg, pg = s(x, src, tgt, val_type="x8Aug_nTraj", return_pi=True, group_size=G, greedy=True)
+    finally:
+        s.first_action_override = None
+    assert l1.shape == lg.shape == (B,) and p1.shape == pg.shape == (B, N)
+    assert torch.equal(p1, p2) and torch.equal(l1, l2) and not torch.equal(p1, p3)
+    assert bool((p1.sort(dim=-1).values.cpu() == torch.arange(N)).all())
 
 
 # ---------------------------------------------------------------- PathSolver.forward surface
