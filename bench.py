@@ -52,6 +52,18 @@ def k3_dram_traffic(args, B, N, G, L):
     return None
 
 
+def k3_pipe_utilisation(args, N, G, L):
+    """What actually limits the rollout kernel (it is NOT the tensor pipe): pipe utilisations of the committed
+    `ncu --set full` capture of the default kernel (profiles/r01_decode_tc_x3_final_raw_summary.txt, 296
+    instances of the same shape); quoted for that kernel and shape only, otherwise null."""
+    if (args.mode, N, G, L) == ("x3", 200, 200, 6) and os.environ.get("HTSP_DECODE_IMPL") != "mma":
+        return {"issue_slots_pct": 59.2, "alu_pct": 44.5, "xu_mufu_pct": 34.4, "tensor_pct": 21.5, "fma_pct": 17.9,
+                "l2_hit_pct": 98.9, "note": "bound by the softmax between the MMAs (issue + MUFU.EX2 + dependency "
+                "latency with one instance per SM in TMEM), see DESIGN.md section 5",
+                "source": "profiles/r01_decode_tc_x3_final_raw_summary.txt"}
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -430,7 +442,8 @@ def run_b200(args):
                          "frac": achieved / tc_peak, "traffic": k3_dram_traffic(args, B, N, G, L),
                          "peak_source": f"bf16_tflops_sustained, {peak_src}",
                          "kernel_ms": kms, "kernel_share_of_step": kms / (total_ms / args.steps),
-                         "algorithmic_flops_per_launch": dec_f * B},
+                         "algorithmic_flops_per_launch": dec_f * B,
+                         "pipes": k3_pipe_utilisation(args, N, G, L)},
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{args.cpu_sample} subproblems (N={N}, G={G}, noAug_nTraj, "
                                        f"L={L}) in {cpu_dt:.1f} s, oracle port, torch CPU fp32",
