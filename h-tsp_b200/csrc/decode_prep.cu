@@ -11,34 +11,50 @@
 
 namespace htsp {
 
+// One CTA (4 warps) per instance.  Pass 1 walks the embedding rows once: warp w takes rows w, w+4, ...,
+// lane l holds columns 4l..4l+3 (one 512-byte row per load instruction), accumulates the column sums for
+// the graph mean and reduces bc . emb[n] (c0) with shuffles.  Pass 2: thread t computes output t of the
+// three 128 x 128 mat-vecs from float4 weight-row reads (L1-resident across the CTAs of an SM).
 __global__ void __launch_bounds__(128)
 decode_prep_kernel(const float* __restrict__ emb, const float* __restrict__ Wg,
                    const float* __restrict__ Ws, const float* __restrict__ Wt,
                    const float* __restrict__ bc, const int32_t* __restrict__ src,
                    const int32_t* __restrict__ tgt, int N, float* __restrict__ qfix,
                    float* __restrict__ c0) {
-  __shared__ float mean[H], es[H], et[H], bcs[H];
-  const int b = blockIdx.x, t = threadIdx.x;
+  __shared__ __align__(16) float part[4][H];
+  __shared__ __align__(16) float mean[H], es[H], et[H];
+  const int b = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const float* e = emb + (size_t)b * N * H;
-  float acc = 0.f;
-  for (int n = 0; n < N; ++n) acc += __ldg(&e[(size_t)n * H + t]);
-  mean[t] = acc / (float)N;
+  const float4 bc4 = __ldg((const float4*)bc + lane);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int n = warp; n < N; n += 4) {
+    const float4 v = __ldg((const float4*)(e + (size_t)n * H) + lane);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    float d = fmaf(v.w, bc4.w, fmaf(v.z, bc4.z, fmaf(v.y, bc4.y, v.x * bc4.x)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    if (lane == 0) c0[(size_t)b * N + n] = d;
+  }
+  *(float4*)&part[warp][4 * lane] = acc;
   es[t] = __ldg(&e[(size_t)src[b] * H + t]);
   et[t] = __ldg(&e[(size_t)tgt[b] * H + t]);
-  bcs[t] = __ldg(&bc[t]);
   __syncthreads();
+  mean[t] = ((part[0][t] + part[1][t]) + (part[2][t] + part[3][t])) / (float)N;
+  __syncthreads();
+  const float4* wg = (const float4*)(Wg + (size_t)t * H);
+  const float4* ws = (const float4*)(Ws + (size_t)t * H);
+  const float4* wt = (const float4*)(Wt + (size_t)t * H);
   float g = 0.f, s = 0.f, q = 0.f;
-  for (int i = 0; i < H; ++i) {
-    g = fmaf(mean[i], __ldg(&Wg[t * H + i]), g);
-    s = fmaf(es[i], __ldg(&Ws[t * H + i]), s);
-    q = fmaf(et[i], __ldg(&Wt[t * H + i]), q);
+#pragma unroll 8
+  for (int i = 0; i < H / 4; ++i) {
+    const float4 a = __ldg(wg + i), c = __ldg(ws + i), d = __ldg(wt + i);
+    const float4 m4 = *(const float4*)&mean[4 * i], s4 = *(const float4*)&es[4 * i], t4 = *(const float4*)&et[4 * i];
+    g = fmaf(m4.w, a.w, fmaf(m4.z, a.z, fmaf(m4.y, a.y, fmaf(m4.x, a.x, g))));
+    s = fmaf(s4.w, c.w, fmaf(s4.z, c.z, fmaf(s4.y, c.y, fmaf(s4.x, c.x, s))));
+    q = fmaf(t4.w, d.w, fmaf(t4.z, d.z, fmaf(t4.y, d.y, fmaf(t4.x, d.x, q))));
   }
   qfix[(size_t)b * H + t] = (g + s) + q;
-  for (int n = t; n < N; n += blockDim.x) {
-    float d = 0.f;
-    for (int i = 0; i < H; ++i) d = fmaf(bcs[i], __ldg(&e[(size_t)n * H + i]), d);
-    c0[(size_t)b * N + n] = d;
-  }
 }
 
 size_t decode_prep_tc_ws_bytes(int Bp, int N) {

@@ -98,21 +98,21 @@ __device__ __forceinline__ void tcd_split8_packed(const float* v, uint4& hi, uin
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// proj fp32 [Bp*N, 640] (K | V | QL | QF | K2) -> operand image
+// proj fp32 [Bp*N, 640] (K | V | QL | QF | K2) -> operand image.  grid = (blocks per instance, Bp): all index
+// math is 32-bit shifts (the first version spent its time in 64-bit divisions by NP)
 __global__ void __launch_bounds__(256)
 decode_tc_pack_kernel(const float* __restrict__ proj, int Bp, int N, int NP, unsigned char* __restrict__ img) {
   const size_t szk = tcd_szk(NP), szvh = tcd_szvh(NP), pair = tcd_pair_bytes(NP), per = tcd_img_bytes(NP);
-  // K and K2: one thread per (instance, key r, matrix m in {K, K2}, 8-column chunk c16)
-  const size_t total_a = (size_t)Bp * NP * 32;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_a;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const int c16 = (int)(i % 16);
-    const int m = (int)((i / 16) % 2);
-    const int r = (int)((i / 32) % NP);
-    const int b = (int)(i / ((size_t)32 * NP));
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int b = blockIdx.y; b < Bp; b += gridDim.y) {
+  const float* pb = proj + (size_t)b * N * PROJ;
+  unsigned char* base = img + (size_t)b * per;
+  // K and K2: one thread per (key r, matrix m in {K, K2}, 8-column chunk c16)
+  if (i < NP * 32) {
+    const int c16 = i & 15, m = (i >> 4) & 1, r = i >> 5;
     float v[8];
     if (r < N) {
-      const float4* p = (const float4*)(proj + ((size_t)b * N + r) * PROJ + (m == 0 ? 0 : 4 * H) + c16 * 8);
+      const float4* p = (const float4*)(pb + (size_t)r * PROJ + (m == 0 ? 0 : 4 * H) + c16 * 8);
       const float4 a = __ldg(p), c = __ldg(p + 1);
       v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
     } else {
@@ -121,7 +121,6 @@ decode_tc_pack_kernel(const float* __restrict__ proj, int Bp, int N, int NP, uns
     }
     uint4 hi, lo;
     tcd_split8(v, hi, lo);
-    unsigned char* base = img + (size_t)b * per;
     if (m == 0) {
       const int h = c16 >> 1, p = h >> 1, e = h & 1;
       unsigned char* blk = base + (size_t)p * pair;
@@ -133,26 +132,23 @@ decode_tc_pack_kernel(const float* __restrict__ proj, int Bp, int N, int NP, uns
       *(uint4*)(blk + 2 * szk + tc::sw128_off(r, c16 & 7)) = lo;
     }
   }
-  // V^T: one thread per (instance, group of 8 keys r8, value column c)
+  // V^T: one thread per (group of 8 keys r8, value column c)
   const int NG = tcd_kb(NP) * 8;
-  const size_t total_v = (size_t)Bp * NG * 128;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_v;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % 128);
-    const int r8 = (int)((i / 128) % NG);
-    const int b = (int)(i / ((size_t)128 * NG));
+  if (i < NG * 128) {
+    const int c = i & 127, r8 = i >> 7;
     float v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int r = r8 * 8 + k;
-      v[k] = (r < N) ? __ldg(proj + ((size_t)b * N + r) * PROJ + H + c) : 0.f;
+      v[k] = (r < N) ? __ldg(pb + (size_t)r * PROJ + H + c) : 0.f;
     }
     uint4 hi, lo;
     tcd_split8(v, hi, lo);
     const int h = c >> 4, d = c & 15, p = h >> 1, e = h & 1;
-    unsigned char* blk = img + (size_t)b * per + (size_t)p * pair + szk + (size_t)e * szvh + (size_t)(r8 >> 3) * 4096;
+    unsigned char* blk = base + (size_t)p * pair + szk + (size_t)e * szvh + (size_t)(r8 >> 3) * 4096;
     *(uint4*)(blk + tc::sw128_off(d, r8 & 7)) = hi;
     *(uint4*)(blk + tc::sw128_off(16 + d, r8 & 7)) = lo;
+  }
   }
 }
 
@@ -1078,10 +1074,8 @@ int launch_decode_tc(const float* x, const float* proj, const float* qfix, const
   const int NP = tcd_np_of(N);
   unsigned char* img = (unsigned char*)(((uintptr_t)pack_ws + 1023) & ~(uintptr_t)1023);
   {
-    const size_t total = (size_t)Bp * NP * 32;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    decode_tc_pack_kernel<<<blocks, 256, 0, s>>>(proj, Bp, N, NP, img);
+    const int items = max(NP * 32, tcd_kb(NP) * 8 * 128);
+    decode_tc_pack_kernel<<<dim3((items + 255) / 256, min(Bp, 65535)), 256, 0, s>>>(proj, Bp, N, NP, img);
     HTSP_CHECK_LAUNCH();
   }
   TcdArgs a;

@@ -67,6 +67,14 @@ __device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t&
   hi = *reinterpret_cast<uint32_t*>(&h);
   lo = *reinterpret_cast<uint32_t*>(&l);
 }
+// same split with the residual as one packed FFMA2 (x - hi is exact in fp32 either way: identical results)
+__device__ __forceinline__ void split2p(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x, y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float2 r = __ffma2_rn(__half22float2(h), make_float2(-1.f, -1.f), make_float2(x, y));
+  const __half2 l = __floats2half2_rn(r.x, r.y);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 __device__ __forceinline__ float ex2_approx(float x) {   // 2^x, rel. error 2^-22, -inf -> +0
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
