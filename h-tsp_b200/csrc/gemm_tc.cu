@@ -8,24 +8,28 @@
 //              of the four operand tiles per k-block into a 3-stage shared-memory ring
 //   warp 1   : MMA issuer    -- tcgen05.mma.cta_group::1.kind::f16, M=128, N=128, K=16, three MMAs
 //              per k16 step (hi*hi, hi*lo, lo*hi) into one of two TMEM accumulators (128 columns each)
-//   warps 2-9: epilogue      -- two warps per TMEM lane quarter (64 of the tile's 128 columns each):
-//              tcgen05.ld (32 lanes x 32 columns), transpose through shared memory so that every global
-//              load / store covers whole 128-byte lines, bias / ReLU / residual /
-//              eval-BatchNorm affine in registers, stores fp32 and/or the fp16 hi/lo split that the
-//              next layer's TMA reads; overlaps with the next tile's MMAs through the second accumulator.
+//   warps 2-17: epilogue     -- four warps per TMEM lane quarter (32 of the tile's 128 columns each):
+//              the residual rows are requested BEFORE the accumulator is waited for, then tcgen05.ld
+//              (32 lanes x 32 columns), transpose through shared memory (two 16-column halves, XOR-swizzled
+//              16-byte slots, st/ld.shared.v4) so that global loads / stores run along the rows,
+//              bias / ReLU / residual / eval-BatchNorm affine in registers, stores fp32 and/or the fp16
+//              hi/lo split that the next layer's TMA reads; overlaps with the next tile's MMAs through the
+//              second accumulator.
 // Synchronisation is mbarrier-only (full/empty per stage, tmem_full/tmem_empty per accumulator);
 // tcgen05.commit releases shared-memory stages and publishes accumulators.
 #include <cuda.h>
 #include "common.cuh"
+#include "mma_util.cuh"
 
 namespace htsp {
 
 constexpr int GT_BM = 128, GT_BN = 128, GT_BK = 64, GT_STAGES = 3;
 constexpr int GT_TILE_BYTES = GT_BM * GT_BK * 2;            // 16 KB, one operand tile
 constexpr int GT_STAGE_BYTES = 4 * GT_TILE_BYTES;           // A_hi, A_lo, B_hi, B_lo
-constexpr int GT_THREADS = 320;          // TMA producer, MMA issuer, 8 epilogue warps
+constexpr int GT_EPI_WARPS = 16;
+constexpr int GT_THREADS = 64 + 32 * GT_EPI_WARPS;          // TMA producer, MMA issuer, 16 epilogue warps
 constexpr uint32_t GT_TMEM_COLS = 256;
-constexpr int GT_EPI_BYTES = 8 * 32 * 33 * 4;               // four 32 x 32 (+1 pad) fp32 transpose tiles
+constexpr int GT_EPI_BYTES = GT_EPI_WARPS * 32 * 16 * 4;    // one 32 x 16 fp32 transpose tile per epilogue warp
 constexpr size_t GT_SMEM_BYTES = (size_t)GT_STAGES * GT_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + GT_EPI_BYTES;
 
 struct GemmEpi {
@@ -110,6 +114,15 @@ __device__ __forceinline__ void gt_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) 
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void gt_sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 gt_lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -129,7 +142,7 @@ gemm_x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < GT_STAGES; ++s) { gt_mbar_init(full0 + 8 * s, 1); gt_mbar_init(empty0 + 8 * s, 1); }
-    for (int a = 0; a < 2; ++a) { gt_mbar_init(tfull0 + 8 * a, 1); gt_mbar_init(tempty0 + 8 * a, 8); }
+    for (int a = 0; a < 2; ++a) { gt_mbar_init(tfull0 + 8 * a, 1); gt_mbar_init(tempty0 + 8 * a, GT_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -197,50 +210,113 @@ gemm_x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   } else {
     // ------------------------------------------------------------------ epilogue warps
     const int q = warp & 3;                   // TMEM lane quarter this warp may access
+    const int c = (warp - 2) >> 2;            // its 32-column chunk of the tile
+    // transpose tile of this warp: 32 rows x 16 columns fp32 (64-byte rows = four 16-byte slots); row r keeps
+    // slot s at s ^ ((r >> 1) & 3): the quarter-warp phases of both the row-wise writes (lane = row) and the
+    // reads (8 rows x 4 slots per pass) touch 8 distinct 16-byte bank groups
+    const uint32_t tr = gt_smem_u32(epi_smem) + (uint32_t)(warp - 2) * (32 * 16 * 4);
+    const uint32_t wr_row = tr + (uint32_t)lane * 64, wr_x = (uint32_t)(lane >> 1) & 3;
+    const int rsub = lane >> 2, slot = lane & 3;             // read phase: 8 rows x 4 slots per pass
+    const bool packed = E.y32 == nullptr && E.residual == nullptr && E.bn_alpha == nullptr && E.yhi != nullptr;
     uint32_t local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const uint32_t acc = local & 1, acc_use = local >> 1;
+      const int col0 = n_blk * GT_BN + c * 32;
+      const int rowb = m_blk * GT_BM + q * 32;
+      // residual rows first: the loads fly while the MMAs of this tile are still running
+      float4 res[2][4];
+      if (E.residual != nullptr) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+          for (int pp = 0; pp < 4; ++pp) {
+            const int row = rowb + pp * 8 + rsub;
+            res[hh][pp] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < E.M) res[hh][pp] = __ldg((const float4*)(E.residual + (size_t)row * E.Nout + col0 + hh * 16 + slot * 4));
+          }
+      }
+      float4 b4[2], al4[2], be4[2];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        b4[hh] = make_float4(0.f, 0.f, 0.f, 0.f); al4[hh] = make_float4(1.f, 1.f, 1.f, 1.f); be4[hh] = b4[hh];
+        if (E.bias != nullptr) b4[hh] = __ldg((const float4*)(E.bias + col0 + hh * 16 + slot * 4));
+        if (E.bn_alpha != nullptr) {
+          al4[hh] = __ldg((const float4*)(E.bn_alpha + col0 + hh * 16 + slot * 4));
+          be4[hh] = __ldg((const float4*)(E.bn_beta + col0 + hh * 16 + slot * 4));
+        }
+      }
       gt_mbar_wait(tfull0 + 8 * acc, acc_use & 1);
       gt_fence_after();
-      float* tr = epi_smem + (warp - 2) * (32 * 33);       // this warp's 32 x 32 transpose tile (row stride 33)
-      const int rsub = lane >> 3, csub = (lane & 7) * 4;   // store phase: 4 rows x 8 column quads per pass
-#pragma unroll 1
-      for (int c = 2 * ((warp - 2) >> 2); c < 2 * ((warp - 2) >> 2) + 2; ++c) {
-        uint32_t r[32];
-        gt_tmem_ld32(tmem_base + acc * GT_BN + c * 32 + ((uint32_t)(q * 32) << 16), r);
-        const int col0 = n_blk * GT_BN + c * 32;
-        // TMEM hands every lane one ROW (32 columns); global memory wants lanes along the columns:
-        // transpose through shared memory so that loads / stores cover whole 128-byte lines
-        __syncwarp();
+      uint32_t r[32];
+      gt_tmem_ld32(tmem_base + acc * GT_BN + c * 32 + ((uint32_t)(q * 32) << 16), r);
+      // the accumulator is in registers: hand the TMEM buffer back before the stores
+      gt_fence_before();
+      __syncwarp();
+      if (lane == 0) gt_mbar_arrive(tempty0 + 8 * acc);
+      if (packed) {
+        // fp16 hi/lo outputs only (QKV, FF1): bias / ReLU / split in the row-owner lane, then the packed
+        // halves are transposed (64-byte rows) so that every lane stores 16 bytes = 8 columns and a row's
+        // 64 bytes leave together
+        uint32_t hl[2][16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = __uint_as_float(r[j]);
-        __syncwarp();
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), al4 = make_float4(1.f, 1.f, 1.f, 1.f), be4 = b4;
-        if (E.bias != nullptr) b4 = __ldg((const float4*)(E.bias + col0 + csub));
-        if (E.bn_alpha != nullptr) {
-          al4 = __ldg((const float4*)(E.bn_alpha + col0 + csub));
-          be4 = __ldg((const float4*)(E.bn_beta + col0 + csub));
+        for (int k = 0; k < 8; ++k) {
+          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (E.bias != nullptr) bb = __ldg((const float4*)(E.bias + col0 + 4 * k));
+          float v0 = __uint_as_float(r[4 * k]) + bb.x, v1 = __uint_as_float(r[4 * k + 1]) + bb.y;
+          float v2 = __uint_as_float(r[4 * k + 2]) + bb.z, v3 = __uint_as_float(r[4 * k + 3]) + bb.w;
+          if (E.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+          split2p(v0, v1, hl[0][2 * k], hl[1][2 * k]);
+          split2p(v2, v3, hl[0][2 * k + 1], hl[1][2 * k + 1]);
         }
 #pragma unroll
-        for (int rr = 0; rr < 32; rr += 4) {
-          const int rl = rr + rsub;
-          const int row = m_blk * GT_BM + q * 32 + rl;
-          float v[4] = {tr[rl * 33 + csub], tr[rl * 33 + csub + 1], tr[rl * 33 + csub + 2], tr[rl * 33 + csub + 3]};
+        for (int part = 0; part < 2; ++part) {
+          __half* dst = part ? E.ylo : E.yhi;
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            gt_sts128(wr_row + (((uint32_t)j ^ wr_x) << 4), hl[part][4 * j], hl[part][4 * j + 1], hl[part][4 * j + 2],
+                      hl[part][4 * j + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int pp = 0; pp < 4; ++pp) {
+            const int rl = pp * 8 + rsub;
+            const int row = rowb + rl;
+            const float4 t4 = gt_lds128(tr + (uint32_t)rl * 64 + ((((uint32_t)slot) ^ (((uint32_t)rl >> 1) & 3)) << 4));
+            if (row < E.M) *(float4*)(dst + (size_t)row * E.Nout + col0 + slot * 8) = t4;
+          }
+        }
+        continue;
+      }
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        // TMEM hands every lane one ROW; global memory wants lanes along the columns
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          gt_sts128(wr_row + (((uint32_t)j ^ wr_x) << 4), r[hh * 16 + 4 * j], r[hh * 16 + 4 * j + 1],
+                    r[hh * 16 + 4 * j + 2], r[hh * 16 + 4 * j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int pp = 0; pp < 4; ++pp) {
+          const int rl = pp * 8 + rsub;
+          const int row = rowb + rl;
+          const float4 t4 = gt_lds128(tr + (uint32_t)rl * 64 + ((((uint32_t)slot) ^ (((uint32_t)rl >> 1) & 3)) << 4));
+          float v[4] = {t4.x, t4.y, t4.z, t4.w};
           if (row < E.M) {
-            const size_t off = (size_t)row * E.Nout + col0 + csub;
-            v[0] += b4.x; v[1] += b4.y; v[2] += b4.z; v[3] += b4.w;
+            const size_t off = (size_t)row * E.Nout + col0 + hh * 16 + slot * 4;
+            v[0] += b4[hh].x; v[1] += b4[hh].y; v[2] += b4[hh].z; v[3] += b4[hh].w;
             if (E.relu) {
 #pragma unroll
               for (int t = 0; t < 4; ++t) v[t] = fmaxf(v[t], 0.f);
             }
             if (E.residual != nullptr) {
-              const float4 x = __ldg((const float4*)(E.residual + off));
+              const float4 x = res[hh][pp];
               v[0] = x.x + v[0]; v[1] = x.y + v[1]; v[2] = x.z + v[2]; v[3] = x.w + v[3];
             }
             if (E.bn_alpha != nullptr) {
-              v[0] = fmaf(v[0], al4.x, be4.x); v[1] = fmaf(v[1], al4.y, be4.y);
-              v[2] = fmaf(v[2], al4.z, be4.z); v[3] = fmaf(v[3], al4.w, be4.w);
+              v[0] = fmaf(v[0], al4[hh].x, be4[hh].x); v[1] = fmaf(v[1], al4[hh].y, be4[hh].y);
+              v[2] = fmaf(v[2], al4[hh].z, be4[hh].z); v[3] = fmaf(v[3], al4[hh].w, be4[hh].w);
             }
             if (E.y32 != nullptr) *(float4*)(E.y32 + off) = make_float4(v[0], v[1], v[2], v[3]);
             if (E.yhi != nullptr) {
@@ -254,9 +330,6 @@ gemm_x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
           }
         }
       }
-      gt_fence_before();
-      __syncwarp();
-      if (lane == 0) gt_mbar_arrive(tempty0 + 8 * acc);
     }
   }
   gt_fence_before();
