@@ -1,7 +1,8 @@
 // K4: best-of-(A*G) selection (rl4cop/train_path_solver.py:290-306) and the path orientation /
 // global-id mapping of the hook (h_tsp.py:206-226); K5: closed tour length from coordinates
 // (rl_utils.py:87-102 over dist_matrix of h_tsp.py:449-453) without the Ntot x Ntot matrix.
-// All three are HBM/latency-bound index kernels: one CTA per subproblem / tour.
+// All three are HBM/latency-bound index kernels: one warp per subproblem (selection), one CTA per
+// subproblem (orientation) / tour (length).
 #include "common.cuh"
 
 namespace htsp {
@@ -9,37 +10,36 @@ namespace htsp {
 // reward [A*B, G] (instance a*B+b), pi [A*B, G, N] i32.  torch semantics: max over g inside each
 // augmentation block, then max over blocks, first maximum wins both times == the smallest
 // linear index a*G+g among the global maxima.
-__global__ void __launch_bounds__(128)
+// One WARP per subproblem (8 per CTA): every lane scans its share of the A*G rewards (coalesced, all loads
+// in flight), one shuffle reduction with the first-index rule, then the 32 lanes copy the winning tour.
+__global__ void __launch_bounds__(256)
 select_best_kernel(const float* __restrict__ reward, const int32_t* __restrict__ pi, int A, int B,
                    int G, int N, float* __restrict__ best_len, int32_t* __restrict__ best_row,
                    long long* __restrict__ best_pi) {
-  const int b = blockIdx.x, tid = threadIdx.x;
-  __shared__ float sv[4];
-  __shared__ int si[4];
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
   float best = -INFINITY;
   int bi = 0x7fffffff;
-  for (int idx = tid; idx < A * G; idx += blockDim.x) {
-    const int a = idx / G, g = idx % G;
-    const float r = __ldg(&reward[((size_t)a * B + b) * G + g]);
-    if (r > best || bi == 0x7fffffff) { best = r; bi = idx; }
+  for (int a = 0; a < A; ++a) {
+    const float* rp = reward + ((size_t)a * B + b) * G;
+#pragma unroll 4
+    for (int g = lane; g < G; g += 32) {
+      const float r = __ldg(&rp[g]);
+      if (r > best || bi == 0x7fffffff) { best = r; bi = a * G + g; }   // ascending index: first maximum stays
+    }
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
-    float ob = __shfl_xor_sync(0xffffffffu, best, off);
-    int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+    const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
     if (oi != 0x7fffffff && (bi == 0x7fffffff || ob > best || (ob == best && oi < bi))) { best = ob; bi = oi; }
   }
-  if ((tid & 31) == 0) { sv[tid >> 5] = best; si[tid >> 5] = bi; }
-  __syncthreads();
-  best = sv[0]; bi = si[0];
-  for (int w = 1; w < 4; ++w) {
-    const float ob = sv[w]; const int oi = si[w];
-    if (oi != 0x7fffffff && (bi == 0x7fffffff || ob > best || (ob == best && oi < bi))) { best = ob; bi = oi; }
-  }
-  const int a = bi / G, g = bi % G;
-  if (tid == 0) { best_len[b] = -best; best_row[b] = bi; }
+  const int a = bi / G, g = bi - a * G;
+  if (lane == 0) { best_len[b] = -best; best_row[b] = bi; }
   const int32_t* srcp = pi + (((size_t)a * B + b) * G + g) * N;
-  for (int i = tid; i < N; i += blockDim.x) best_pi[(size_t)b * N + i] = (long long)__ldg(&srcp[i]);
+#pragma unroll 4
+  for (int i = lane; i < N; i += 32) best_pi[(size_t)b * N + i] = (long long)__ldg(&srcp[i]);
 }
 
 // h_tsp.py:206-226.  status bits: 1 = local node 0 missing, 2 = path does not end at N-1 after
@@ -82,31 +82,53 @@ finalize_paths_kernel(const long long* __restrict__ best_pi, const long long* __
 }
 
 // closed tour length: sum_i fp32( |1000 x[t_i] - 1000 x[t_{i+1}]|_fp64 ), fp32 sum, / 1000.
-__global__ void __launch_bounds__(256)
+// One CTA of 1024 threads per tour: a thread gathers ONE coordinate per edge (the edge's other end comes from
+// the next lane by shuffle; lane 31 fetches it) and keeps four edges in flight.
+constexpr int kTourThreads = 1024;
+__global__ void __launch_bounds__(kTourThreads)
 tour_length_kernel(const float2* __restrict__ coords, const long long* __restrict__ tours,
                    const int32_t* __restrict__ tour_len, int Ntot, int Tmax,
                    float* __restrict__ out) {
-  const int e = blockIdx.x, tid = threadIdx.x;
+  const int e = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   const int T = tour_len[e];
   const float2* xy = coords + (size_t)e * Ntot;
   const long long* t = tours + (size_t)e * Tmax;
   float acc = 0.f;
-  for (int i = tid; i < T; i += blockDim.x) {
-    const long long a = __ldg(&t[i]), c = __ldg(&t[i + 1 == T ? 0 : i + 1]);
-    const float2 pa = __ldg(&xy[a]), pc = __ldg(&xy[c]);
-    const double dx = (double)pa.x * 1000.0 - (double)pc.x * 1000.0;
-    const double dy = (double)pa.y * 1000.0 - (double)pc.y * 1000.0;
-    acc += (float)sqrt(dx * dx + dy * dy);
+  for (int base = 0; base < T; base += 4 * kTourThreads) {
+    float2 pa[4], pn[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * kTourThreads + tid;
+      pa[u] = make_float2(0.f, 0.f);
+      if (i < T) pa[u] = __ldg(&xy[__ldg(&t[i])]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * kTourThreads + tid;
+      pn[u].x = __shfl_down_sync(0xffffffffu, pa[u].x, 1);
+      pn[u].y = __shfl_down_sync(0xffffffffu, pa[u].y, 1);
+      if (i < T && (lane == 31 || i + 1 == T)) pn[u] = __ldg(&xy[__ldg(&t[i + 1 == T ? 0 : i + 1])]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * kTourThreads + tid;
+      if (i < T) {
+        const double dx = (double)pa[u].x * 1000.0 - (double)pn[u].x * 1000.0;
+        const double dy = (double)pa[u].y * 1000.0 - (double)pn[u].y * 1000.0;
+        acc += (float)sqrt(dx * dx + dy * dy);
+      }
+    }
   }
-  __shared__ float red[8];
+  __shared__ float red[kTourThreads / 32];
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-  if ((tid & 31) == 0) red[tid >> 5] = acc;
+  if (lane == 0) red[tid >> 5] = acc;
   __syncthreads();
-  if (tid == 0) {
-    float s = 0.f;
-    for (int w = 0; w < 8; ++w) s += red[w];
-    out[e] = T > 0 ? s / 1000.0f : 0.f;
+  if (tid < 32) {
+    float s = red[tid];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (tid == 0) out[e] = T > 0 ? s / 1000.0f : 0.f;
   }
 }
 
@@ -120,7 +142,7 @@ extern "C" int htsp_select_best(const float* reward, const int32_t* pi, int n_au
   HTSP_REQUIRE(reward && pi && best_len && best_row && best_pi, "null pointer");
   HTSP_REQUIRE((n_aug == 1 || n_aug == 8) && B >= 0 && G >= 1 && N >= 1, "bad shape");
   if (B == 0) return HTSP_OK;
-  select_best_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(reward, pi, n_aug, B, G, N, best_len,
+  select_best_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(reward, pi, n_aug, B, G, N, best_len,
                                                           best_row, (long long*)best_pi);
   HTSP_CHECK_LAUNCH();
   return HTSP_OK;
@@ -146,7 +168,7 @@ extern "C" int htsp_tour_length(const float* coords, const int64_t* tours, const
   HTSP_REQUIRE(coords && tours && tour_len && out, "null pointer");
   HTSP_REQUIRE(E >= 0 && Ntot >= 1 && Tmax >= 1, "bad shape");
   if (E == 0) return HTSP_OK;
-  tour_length_kernel<<<E, 256, 0, (cudaStream_t)stream>>>((const float2*)coords,
+  tour_length_kernel<<<E, kTourThreads, 0, (cudaStream_t)stream>>>((const float2*)coords,
                                                           (const long long*)tours, tour_len, Ntot,
                                                           Tmax, out);
   HTSP_CHECK_LAUNCH();

@@ -112,7 +112,7 @@ def main():
     out.append({"kernel": "K5 tour_length (TSP-10000 tours)", "tours": Et, "seconds": t, "algorithmic_bytes": byt,
                 "roofline": {"bound": "hbm", "achieved": byt / t / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": byt / t / 1e9 / peak, "peak_source": src},
-                "note": "one CTA of 256 threads per tour; random 8-byte coordinate gathers"})
+                "note": "one CTA of 1024 threads per tour, four edges in flight per thread, the edge end from the next lane by shuffle; random 8-byte coordinate gathers"})
     for o in out:
         print(json.dumps(o))
 
