@@ -236,16 +236,6 @@ gemm_x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             if (row < E.M) res[hh][pp] = __ldg((const float4*)(E.residual + (size_t)row * E.Nout + col0 + hh * 16 + slot * 4));
           }
       }
-      float4 b4[2], al4[2], be4[2];
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        b4[hh] = make_float4(0.f, 0.f, 0.f, 0.f); al4[hh] = make_float4(1.f, 1.f, 1.f, 1.f); be4[hh] = b4[hh];
-        if (E.bias != nullptr) b4[hh] = __ldg((const float4*)(E.bias + col0 + hh * 16 + slot * 4));
-        if (E.bn_alpha != nullptr) {
-          al4[hh] = __ldg((const float4*)(E.bn_alpha + col0 + hh * 16 + slot * 4));
-          be4[hh] = __ldg((const float4*)(E.bn_beta + col0 + hh * 16 + slot * 4));
-        }
-      }
       gt_mbar_wait(tfull0 + 8 * acc, acc_use & 1);
       gt_fence_after();
       uint32_t r[32];
@@ -291,6 +281,12 @@ gemm_x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         // TMEM hands every lane one ROW; global memory wants lanes along the columns
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), al4 = make_float4(1.f, 1.f, 1.f, 1.f), be4 = b4;
+        if (E.bias != nullptr) b4 = __ldg((const float4*)(E.bias + col0 + hh * 16 + slot * 4));
+        if (E.bn_alpha != nullptr) {
+          al4 = __ldg((const float4*)(E.bn_alpha + col0 + hh * 16 + slot * 4));
+          be4 = __ldg((const float4*)(E.bn_beta + col0 + hh * 16 + slot * 4));
+        }
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -305,7 +301,7 @@ gemm_x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
           float v[4] = {t4.x, t4.y, t4.z, t4.w};
           if (row < E.M) {
             const size_t off = (size_t)row * E.Nout + col0 + hh * 16 + slot * 4;
-            v[0] += b4[hh].x; v[1] += b4[hh].y; v[2] += b4[hh].z; v[3] += b4[hh].w;
+            v[0] += b4.x; v[1] += b4.y; v[2] += b4.z; v[3] += b4.w;
             if (E.relu) {
 #pragma unroll
               for (int t = 0; t < 4; ++t) v[t] = fmaxf(v[t], 0.f);
@@ -315,8 +311,8 @@ gemm_x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
               v[0] = x.x + v[0]; v[1] = x.y + v[1]; v[2] = x.z + v[2]; v[3] = x.w + v[3];
             }
             if (E.bn_alpha != nullptr) {
-              v[0] = fmaf(v[0], al4[hh].x, be4[hh].x); v[1] = fmaf(v[1], al4[hh].y, be4[hh].y);
-              v[2] = fmaf(v[2], al4[hh].z, be4[hh].z); v[3] = fmaf(v[3], al4[hh].w, be4[hh].w);
+              v[0] = fmaf(v[0], al4.x, be4.x); v[1] = fmaf(v[1], al4.y, be4.y);
+              v[2] = fmaf(v[2], al4.z, be4.z); v[3] = fmaf(v[3], al4.w, be4.w);
             }
             if (E.y32 != nullptr) *(float4*)(E.y32 + off) = make_float4(v[0], v[1], v[2], v[3]);
             if (E.yhi != nullptr) {
