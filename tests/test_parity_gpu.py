@@ -440,6 +440,21 @@ def test_select_best_first_max_semantics(solvers):
     assert torch.equal(-got_len.cpu(), want_r) and torch.equal(got_pi.cpu(), want_pi.reshape(A * B, N))
 
 
+def test_select_best_ragged_batch_full_size(solvers):
+    """Warp-per-subproblem selection at N = G = 200 with a batch that is not a multiple of the 8 warps of a CTA,
+    rewards drawn from a few values so that the first-max rule decides most subproblems."""
+    s = solvers["fp32"]
+    A, B, G, N = 8, 19, 200, 200
+    g = torch.Generator().manual_seed(5)
+    reward = -torch.randint(3, 9, (A * B, G), generator=g).float() / 8
+    pi = torch.argsort(torch.rand(A * B, G, N, generator=g), dim=-1).int()
+    for n_aug, vt in ((8, "x8Aug_2Traj"), (1, "noAug_nTraj")):
+        want_r, want_pi = po.select_best(reward, pi.long(), vt)
+        got_len, got_pi, _ = s.select_best(reward.cuda(), pi.cuda(), n_aug)
+        rows = B if n_aug == 8 else A * B
+        assert torch.equal(-got_len.cpu(), want_r) and torch.equal(got_pi.cpu(), want_pi.reshape(rows, N))
+
+
 def test_finalize_paths_orientation_and_status(built_lib):
     from htsp_b200 import _abi
     lib = _abi.lib()
@@ -484,6 +499,25 @@ def test_tour_length_matches_golden_and_oracle(built_lib, golden):
     want = float((a - b).norm(dim=1).float().sum() / 1000)
     got = tour_length(big.cuda(), t.tolist())
     assert abs(got - want) <= 1e-5 * want
+
+
+def test_tour_length_ragged_lengths(built_lib):
+    """Tour lengths around the warp / CTA / unroll boundaries of the kernel (the edge end comes from the next lane
+    by shuffle, lane 31 and the closing edge fetch it), several tours of different lengths in one launch."""
+    from htsp_b200.scoring import tour_lengths
+    g = torch.Generator().manual_seed(3)
+    Ntot = 5000
+    lens = [1, 2, 3, 31, 32, 33, 1023, 1024, 1025, 4095, 4096, 4097, 5000]
+    xs = torch.rand(len(lens), Ntot, 2, generator=g)
+    tours = torch.zeros(len(lens), Ntot, dtype=torch.long)
+    want = []
+    for e, T_ in enumerate(lens):
+        t = torch.randperm(Ntot, generator=g)[:T_]
+        tours[e, :T_] = t
+        a, b = xs[e][t].double() * 1000, xs[e][t.roll(-1)].double() * 1000
+        want.append(float((a - b).norm(dim=1).float().sum() / 1000))
+    got = tour_lengths(xs.cuda(), tours.cuda(), torch.tensor(lens, dtype=torch.int32).cuda()).cpu().numpy()
+    np.testing.assert_allclose(got, np.array(want, dtype=np.float32), rtol=1e-5, atol=1e-7)
 
 
 # ---------------------------------------------------------------- size-independent properties
