@@ -13,8 +13,9 @@
 //              (32 lanes x 32 columns), transpose through shared memory (two 16-column halves, XOR-swizzled
 //              16-byte slots, st/ld.shared.v4) so that global loads / stores run along the rows,
 //              bias / ReLU / residual / eval-BatchNorm affine in registers, stores fp32 and/or the fp16
-//              hi/lo split that the next layer's TMA reads; overlaps with the next tile's MMAs through the
-//              second accumulator.
+//              hi/lo split that the next layer's TMA reads; launches that only emit the fp16 split (QKV, FF1)
+//              write each 32 x 32 box of halves into a SWIZZLE_64B tile and hand it to a TMA store;
+//              overlaps with the next tile's MMAs through the second accumulator.
 // Synchronisation is mbarrier-only (full/empty per stage, tmem_full/tmem_empty per accumulator);
 // tcgen05.commit releases shared-memory stages and publishes accumulators.
 #include <cuda.h>
@@ -30,7 +31,7 @@ constexpr int GT_EPI_WARPS = 16;
 constexpr int GT_THREADS = 64 + 32 * GT_EPI_WARPS;          // TMA producer, MMA issuer, 16 epilogue warps
 constexpr uint32_t GT_TMEM_COLS = 256;
 constexpr int GT_EPI_BYTES = GT_EPI_WARPS * 32 * 16 * 4;    // one 32 x 16 fp32 transpose tile per epilogue warp
-constexpr size_t GT_SMEM_BYTES = (size_t)GT_STAGES * GT_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + GT_EPI_BYTES;
+constexpr size_t GT_SMEM_BYTES = (size_t)GT_STAGES * GT_STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/ + GT_EPI_BYTES;
 
 struct GemmEpi {
   const float* bias;       // [Nout] or null
@@ -123,16 +124,27 @@ __device__ __forceinline__ float4 gt_lds128(uint32_t addr) {
   return v;
 }
 
+// TMA store of one 32-row x 32-column fp16 box (64-byte rows, SWIZZLE_64B) from shared memory
+__device__ __forceinline__ void gt_tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// every earlier bulk store of this thread has finished READING its shared-memory source
+__device__ __forceinline__ void gt_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                  const __grid_constant__ CUtensorMap tmY_hi, const __grid_constant__ CUtensorMap tmY_lo,
                   const GemmEpi E) {
   extern __shared__ unsigned char gt_smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   unsigned char* smem = (unsigned char*)(((uintptr_t)gt_smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + (size_t)GT_STAGES * GT_STAGE_BYTES);
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * GT_STAGES + 4);
-  float* epi_smem = (float*)(smem + (size_t)GT_STAGES * GT_STAGE_BYTES + 256);
+  float* epi_smem = (float*)(smem + (size_t)GT_STAGES * GT_STAGE_BYTES + 512);   // 512-byte aligned: SWIZZLE_64B atoms
   const uint32_t full0 = gt_smem_u32(bars), empty0 = gt_smem_u32(bars + GT_STAGES);
   const uint32_t tfull0 = gt_smem_u32(bars + 2 * GT_STAGES), tempty0 = gt_smem_u32(bars + 2 * GT_STAGES + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -245,9 +257,7 @@ gemm_x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       __syncwarp();
       if (lane == 0) gt_mbar_arrive(tempty0 + 8 * acc);
       if (packed) {
-        // fp16 hi/lo outputs only (QKV, FF1): bias / ReLU / split in the row-owner lane, then the packed
-        // halves are transposed (64-byte rows) so that every lane stores 16 bytes = 8 columns and a row's
-        // 64 bytes leave together
+        // fp16 hi/lo outputs only (QKV, FF1): bias / ReLU / split in the row-owner lane (TMEM lane = output row)
         uint32_t hl[2][16];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -259,22 +269,20 @@ gemm_x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
           split2p(v0, v1, hl[0][2 * k], hl[1][2 * k]);
           split2p(v2, v3, hl[0][2 * k + 1], hl[1][2 * k + 1]);
         }
+        // the row-owner lane writes its 64-byte row of halves into the SWIZZLE_64B box (16-byte chunk j at
+        // j ^ ((row >> 1) & 3): conflict-free), one TMA store per part moves the 32 x 32 box out -- rows past M
+        // are clipped by the tensor map
 #pragma unroll
         for (int part = 0; part < 2; ++part) {
-          __half* dst = part ? E.ylo : E.yhi;
+          if (lane == 0) gt_bulk_wait_read();       // the previous store out of this buffer has read it
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             gt_sts128(wr_row + (((uint32_t)j ^ wr_x) << 4), hl[part][4 * j], hl[part][4 * j + 1], hl[part][4 * j + 2],
                       hl[part][4 * j + 3]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
-#pragma unroll
-          for (int pp = 0; pp < 4; ++pp) {
-            const int rl = pp * 8 + rsub;
-            const int row = rowb + rl;
-            const float4 t4 = gt_lds128(tr + (uint32_t)rl * 64 + ((((uint32_t)slot) ^ (((uint32_t)rl >> 1) & 3)) << 4));
-            if (row < E.M) *(float4*)(dst + (size_t)row * E.Nout + col0 + slot * 8) = t4;
-          }
+          if (lane == 0) gt_tma_store_2d(part ? &tmY_lo : &tmY_hi, tr, col0, rowb);
         }
         continue;
       }
@@ -328,6 +336,7 @@ gemm_x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       }
     }
   }
+  if (warp >= 2 && lane == 0) gt_bulk_wait_read();     // no bulk store may still read this CTA's shared memory
   gt_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -401,6 +410,27 @@ static int make_map(CUtensorMap* m, const __half* ptr, int rows, int K) {
   return HTSP_OK;
 }
 
+// row-major fp16 output [rows, cols] -> boxes of 32 rows x 32 halves (64 B), SWIZZLE_64B (epilogue TMA stores)
+static int make_out_map(CUtensorMap* m, const __half* ptr, int rows, int cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return HTSP_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)ptr, gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (output) failed (%d) rows=%d cols=%d", (int)r, rows, cols);
+    return HTSP_ERR_CUDA;
+  }
+  return HTSP_OK;
+}
+
 int launch_linear_tc(const __half* xhi, const __half* xlo, const __half* whi, const __half* wlo,
                      const float* bias, const float* residual, const float* bn_alpha,
                      const float* bn_beta, bool relu, float* y32, __half* yhi, __half* ylo, int M,
@@ -413,6 +443,12 @@ int launch_linear_tc(const __half* xhi, const __half* xlo, const __half* whi, co
   if ((rc = make_map(&ma_lo, xlo, M, K))) return rc;
   if ((rc = make_map(&mb_hi, whi, Nout, K))) return rc;
   if ((rc = make_map(&mb_lo, wlo, Nout, K))) return rc;
+  // the packed (fp16 hi/lo only) epilogue stores through TMA; other launches never touch these maps
+  CUtensorMap my_hi = ma_hi, my_lo = ma_lo;
+  if (yhi != nullptr && y32 == nullptr && residual == nullptr && bn_alpha == nullptr) {
+    if ((rc = make_out_map(&my_hi, yhi, M, Nout))) return rc;
+    if ((rc = make_out_map(&my_lo, ylo, M, Nout))) return rc;
+  }
   GemmEpi e;
   e.bias = bias; e.residual = residual; e.bn_alpha = bn_alpha; e.bn_beta = bn_beta;
   e.y32 = y32; e.yhi = yhi; e.ylo = ylo; e.M = M; e.Nout = Nout; e.K = K; e.relu = relu ? 1 : 0;
@@ -420,7 +456,7 @@ int launch_linear_tc(const __half* xhi, const __half* xlo, const __half* whi, co
                                        (int)GT_SMEM_BYTES));
   const int tiles = ((M + GT_BM - 1) / GT_BM) * (Nout / GT_BN);
   const int grid = tiles < 148 ? tiles : 148;
-  gemm_x3_tc_kernel<<<grid, GT_THREADS, GT_SMEM_BYTES, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, e);
+  gemm_x3_tc_kernel<<<grid, GT_THREADS, GT_SMEM_BYTES, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, my_hi, my_lo, e);
   HTSP_CHECK_LAUNCH();
   return HTSP_OK;
 }

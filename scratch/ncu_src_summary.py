@@ -3,7 +3,7 @@ path = sys.argv[1]
 rows = list(csv.reader(open(path)))
 hdr = rows[1]
 I = {h:i for i,h in enumerate(hdr)}
-data = rows[2:]
+data = [r for r in rows[2:] if len(r) >= len(hdr)]
 def num(x):
     try: return float(x.replace(',',''))
     except: return 0.0
