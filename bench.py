@@ -304,7 +304,9 @@ def run_b200(args):
     lib = _abi.lib()
     N, G, L, B = args.nodes, args.group, args.layers, args.batch
     model = B200PathSolver(state_dict=synthetic_state_dict(1234, L), mode=args.mode, device=dev)
-    model.first_action_override = torch.randperm(N, generator=torch.Generator().manual_seed(7))[:G]
+    # on the device: a host tensor here would be copied (and the stream synchronised) inside every step, which puts
+    # the launching thread in lock-step with the GPU and turns any host hiccup into GPU idle time
+    model.first_action_override = torch.randperm(N, generator=torch.Generator().manual_seed(7))[:G].to(dev)
     src = torch.zeros(B, 1, dtype=torch.long, device=dev)
     tgt = torch.full((B, 1), N - 1, dtype=torch.long, device=dev)
     n_in = min(args.warmup + args.steps, 4)
@@ -345,10 +347,16 @@ def run_b200(args):
     launches0 = lib.htsp_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    marks, host_ms = [], []
     for i in range(args.steps):
+        t_h = time.perf_counter()
         length, pi = step(args.warmup + i, timers[i])
+        marks.append(torch.cuda.Event(enable_timing=True))
+        marks[-1].record()
+        host_ms.append(round((time.perf_counter() - t_h) * 1e3, 3))
     e1.record()
     barrier()
+    step_ms = [round(a.elapsed_time(b), 3) for a, b in zip([e0] + marks[:-1], marks)]   # diagnostic: one entry per step
     clocks = sampler.stop() if rank == 0 else None
     launches = lib.htsp_launch_count() - launches0
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -436,6 +444,8 @@ def run_b200(args):
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "B200PathSolver.forward(host pinned batch) -> host tours"},
             "gpu_launches": int(nl),
+            "ms_steps": step_ms,
+            "host_enqueue_ms_steps": host_ms,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "rollout (decode) kernel",
                          "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",

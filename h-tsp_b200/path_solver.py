@@ -237,6 +237,10 @@ class B200PathSolver(torch.nn.Module):
         if self.first_action_override is not None:
             fa = self.first_action_override.reshape(-1)
             assert fa.numel() == G
+            if fa.device != torch.device(self.device):
+                # copied once: a host tensor would be copied, and the stream synchronised, in every call
+                fa = fa.to(self.device)
+                self.first_action_override = fa
             return fa
         return torch.randperm(N, device=self.device)[:G]
 
