@@ -230,6 +230,8 @@ gemm_x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     const uint32_t wr_row = tr + (uint32_t)lane * 64, wr_x = (uint32_t)(lane >> 1) & 3;
     const int rsub = lane >> 2, slot = lane & 3;             // read phase: 8 rows x 4 slots per pass
     const bool packed = E.y32 == nullptr && E.residual == nullptr && E.bn_alpha == nullptr && E.yhi != nullptr;
+    const bool raw32 = E.y32 != nullptr && E.yhi == nullptr && E.residual == nullptr && E.bn_alpha == nullptr &&
+                       E.bias == nullptr && !E.relu;
     uint32_t local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
@@ -283,6 +285,23 @@ gemm_x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) gt_tma_store_2d(part ? &tmY_lo : &tmY_hi, tr, col0, rowb);
+        }
+        continue;
+      }
+      if (raw32) {
+        // fp32 output without an epilogue (the decoder projection tables): the row-owner lane writes its 16
+        // columns of a half chunk (64 bytes) into the SWIZZLE_64B box, one TMA store per half
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          if (lane == 0) gt_bulk_wait_read();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            gt_sts128(wr_row + (((uint32_t)j ^ wr_x) << 4), r[hh * 16 + 4 * j], r[hh * 16 + 4 * j + 1],
+                      r[hh * 16 + 4 * j + 2], r[hh * 16 + 4 * j + 3]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) gt_tma_store_2d(&tmY_hi, tr, col0 + hh * 16, rowb);
         }
         continue;
       }
@@ -431,6 +450,27 @@ static int make_out_map(CUtensorMap* m, const __half* ptr, int rows, int cols) {
   return HTSP_OK;
 }
 
+// row-major fp32 output [rows, cols] -> boxes of 32 rows x 16 floats (64 B), SWIZZLE_64B
+static int make_out_map_f32(CUtensorMap* m, const float* ptr, int rows, int cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return HTSP_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)cols * 4};
+  cuuint32_t box[2] = {16, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (fp32 output) failed (%d) rows=%d cols=%d", (int)r, rows, cols);
+    return HTSP_ERR_CUDA;
+  }
+  return HTSP_OK;
+}
+
 int launch_linear_tc(const __half* xhi, const __half* xlo, const __half* whi, const __half* wlo,
                      const float* bias, const float* residual, const float* bn_alpha,
                      const float* bn_beta, bool relu, float* y32, __half* yhi, __half* ylo, int M,
@@ -448,6 +488,8 @@ int launch_linear_tc(const __half* xhi, const __half* xlo, const __half* whi, co
   if (yhi != nullptr && y32 == nullptr && residual == nullptr && bn_alpha == nullptr) {
     if ((rc = make_out_map(&my_hi, yhi, M, Nout))) return rc;
     if ((rc = make_out_map(&my_lo, ylo, M, Nout))) return rc;
+  } else if (y32 != nullptr && yhi == nullptr && residual == nullptr && bn_alpha == nullptr && bias == nullptr && !relu) {
+    if ((rc = make_out_map_f32(&my_hi, y32, M, Nout))) return rc;     // epilogue-free fp32 output: TMA stores too
   }
   GemmEpi e;
   e.bias = bias; e.residual = residual; e.bn_alpha = bn_alpha; e.bn_beta = bn_beta;
