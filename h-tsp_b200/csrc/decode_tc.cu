@@ -500,6 +500,10 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
     if (lane == 0) {
       const size_t szk = tcd_szk(NP), szvh = tcd_szvh(NP), pair = tcd_pair_bytes(NP);
       const int per_step = 24;                             // ring stages one tile consumes per decode step
+      // back-off of the polling lane when no stage is free: a long sleep leaves scheduler 0's issue slots to its
+      // softmax warps (+0.9 % at N = 200), but it must stay well below the time one stage lasts (1.7 us at N = 200,
+      // 0.9 us at N = 100: 512 ns cost 4 % there, 1024 ns cost 4 % at N = 200)
+      const unsigned poll_ns = NP >= 144 ? 512u : 64u;
       const uint32_t total = (uint32_t)n_steps * (uint32_t)per_step;
       uint32_t it[2] = {0, 0};
       int rem = n_tiles;
@@ -533,7 +537,7 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
         }
         if (pushed) idle = 0;
         else if (++idle > (1u << 28)) __trap();
-        else __nanosleep(64);
+        else __nanosleep(poll_ns);
       }
     }
   };
