@@ -269,7 +269,7 @@ __device__ __forceinline__ float tcd_gumbel(uint32_t bits) {
 // PSINGLE (HTSP_MODE_TC_FAST): the softmax probabilities are stored as one fp16 (no lo part), the row
 // sum is taken from the ROUNDED values so that the normalisation stays consistent; S, V and the pointer
 // logits keep the full split.  Logit error ~2.5e-4 (bound 1e-3) instead of ~3e-5.
-template <bool LOGITS, bool DEBUG, bool PSINGLE, bool SPLIT, bool SAMPLE>
+template <bool LOGITS, bool DEBUG, bool PSINGLE, bool SPLIT, bool SAMPLE, bool P15 = false>
 __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs A) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31;
@@ -339,6 +339,13 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
   // instance has no rows in lane quarter 3, so its softmax warp 19 is free to be tile 1's issuer
   // (when tile 1 does use that quarter, warp 2 issues instead).
   const int iss1_warp = (G - 128 > 96) ? 2 : 19;
+  // The operand producer polls two rings; on scheduler 0 its polling competes with four softmax warps.  P15 (chosen
+  // by the host for two row tiles of long rows, NP >= 144, with tile 1 leaving lane quarter 3 free): warp 15 (tile 1,
+  // primary, quarter 3) has no rows and takes the role on scheduler 3 instead (+0.9 % at N = G = 200, +2.7 % at 150).
+  // Short problems (one stage lasts < 1 us) and single-tile launches lose 5 % that way (the issuer shares that
+  // scheduler); it is a template parameter so that their kernels stay exactly as they were (the same code with a
+  // run-time choice cost them 1.9 %).
+  constexpr int prod_warp = P15 ? 15 : 0;
   auto run_issuer = [&](const int t) {
     // The issuers sit on scheduler 3 (warp % 4 == 3), the least loaded one: row tile 1 of a 200-row
     // instance has no rows in lane quarter 3, so its softmax warp 19 is free to be tile 1's issuer
@@ -503,7 +510,7 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
       // back-off of the polling lane when no stage is free: a long sleep leaves scheduler 0's issue slots to its
       // softmax warps (+0.9 % at N = 200), but it must stay well below the time one stage lasts (1.7 us at N = 200,
       // 0.9 us at N = 100: 512 ns cost 4 % there, 1024 ns cost 4 % at N = 200)
-      const unsigned poll_ns = NP >= 144 ? 512u : 64u;
+      const unsigned poll_ns = (prod_warp == 0 && NP >= 144) ? 512u : 64u;     // on scheduler 3 a short back-off is free
       const uint32_t total = (uint32_t)n_steps * (uint32_t)per_step;
       uint32_t it[2] = {0, 0};
       int rem = n_tiles;
@@ -992,12 +999,13 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
   // role dispatch is repeated inside each branch so that ptxas sees one register budget per path
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
-    if (warp == 0) run_producer();
+    if (!P15 && warp == 0) run_producer();
     else if (warp == 3) run_issuer(0);
     else if (warp == 2 && iss1_warp == 2) run_issuer(1);
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
     if (warp == 19 && iss1_warp == 19) run_issuer(1);
+    else if (P15 && warp == 15) run_producer();
     else run_softmax();
   }
 
@@ -1050,7 +1058,7 @@ static void tcd_choose_split(int Bp, int G, bool debug, int& split, int& rows_pe
   }
 }
 
-template <bool LOGITS, bool DEBUG, bool PSINGLE, bool SPLIT, bool SAMPLE = false>
+template <bool LOGITS, bool DEBUG, bool PSINGLE, bool SPLIT, bool SAMPLE = false, bool P15 = false>
 static int launch_tcd(const TcdArgs& a, int Bp, cudaStream_t s) {
   const size_t smem = (size_t)2 * TCD_TILE_STAGING + (size_t)2 * TCD_STAGES * TCD_STAGE +
                       (size_t)a.NP * 4 + 2 * TB_PER_TILE * 8 + 16;   // 224 KB + c0 + barriers
@@ -1058,10 +1066,10 @@ static int launch_tcd(const TcdArgs& a, int Bp, cudaStream_t s) {
     set_error("decode_tc: N=%d needs %zu bytes of shared memory", a.N, smem);
     return HTSP_ERR_UNSUPPORTED;
   }
-  HTSP_CHECK_CUDA(cudaFuncSetAttribute(decode_tc_kernel<LOGITS, DEBUG, PSINGLE, SPLIT, SAMPLE>,
+  HTSP_CHECK_CUDA(cudaFuncSetAttribute(decode_tc_kernel<LOGITS, DEBUG, PSINGLE, SPLIT, SAMPLE, P15>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kernel_timer_begin(s);
-  decode_tc_kernel<LOGITS, DEBUG, PSINGLE, SPLIT, SAMPLE><<<SPLIT ? Bp * ((a.G + a.dbg_step - 1) / a.dbg_step) : Bp, TCD_THREADS, smem, s>>>(a);
+  decode_tc_kernel<LOGITS, DEBUG, PSINGLE, SPLIT, SAMPLE, P15><<<SPLIT ? Bp * ((a.G + a.dbg_step - 1) / a.dbg_step) : Bp, TCD_THREADS, smem, s>>>(a);
   kernel_timer_end(s);
   HTSP_CHECK_LAUNCH();
   return HTSP_OK;
@@ -1101,6 +1109,10 @@ int launch_decode_tc(const float* x, const float* proj, const float* qfix, const
     if (a.fast) return split ? launch_tcd<true, false, true, true>(a, Bp, s) : launch_tcd<true, false, true, false>(a, Bp, s);
     return split ? launch_tcd<true, false, false, true>(a, Bp, s) : launch_tcd<true, false, false, false>(a, Bp, s);
   }
+  // producer on warp 15 (see prod_warp in the kernel): unsplit greedy launches with two row tiles, tile 1 without
+  // rows in lane quarter 3, long rows
+  const bool p15 = !split && G > 128 && G - 128 <= 96 && NP >= 144;
+  if (p15) return a.fast ? launch_tcd<false, false, true, false, false, true>(a, Bp, s) : launch_tcd<false, false, false, false, false, true>(a, Bp, s);
   if (a.fast) return split ? launch_tcd<false, false, true, true>(a, Bp, s) : launch_tcd<false, false, true, false>(a, Bp, s);
   return split ? launch_tcd<false, false, false, true>(a, Bp, s) : launch_tcd<false, false, false, false>(a, Bp, s);
 }
