@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libhtsp_b200.so")
+# HTSP_LIB_PATH: another build of the same library (tools/ab_rollout.py compares two builds); never a fallback
+LIB_PATH = os.environ.get("HTSP_LIB_PATH") or os.path.join(_PKG_DIR, "libhtsp_b200.so")
 
 MODE_FP32, MODE_TC_X3, MODE_TC_FAST = 0, 1, 2
 MODES = {"fp32": MODE_FP32, "x3": MODE_TC_X3, "fast": MODE_TC_FAST}

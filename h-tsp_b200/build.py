@@ -42,17 +42,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if (not force and os.path.isfile(LIB_PATH) and os.path.isfile(STAMP)
             and open(STAMP).read().strip() == dig):
         return LIB_PATH
-    objs = []
     flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
-    for src in SOURCES:
+    os.makedirs(os.path.join(PKG_DIR, "build"), exist_ok=True)
+
+    def compile_one(src: str) -> str:
         obj = os.path.join(PKG_DIR, "build", src.replace(".cu", ".o"))
-        os.makedirs(os.path.dirname(obj), exist_ok=True)
         cmd = [_nvcc(), *flags, "-Xptxas", "-v" if verbose else "-warn-spills",
                "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
         subprocess.run(cmd, check=True)
-        objs.append(obj)
+        return obj
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:   # one nvcc per translation unit
+        objs = list(pool.map(compile_one, SOURCES))
     cmd = [_nvcc(), "-shared", *flags, "-o", LIB_PATH, *objs]
     subprocess.run(cmd, check=True)
     with open(STAMP, "w") as f:
