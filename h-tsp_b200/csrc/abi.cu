@@ -155,6 +155,7 @@ static size_t dec_c0_bytes(int Bp, int N) { return align_up((size_t)Bp * N * 4, 
 static size_t dec_pack_bytes(int Bp, int N, int G) {
   size_t a = decode_mma_pack_bytes(Bp, N);
   if (decode_tc_supported(N, G)) a = std::max(a, decode_tc_pack_bytes(Bp, N));
+  if (decode_tc2_supported(N, G)) a = std::max(a, decode_tc2_pack_bytes(Bp, N));
   return a;
 }
 // HTSP_DECODE_IMPL=mma forces the mma.sync rollout kernel (A/B comparisons); default is tcgen05 when it fits
@@ -162,6 +163,13 @@ static bool use_tc_kernel(int N, int G) {
   const char* e = getenv("HTSP_DECODE_IMPL");
   if (e != nullptr && strcmp(e, "mma") == 0) return false;
   return decode_tc_supported(N, G);
+}
+// HTSP_MODE_TC_FAST runs on the second tcgen05 kernel (decode_tc2.cu) when the shape fits; HTSP_DECODE_IMPL=tc1
+// keeps the first kernel's single-fp16 variant (A/B comparisons)
+static bool use_tc2_kernel(int N, int G, int mode) {
+  const char* e = getenv("HTSP_DECODE_IMPL");
+  if (e != nullptr && (strcmp(e, "mma") == 0 || strcmp(e, "tc1") == 0)) return false;
+  return mode == HTSP_MODE_TC_FAST && decode_tc2_supported(N, G);
 }
 
 extern "C" size_t htsp_decode_workspace_bytes(int Bp, int N, int G, int mode) {
@@ -205,6 +213,9 @@ static int decode_impl(const void* blob, int n_layers, const float* x, const flo
   if (mode == HTSP_MODE_FP32)
     return launch_decode_f32((const float*)blob, n_layers, x, emb, proj, qfix, src, tgt, first, Bp,
                              N, G, forced_pi, pi, reward, logits_out, s);
+  if (use_tc2_kernel(N, G, mode))
+    return launch_decode_tc2(x, proj, qfix, c0, src, tgt, first, Bp, N, G, forced_pi, pi, reward, logits_out, pack_ws,
+                             dbg, dbg_step, sample_seed, s);
   if (use_tc_kernel(N, G))
     return launch_decode_tc(x, proj, qfix, c0, src, tgt, first, Bp, N, G, mode, forced_pi, pi, reward,
                             logits_out, pack_ws, dbg, dbg_step, sample_seed, s);
@@ -230,7 +241,7 @@ extern "C" int htsp_decode_sample(const void* blob, int n_layers, const float* x
                      workspace, workspace_bytes, nullptr, 0, stream, &seed);
 }
 
-extern "C" size_t htsp_decode_debug_floats(int N) { return decode_tc_dbg_floats(N); }
+extern "C" size_t htsp_decode_debug_floats(int N) { return std::max(decode_tc_dbg_floats(N), decode_tc2_dbg_floats(N)); }
 extern "C" int htsp_decode_debug(const void* blob, int n_layers, const float* x, const float* emb,
                                  const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp,
                                  int N, int G, int mode, const int32_t* forced_pi, int32_t* pi,

@@ -170,4 +170,14 @@ int launch_decode_tc(const float* x, const float* proj, const float* qfix, const
                      float* logits_out, void* pack_ws, float* dbg, int dbg_step, const uint64_t* sample_seed,
                      cudaStream_t s);
 
+// decode_tc2.cu (second tcgen05 rollout kernel: tf32 probabilities in place, three softmax warps per row quarter)
+bool decode_tc2_supported(int N, int G);
+size_t decode_tc2_pack_bytes(int Bp, int N);
+size_t decode_tc2_dbg_floats(int N);
+int launch_decode_tc2(const float* x, const float* proj, const float* qfix, const float* c0,
+                      const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp, int N,
+                      int G, const int32_t* forced_pi, int32_t* pi, float* reward,
+                      float* logits_out, void* pack_ws, float* dbg, int dbg_step, const uint64_t* sample_seed,
+                      cudaStream_t s);
+
 }  // namespace htsp

@@ -1,0 +1,851 @@
+// K3, second tcgen05 rollout kernel (HTSP_MODE_TC_FAST, 33 <= N <= 208): the glimpse probabilities stay in TMEM as the
+// fp32 words they were computed in and feed a kind::tf32 MMA in place, and every row quarter is served by THREE
+// softmax warps.
+//
+// Why (measured, tools/lab_tc.cu, tools/ab_rollout.py --g 32 ... 200): the first kernel
+// (decode_tc.cu) is bound by the serial chain of one row quarter -- a launch with 32 POMO rows per instance takes
+// 76 % of the time of one with 200 -- not by any pipe: S MMA -> 6-7 chunks of softmax in one warp -> drain -> P V
+// -> S ... for eight heads, then logits -> arg-max -> gather.  Splitting the keys of a row over more warps
+// shortens that chain, but split-fp16 probabilities need a per-warp shift (p must fit fp16) and therefore one
+// accumulator per key part, and TMEM is full (2 x 208 score columns).  With P = 2^s kept as fp32 there is no
+// shift (the exponent range is that of fp32; keys are centred per head so that scores sit around zero), all key
+// parts of a tile accumulate into ONE accumulator, and the softmax inner loop is mask + ex2 + store.
+//
+// Per step and head h, row tile t (128 rows), key part j (3 parts of 48-80 keys):
+//   S_h^j  = Q_h K_h[j]^T          tcgen05.mma kind::f16, split-fp16 (3 MMAs), K block K-major SWIZZLE_64B
+//   P_h^j  = 2^(S_h^j) masked      softmax warp (t, j, lane quarter): tcgen05.ld -> ex2 -> tcgen05.st in place;
+//                                  row sum of the truncated values (what the tensor core will read) in registers
+//   O_h   += P_h^j [Vhi | Vlo]     tcgen05.mma kind::tf32, A = P in TMEM, B = V^T tf32 hi/lo stacked (N = 32)
+//   O_h / sum_j l_j -> fp16 hi/lo into the shared-memory A tile (part-0 warps, before they publish P_{h+1})
+// and once per step U = O K2^T (split-fp16), arg-max of 10 tanh((U + c0)/sqrt(128)) over the unvisited keys by the
+// three warps of a row quarter, state update, query gather (PathDecoder.forward, rl4cop/models/models.py:404-446;
+// GroupState / Env, rl4cop/train_path_solver.py:45-149, 256-288).
+//
+// Warps (896 threads): 0, 1 = MMA issuers of row tiles 0, 1 (parts served in the fixed order 0, 1, 2); 2 = operand
+// producer (ONE ring of 8 x 12 KB for both tiles: every K / V / K2 block is fetched once per CTA and step, released
+// by both issuers); 3 = TMEM allocation; 4-27 = softmax warps (tile, part, lane quarter = warp % 4).
+// Precision: logits within 1e-3 of the fp32 reference (P carries 10 mantissa bits, as a single fp16 would; V, Q, K,
+// K2 and O keep their hi/lo splits); a row whose softmax sum leaves the fp32 range returns a NaN reward.
+#include <stdlib.h>
+#include <string.h>
+#include "common.cuh"
+#include "mma_util.cuh"
+#include "tc_util.cuh"
+#include "tc_rollout_util.cuh"
+
+namespace htsp {
+
+constexpr int T2_THREADS = 896;
+constexpr int T2_PARTS = 3;
+constexpr int T2_SLOTS = 8;
+constexpr int T2_SLOT = 12288;            // ring slot: one K_h^j (<= 5 KB), V_h^j (<= 12 KB) or K2_i^j (<= 10 KB) block
+constexpr int T2_TILE_STAGING = 65536;    // per row tile: [hi k0-63 | hi k64-127 | lo k0-63 | lo k64-127], 16 KB each
+constexpr int T2_OCOL = 416;              // O accumulator of tile t: columns 416 + 32 t .. + 31 ([P Vhi | P Vlo])
+constexpr int T2_XCOL = 480;              // exchange columns of tile t: 480 + 16 t: l[head & 1][part] (6), candidates (4), chosen (1)
+constexpr float kT2InvSqrtH = 0.08838834764831845f;   // 1/sqrt(128)
+
+// key parts in 16-key chunks: part 0 (whose warps also drain O) is the shortest
+struct T2Parts {
+  int cb[T2_PARTS + 1];
+};
+__host__ __device__ inline T2Parts t2_parts(int NP) {
+  const int nch = NP >> 4;
+  T2Parts p;
+  int c1 = (3 * nch + 6) / 13;
+  if (c1 < 1) c1 = 1;
+  p.cb[0] = 0;
+  p.cb[1] = c1;
+  p.cb[2] = c1 + (nch - c1) / 2;
+  p.cb[3] = nch;
+  return p;
+}
+// ---- per-instance operand image (bytes) ----------------------------------------------------------
+//   K  : 8 heads x [NP keys x 64 B]   K-major SWIZZLE_64B, row = key: hi d0-15 | lo d0-15 (fp16), keys centred
+//   V  : 8 heads x 3 parts x blocks of 32 keys [32 rows (hi d0-15 | lo d0-15) x 128 B] tf32, K-major SWIZZLE_128B
+//   K2 : 4 blocks (hi cols 0-63, hi cols 64-127, lo cols 0-63, lo cols 64-127) x [NP keys x 128 B] SWIZZLE_128B
+__host__ __device__ inline int t2_vblocks(int keys) { return (keys + 31) >> 5; }
+__host__ __device__ inline size_t t2_szk(int NP) { return (size_t)NP * 64; }
+__host__ __device__ inline size_t t2_szv(int NP) {
+  const T2Parts p = t2_parts(NP);
+  size_t b = 0;
+  for (int j = 0; j < T2_PARTS; ++j) b += (size_t)t2_vblocks(16 * (p.cb[j + 1] - p.cb[j])) * 4096;
+  return b;
+}
+__host__ __device__ inline size_t t2_voff(int NP, int j) {
+  const T2Parts p = t2_parts(NP);
+  size_t b = 0;
+  for (int i = 0; i < j; ++i) b += (size_t)t2_vblocks(16 * (p.cb[i + 1] - p.cb[i])) * 4096;
+  return b;
+}
+__host__ __device__ inline size_t t2_szk2(int NP) { return (size_t)NP * 128; }
+__host__ __device__ inline size_t t2_img_bytes(int NP) { return 8 * t2_szk(NP) + 8 * t2_szv(NP) + 4 * t2_szk2(NP); }
+
+// mean key of every head (the centring vector): kbar[b][c] = mean_n K[b, n, c]
+__global__ void __launch_bounds__(128) decode_tc2_kbar_kernel(const float* __restrict__ proj, int N, float* __restrict__ kbar) {
+  const int b = blockIdx.x, c = threadIdx.x;
+  const float* pb = proj + (size_t)b * N * PROJ + c;
+  float s = 0.f;
+  for (int n = 0; n < N; ++n) s += __ldg(pb + (size_t)n * PROJ);
+  kbar[(size_t)b * H + c] = s / (float)N;
+}
+
+// proj fp32 [Bp*N, 640] (K | V | QL | QF | K2) -> operand image.  grid = (blocks per instance, Bp)
+__global__ void __launch_bounds__(256)
+decode_tc2_pack_kernel(const float* __restrict__ proj, const float* __restrict__ kbar, int Bp, int N, int NP,
+                       unsigned char* __restrict__ img) {
+  const size_t szk = t2_szk(NP), szv = t2_szv(NP), szk2 = t2_szk2(NP), per = t2_img_bytes(NP);
+  const T2Parts parts = t2_parts(NP);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int b = blockIdx.y; b < Bp; b += gridDim.y) {
+    const float* pb = proj + (size_t)b * N * PROJ;
+    unsigned char* base = img + (size_t)b * per;
+    // K (centred) and K2: one thread per (key r, matrix m in {K, K2}, 8-column chunk c16)
+    if (i < NP * 32) {
+      const int c16 = i & 15, m = (i >> 4) & 1, r = i >> 5;
+      float v[8];
+      if (r < N) {
+        const float4* p = (const float4*)(pb + (size_t)r * PROJ + (m == 0 ? 0 : 4 * H) + c16 * 8);
+        const float4 a = __ldg(p), c = __ldg(p + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+        if (m == 0) {
+          const float4* kb = (const float4*)(kbar + (size_t)b * H + c16 * 8);
+          const float4 ka = __ldg(kb), kc = __ldg(kb + 1);
+          v[0] -= ka.x; v[1] -= ka.y; v[2] -= ka.z; v[3] -= ka.w; v[4] -= kc.x; v[5] -= kc.y; v[6] -= kc.z; v[7] -= kc.w;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = 0.f;
+      }
+      uint4 hi, lo;
+      tcd_split8(v, hi, lo);
+      if (m == 0) {
+        const int h = c16 >> 1;
+        unsigned char* blk = base + (size_t)h * szk;
+        *(uint4*)(blk + tc::sw64_off(r, (c16 & 1))) = hi;
+        *(uint4*)(blk + tc::sw64_off(r, 2 + (c16 & 1))) = lo;
+      } else {
+        unsigned char* blk = base + 8 * szk + 8 * szv + (size_t)(c16 >> 3) * szk2;
+        *(uint4*)(blk + tc::sw128_off(r, c16 & 7)) = hi;
+        *(uint4*)(blk + 2 * szk2 + tc::sw128_off(r, c16 & 7)) = lo;
+      }
+    }
+    // V^T: one thread per (group of 4 keys r4, value column c): tf32 hi = top 19 bits, lo = the rest
+    if (i < (NP >> 2) * 128) {
+      const int c = i & 127, r4 = i >> 7;
+      float hi[4], lo[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = r4 * 4 + k;
+        const float v = (r < N) ? __ldg(pb + (size_t)r * PROJ + H + c) : 0.f;
+        hi[k] = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        lo[k] = v - hi[k];
+      }
+      const int ch = r4 >> 2;                                   // 16-key chunk of these keys
+      const int j = ch >= parts.cb[2] ? 2 : (ch >= parts.cb[1] ? 1 : 0);
+      const int kl = r4 * 4 - 16 * parts.cb[j];                 // key index inside the part
+      const int h = c >> 4, d = c & 15;
+      unsigned char* blk = base + 8 * szk + (size_t)h * szv + t2_voff(NP, j) + (size_t)(kl >> 5) * 4096;
+      *(float4*)(blk + tc::sw128_off(d, (kl & 31) >> 2)) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *(float4*)(blk + tc::sw128_off(16 + d, (kl & 31) >> 2)) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+
+struct T2Args {
+  const float* x;        // [Bp,N,2]
+  const float* proj;     // [Bp*N,640]  (QL at +256, QF at +384)
+  const float* qfix;     // [Bp,128]
+  const float* c0;       // [Bp,N]
+  const unsigned char* img;
+  const int32_t* src;
+  const int32_t* tgt;
+  const int32_t* first;
+  const int32_t* forced_pi;
+  int32_t* pi;
+  float* reward;
+  float* logits_out;
+  float* dbg;            // DEBUG builds: [S raw 2*8*128*NP | O 256*128 | U raw 256*NP | phase cycles] of instance 0
+  unsigned long long seed;
+  int N, NP, G, rows_per_cta, dbg_step;
+};
+
+// barrier slots: per row tile, then the shared ring
+enum { T2B_SFULL = 0, T2B_PFULL = 3, T2B_OFULL = 6, T2B_OREADY = 7, T2B_QFULL = 8, T2B_UFULL = 9, T2B_PER_TILE = 10 };
+enum { T2B_FULL = 2 * T2B_PER_TILE, T2B_EMPTY = T2B_FULL + T2_SLOTS, T2B_TOTAL = T2B_EMPTY + T2_SLOTS };
+
+template <bool LOGITS, bool DEBUG, bool SPLIT, bool SAMPLE>
+__global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args A) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler too
+  const int n_cta_parts = SPLIT ? (A.G + A.rows_per_cta - 1) / A.rows_per_cta : 1;
+  const int b = SPLIT ? blockIdx.x / n_cta_parts : blockIdx.x;
+  const int r0 = SPLIT ? (blockIdx.x - b * n_cta_parts) * A.rows_per_cta : 0;
+  const int N = A.N, NP = A.NP, GT = A.G;
+  const int G = SPLIT ? min(A.rows_per_cta, GT - r0) : A.G;   // rows of this CTA, from row r0 of the instance
+  const int n_steps = N - 2;
+  const int n_tiles = G > 128 ? 2 : 1;
+  const T2Parts parts = t2_parts(NP);
+
+  unsigned char* staging = smem;                                         // 2 x 64 KB
+  unsigned char* ring = smem + 2 * T2_TILE_STAGING;                      // T2_SLOTS x 12 KB
+  float* c0s = (float*)(ring + (size_t)T2_SLOTS * T2_SLOT);              // [NP]
+  uint64_t* bars = (uint64_t*)(c0s + NP);
+  uint32_t* tmem_slot = (uint32_t*)(bars + T2B_TOTAL);
+  const uint32_t bar0 = tc::smem_u32(bars);
+  auto TBAR = [&](int t, int i) { return bar0 + 8u * (uint32_t)(t * T2B_PER_TILE + i); };
+  auto RBAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+
+  const unsigned char* imgb = A.img + (size_t)b * t2_img_bytes(NP);
+  const float* projb = A.proj + (size_t)b * N * PROJ;
+
+  if ((tc::smem_u32(smem) & 1023u) != 0u) __trap();   // swizzle atoms need 1024-byte alignment
+  if (G > 224) __trap();                               // tile 1 has three lane quarters (the host splits larger instances)
+  if (tid == 0) {
+    for (int t = 0; t < 2; ++t) {
+      const int rows_t = min(128, G - 128 * t);
+      const int warps_t = rows_t > 0 ? (rows_t + 31) / 32 : 1;
+      for (int j = 0; j < T2_PARTS; ++j) {
+        tc::mbar_init(TBAR(t, T2B_SFULL + j), 1);
+        tc::mbar_init(TBAR(t, T2B_PFULL + j), warps_t);
+      }
+      tc::mbar_init(TBAR(t, T2B_OFULL), 1);
+      tc::mbar_init(TBAR(t, T2B_OREADY), warps_t);
+      tc::mbar_init(TBAR(t, T2B_QFULL), T2_PARTS * warps_t);
+      tc::mbar_init(TBAR(t, T2B_UFULL), 1);
+    }
+    for (int s = 0; s < T2_SLOTS; ++s) {
+      tc::mbar_init(RBAR(T2B_FULL + s), 1);
+      tc::mbar_init(RBAR(T2B_EMPTY + s), n_tiles);      // a slot is released by every tile's issuer
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // zero the A tiles (rows that never receive a query must hold finite values)
+  for (int i = tid; i < 2 * T2_TILE_STAGING / 16; i += T2_THREADS) ((uint4*)staging)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < NP; i += T2_THREADS) c0s[i] = i < N ? __ldg(&A.c0[(size_t)b * N + i]) : 0.f;
+  if (warp == 3) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc::fence_async_smem();
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // stages of one decode step in stream order: K_0^{0,1,2}; per head h: V_h^j, K_{h+1}^j (h < 7) for j = 0,1,2;
+  // K2_i^j for i = 0..3, j = 0,1,2
+  constexpr int PER_STEP = 3 + 7 * 6 + 3 + 12;
+
+  if (warp < 2) {
+    // ================================================================== MMA issuer of row tile t = warp
+    const int t = warp;
+    if (t < n_tiles) {
+      const uint32_t stg = tc::smem_u32(staging) + t * T2_TILE_STAGING;
+      const uint32_t ring0 = tc::smem_u32(ring);
+      const uint32_t dS = tmem_base + (uint32_t)(t * NP);
+      const uint32_t dO = tmem_base + (uint32_t)(T2_OCOL + 32 * t);
+      const uint32_t idO = tc::idesc_tf32(32);
+      uint32_t idK[T2_PARTS];
+      int kk8[T2_PARTS];                     // 8-key steps of P V per part
+#pragma unroll
+      for (int j = 0; j < T2_PARTS; ++j) {
+        idK[j] = tc::idesc_f16(16 * (parts.cb[j + 1] - parts.cb[j]));
+        kk8[j] = 2 * (parts.cb[j + 1] - parts.cb[j]);
+      }
+      uint32_t it = 0;
+      long long tph[6] = {0, 0, 0, 0, 0, 0};   // DEBUG: 0 ring wait, 1 wait P, 2 issue, 3 wait Q, 4 wait O staged, 5 logits
+      long long tlast = DEBUG ? clock64() : 0;
+      auto tick = [&](int ph) {
+        if (DEBUG) {
+          const long long now = clock64();
+          tph[ph] += now - tlast;
+          tlast = now;
+        }
+      };
+      auto take = [&]() {                      // next ring slot, in stream order
+        const uint32_t s = it % T2_SLOTS, use = it / T2_SLOTS;
+        tick(2);
+        tc::mbar_wait(RBAR(T2B_FULL + s), use & 1);
+        tc::fence_after();
+        tick(0);
+        ++it;
+        return s;
+      };
+      auto release = [&](uint32_t s) {
+        if (tc::elect_one()) tc::commit(RBAR(T2B_EMPTY + s));
+        __syncwarp();
+      };
+      // S_h^j into the score columns of part j; sk = ring slot holding K_h^j ([keys x (hi | lo)], SWIZZLE_64B)
+      auto issue_S = [&](int h, int j, uint32_t sk) {
+        const uint32_t a_hi = (stg >> 4) + (h >> 2) * 1024 + (h & 3) * 2, a_lo = a_hi + 2048;
+        const uint32_t b_hi = (ring0 + sk * T2_SLOT) >> 4, b_lo = b_hi + 2;
+        const uint32_t d = dS + (uint32_t)(16 * parts.cb[j]);
+        if (tc::elect_one()) {
+          tc::mma_ss_lo_b64(d, a_hi, b_hi, idK[j], 0);
+          tc::mma_ss_lo_b64(d, a_hi, b_lo, idK[j], 1);
+          tc::mma_ss_lo_b64(d, a_lo, b_hi, idK[j], 1);
+          tc::commit(TBAR(t, T2B_SFULL + j));
+        }
+        __syncwarp();
+      };
+      // O (+)= P_h^j [Vhi | Vlo]: A = fp32 words in the score columns of part j, B = V^T blocks of 32 keys in slot sv
+      auto issue_PV = [&](int j, uint32_t sv) {
+        const uint32_t vb = (ring0 + sv * T2_SLOT) >> 4;
+        const uint32_t pa = dS + (uint32_t)(16 * parts.cb[j]);
+        const int n8 = kk8[j];
+        if (tc::elect_one()) {
+#pragma unroll 1
+          for (int ks = 0; ks < n8; ++ks)
+            tc::mma_ts_tf32_lo(dO, pa + 8 * ks, vb + (ks >> 2) * 256 + (ks & 3) * 2, idO, (j | ks) != 0);
+          if (j == T2_PARTS - 1) tc::commit(TBAR(t, T2B_OFULL));
+        }
+        __syncwarp();
+      };
+      for (int step = 0; step < n_steps; ++step) {
+        uint32_t k0[T2_PARTS];
+#pragma unroll
+        for (int j = 0; j < T2_PARTS; ++j) k0[j] = take();
+        tc::mbar_wait(TBAR(t, T2B_QFULL), step & 1);
+        tc::fence_after();
+        tick(3);
+#pragma unroll
+        for (int j = 0; j < T2_PARTS; ++j) {
+          issue_S(0, j, k0[j]);
+          release(k0[j]);
+        }
+        for (int h = 0; h < NH; ++h) {
+          const uint32_t par = (uint32_t)(step * NH + h) & 1u;
+#pragma unroll
+          for (int j = 0; j < T2_PARTS; ++j) {
+            const uint32_t sv = take();                               // V_h^j
+            const uint32_t sk = (h + 1 < NH) ? take() : 0u;           // K_{h+1}^j
+            tick(2);
+            tc::mbar_wait(TBAR(t, T2B_PFULL + j), par);
+            tc::fence_after();
+            tick(1);
+            issue_PV(j, sv);
+            release(sv);
+            if (h + 1 < NH) {
+              issue_S(h + 1, j, sk);
+              release(sk);
+            }
+          }
+        }
+        // pointer logits U = O K2^T into the (consumed) score columns, part by part
+        for (int i = 0; i < 4; ++i) {
+          const int half = i & 1;                    // O / K2 columns 64*half .. +63
+          const uint32_t o_hi = (stg >> 4) + half * 1024, o_lo = o_hi + 2048;
+#pragma unroll
+          for (int j = 0; j < T2_PARTS; ++j) {
+            const uint32_t sk = take();
+            if (i == 0 && j == 0) {
+              tc::mbar_wait(TBAR(t, T2B_OREADY), step & 1);
+              tc::fence_after();
+              tick(4);
+            }
+            const uint32_t kb = (ring0 + sk * T2_SLOT) >> 4;
+            const uint32_t d = dS + (uint32_t)(16 * parts.cb[j]);
+            if (tc::elect_one()) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                tc::mma_ss_lo(d, o_hi + kk * 2, kb + kk * 2, idK[j], (i | kk) != 0);
+                if (i < 2) tc::mma_ss_lo(d, o_lo + kk * 2, kb + kk * 2, idK[j], 1);
+              }
+              tc::commit(RBAR(T2B_EMPTY + sk));
+            }
+            __syncwarp();
+          }
+        }
+        if (tc::elect_one()) tc::commit(TBAR(t, T2B_UFULL));
+        __syncwarp();
+        tick(5);
+      }
+      if (DEBUG && b == 0 && lane == 0) {
+        float* dT = A.dbg + (size_t)2 * 8 * 128 * NP + (size_t)256 * 128 + (size_t)256 * NP + (24 + t) * 8;
+        for (int i = 0; i < 6; ++i) dT[i] = (float)tph[i];
+      }
+    }
+  } else if (warp == 2) {
+    // ================================================================== operand producer (one stream for both tiles)
+    if (lane == 0) {
+      const size_t szk = t2_szk(NP), szv = t2_szv(NP), szk2 = t2_szk2(NP);
+      const int c1 = parts.cb[1], c2 = parts.cb[2], c3 = parts.cb[3];
+      auto keys_of = [&](int j) { return (uint32_t)(16 * (j == 0 ? c1 : (j == 1 ? c2 - c1 : c3 - c2))); };
+      auto krow_of = [&](int j) { return (uint32_t)(16 * (j == 0 ? 0 : (j == 1 ? c1 : c2))); };
+      auto vbytes_of = [&](int j) { return (uint32_t)t2_vblocks((int)keys_of(j)) * 4096u; };
+      auto voff_of = [&](int j) { return (size_t)((j > 0 ? vbytes_of(0) : 0u) + (j > 1 ? vbytes_of(1) : 0u)); };
+      const uint32_t total = (uint32_t)n_steps * (uint32_t)PER_STEP;
+      for (uint32_t it = 0; it < total; ++it) {
+        const uint32_t s = it % T2_SLOTS, use = it / T2_SLOTS;
+        tc::mbar_wait(RBAR(T2B_EMPTY + s), (use & 1) ^ 1);
+        const int i = (int)(it % (uint32_t)PER_STEP);
+        size_t off;
+        uint32_t bytes;
+        if (i < 3) {                                   // K_0^j
+          off = (size_t)krow_of(i) * 64;
+          bytes = keys_of(i) * 64u;
+        } else if (i < 3 + 42) {                       // heads 0..6: V_h^j, K_{h+1}^j
+          const int r = i - 3, h = r / 6, e = r - 6 * h, j = e >> 1;
+          if ((e & 1) == 0) { off = 8 * szk + (size_t)h * szv + voff_of(j); bytes = vbytes_of(j); }
+          else { off = (size_t)(h + 1) * szk + (size_t)krow_of(j) * 64; bytes = keys_of(j) * 64u; }
+        } else if (i < 48) {                           // head 7: V_7^j
+          const int j = i - 45;
+          off = 8 * szk + (size_t)7 * szv + voff_of(j);
+          bytes = vbytes_of(j);
+        } else {                                       // K2_i^j
+          const int r = i - 48, blk = r / 3, j = r - 3 * blk;
+          off = 8 * szk + 8 * szv + (size_t)blk * szk2 + (size_t)krow_of(j) * 128;
+          bytes = keys_of(j) * 128u;
+        }
+        tc::mbar_expect_tx(RBAR(T2B_FULL + s), bytes);
+        tc::bulk_g2s(tc::smem_u32(ring + (size_t)s * T2_SLOT), imgb + off, bytes, RBAR(T2B_FULL + s));
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================================================== softmax / state warps
+    const int sw = warp - 4;
+    const int t = sw / 12, part = (sw % 12) >> 2, q = warp & 3;
+    const int rows_t = min(128, G - 128 * t);
+    if (q * 32 < rows_t) {
+      const int row = q * 32 + lane;                 // row inside the tile = TMEM lane
+      const int g = t * 128 + row;
+      const bool valid = g < G;
+      const int gc = min(g, G - 1);
+      const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+      const uint32_t tS = tmem_base + lane_addr + (uint32_t)(t * NP);
+      const uint32_t tO = tmem_base + lane_addr + (uint32_t)(T2_OCOL + 32 * t);
+      const uint32_t tX = tmem_base + lane_addr + (uint32_t)(T2_XCOL + 16 * t);
+      unsigned char* stg = staging + t * T2_TILE_STAGING;
+      const int src = A.src[b], tgt = A.tgt[b];
+      const int first = A.first[r0 + gc];
+      int32_t* pirow = A.pi + ((size_t)b * GT + r0 + gc) * N;
+      const int c_lo = part == 0 ? 0 : (part == 1 ? parts.cb[1] : parts.cb[2]);
+      const int c_hi = part == 0 ? parts.cb[1] : (part == 1 ? parts.cb[2] : parts.cb[3]);
+      bool bad = false;                              // softmax sum left the fp32 range (part 0 only)
+
+      unsigned vis[7];
+#pragma unroll
+      for (int w = 0; w < 7; ++w) {           // padded keys (>= N) are permanently visited
+        const int lo = w * 32;
+        vis[w] = (lo + 32 <= N) ? 0u : ((N <= lo) ? 0xffffffffu : (0xffffffffu << (N - lo)));
+      }
+      int cur = 0, cnt = 0;
+      auto mark = [&](int a) {
+#pragma unroll
+        for (int w = 0; w < 7; ++w) vis[w] |= ((a >> 5) == w) ? (1u << (a & 31)) : 0u;
+      };
+      // visit(a) with source<->target coupling (train_path_solver.py:45-66); only part 0 records pi
+      auto visit = [&](int a) {
+        if (valid && part == 0 && cnt < N) pirow[cnt] = a;
+        mark(a);
+        cnt++;
+        cur = a;
+        const int partner = (a == src) ? tgt : ((a == tgt) ? src : -1);
+        if (partner >= 0) {
+          if (valid && part == 0 && cnt < N) pirow[cnt] = partner;
+          mark(partner);
+          cnt++;
+          cur = partner;
+        }
+      };
+      long long tph[6] = {0, 0, 0, 0, 0, 0};   // DEBUG: 0 wait S, 1 softmax, 2 wait O + drain, 3 wait U, 4 arg-max, 5 state + gather
+      long long tlast = DEBUG ? clock64() : 0;
+      auto tick = [&](int ph) {
+        if (DEBUG) {
+          const long long now = clock64();
+          tph[ph] += now - tlast;
+          tlast = now;
+        }
+      };
+
+      // ---- P = 2^S of this warp's key chunks of head h, in place; returns the row sum of what the tensor core
+      // will read (the top 19 bits of every word)
+      auto softmax_pass = [&](int step, int h) {
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll 1
+        for (int c = c_lo; c < c_hi; ++c) {
+          uint32_t s[32];
+          tld<16>(tS + 16 * c, s);
+          const unsigned bits = (tcd_word(vis, c >> 1) >> ((c & 1) * 16)) & 0xffffu;
+          tld_wait16(s);
+          if (DEBUG && b == 0 && step == A.dbg_step) {
+            float* dSd = A.dbg + ((size_t)(t * 8 + h) * 128 + row) * NP + 16 * c;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dSd[j] = __uint_as_float(s[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const float p0 = ex2_approx(((bits >> j) & 1u) ? -INFINITY : __uint_as_float(s[j]));
+            const float p1 = ex2_approx(((bits >> (j + 1)) & 1u) ? -INFINITY : __uint_as_float(s[j + 1]));
+            s[j] = __float_as_uint(p0);
+            s[j + 1] = __float_as_uint(p1);
+            acc = __fadd2_rn(acc, make_float2(__uint_as_float(s[j] & 0xffffe000u), __uint_as_float(s[j + 1] & 0xffffe000u)));
+          }
+          tst<16>(tS + 16 * c, s);
+        }
+        return acc.x + acc.y;
+      };
+      // publish the row sum of this part, then P itself
+      auto publish = [&](int h, float l) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tX + (h & 1) * 3 + part), "r"(__float_as_uint(l))
+                     : "memory");
+        tc::st_wait();
+        tc::fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(TBAR(t, T2B_PFULL + part));
+      };
+
+      const float4 qfix4 = __ldg((const float4*)(A.qfix + (size_t)b * H) + lane);
+      const uint32_t trio_bar = 1u + (uint32_t)(t * 4 + q);     // named barrier of the three warps of this row quarter
+      auto trio_sync = [&]() { asm volatile("bar.sync %0, 96;" ::"r"(trio_bar) : "memory"); };
+      // query rows -> A tile (fp16 hi/lo, K-major SWIZZLE_128B):
+      // q = ((q_graph+q_source+q_target) + q_first) + q_last (models.py:413), 1/sqrt(dk)*log2(e) folded in.
+      // The three warps of a row quarter gather a third of its rows each; lane l carries columns 4l..4l+3 of every
+      // row; 4 rows (8 L2 loads) are in flight at a time.
+      auto gather_q = [&]() {
+        const uint32_t sub = (uint32_t)(lane >> 4) * 16384u + (uint32_t)(lane & 1) * 8u;
+        const uint32_t chunk = (uint32_t)(lane & 15) >> 1;
+        const int nrows = min(32, rows_t - q * 32);
+        const int r_beg = min(nrows, (32 * part) / 3), r_end = min(nrows, (32 * (part + 1)) / 3);
+#pragma unroll 1
+        for (int rr = r_beg; rr < r_end; rr += 4) {
+          float4 ql[4], qf[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int cr = __shfl_sync(0xffffffffu, cur, (rr + i) & 31), fr = __shfl_sync(0xffffffffu, first, (rr + i) & 31);
+            ql[i] = __ldg((const float4*)(projb + (size_t)cr * PROJ + 2 * H) + lane);
+            qf[i] = __ldg((const float4*)(projb + (size_t)fr * PROJ + 3 * H) + lane);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (rr + i < r_end) {
+              uint32_t h0, l0, h1, l1;
+              split2(((qfix4.x + qf[i].x) + ql[i].x) * kScoreScale, ((qfix4.y + qf[i].y) + ql[i].y) * kScoreScale, h0, l0);
+              split2(((qfix4.z + qf[i].z) + ql[i].z) * kScoreScale, ((qfix4.w + qf[i].w) + ql[i].w) * kScoreScale, h1, l1);
+              unsigned char* p = stg + sub + tc::sw128_off((uint32_t)(q * 32 + rr + i), chunk);
+              *(uint2*)p = make_uint2(h0, h1);
+              *(uint2*)(p + 32768) = make_uint2(l0, l1);
+            }
+          }
+        }
+        tc::fence_async_smem();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(TBAR(t, T2B_QFULL));
+      };
+
+      // step 0: no decoder call (train_path_solver.py:256-257)
+      visit(first);
+      gather_q();
+
+      // drain O_h (part 0): (P Vhi + P Vlo) / sum of the three row sums -> fp16 hi/lo -> A tile columns
+      // 16h..16h+15 (the consumed Q_h slot)
+      auto drain_o = [&](int step, int h) {
+        tc::mbar_wait(TBAR(t, T2B_OFULL), (step * NH + h) & 1);
+        tc::fence_after();
+        uint32_t oa[16], ob[16], x0, x1, x2, x3;
+        tc::ld16(tO, oa);
+        tc::ld16(tO + 16, ob);
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)
+                     : "r"(tX + (h & 1) * 3)
+                     : "memory");
+        tc::ld16_wait(oa);
+        tc::ld16_wait(ob);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(x0), "+r"(x1), "+r"(x2), "+r"(x3)::"memory");
+        const float l = (__uint_as_float(x0) + __uint_as_float(x1)) + __uint_as_float(x2);
+        float inv;         // MUFU reciprocal (1 ulp): the normalisation error is far below the tf32 probabilities
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(l));
+        if (!(l > 0.f && l < 3.0e38f)) {   // empty or overflowed softmax: flag the row, keep the state machine finite
+          inv = 0.f;
+          bad = bad || valid;
+        }
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = (__uint_as_float(oa[j]) + __uint_as_float(ob[j])) * inv;
+        if (!(l > 0.f && l < 3.0e38f)) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        }
+        if (DEBUG && b == 0 && step == A.dbg_step) {
+          float* dOd = A.dbg + (size_t)2 * 8 * 128 * NP + (size_t)(t * 128 + row) * 128 + 16 * h;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) dOd[j] = v[j];
+        }
+        uint4 h0, l0, h1, l1;
+        tcd_split8_packed(v, h0, l0);
+        tcd_split8_packed(v + 8, h1, l1);
+        unsigned char* p = stg + (h >> 2) * 16384;
+        const uint32_t c = (uint32_t)(h & 3) * 2;
+        *(uint4*)(p + tc::sw128_off((uint32_t)row, c)) = h0;
+        *(uint4*)(p + tc::sw128_off((uint32_t)row, c + 1)) = h1;
+        *(uint4*)(p + 32768 + tc::sw128_off((uint32_t)row, c)) = l0;
+        *(uint4*)(p + 32768 + tc::sw128_off((uint32_t)row, c + 1)) = l1;
+      };
+
+      for (int step = 0; step < n_steps; ++step) {
+        // ------------------------------------------------------------ glimpse, one head at a time
+#pragma unroll 1
+        for (int h = 0; h < NH; ++h) {
+          tc::mbar_wait(TBAR(t, T2B_SFULL + part), (step * NH + h) & 1);
+          tc::fence_after();
+          tick(0);
+          const float l = softmax_pass(step, h);
+          tick(1);
+          // the previous head's accumulator must be drained before this head's first P V (part 0, which the
+          // issuer serves first) overwrites it
+          if (part == 0 && h > 0) {
+            drain_o(step, h - 1);
+            tick(2);
+          }
+          publish(h, l);
+        }
+        if (part == 0) {
+          drain_o(step, NH - 1);
+          tc::fence_async_smem();
+          tc::fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(TBAR(t, T2B_OREADY));
+          tick(2);
+        }
+
+        // ------------------------------------------------------------ pointer logits + arg-max
+        // Each warp of the trio scans its own key chunks and reduces them to one candidate (clipped logit, key);
+        // part 0 merges the three (ties -> lower key = the lower part).
+        tc::mbar_wait(TBAR(t, T2B_UFULL), step & 1);
+        tc::fence_after();
+        tick(3);
+        float best = -INFINITY;
+        int idx = 0x7fffffff;
+        float* lo_out = nullptr;
+        if (LOGITS && A.logits_out != nullptr)
+          lo_out = A.logits_out + (((size_t)b * GT + r0 + gc) * n_steps + step) * N;
+        // pass(EXACT): EXACT compares the clipped logits 10*tanh(.) themselves (models.py:438-440); otherwise the
+        // monotone pre-activation is compared, which picks the same key except when two clipped logits round to
+        // the same float (handled by re-running EXACT near the clip).  Four independent running maxima (column
+        // slot mod 4), merged with the lowest key winning ties (torch.argmax returns the first maximum).
+        auto pass = [&](auto exact_tag) {
+          constexpr bool EXACT = decltype(exact_tag)::value;
+          float bj[4];
+          int kj[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { bj[j] = -INFINITY; kj[j] = 0x7fffffff; }
+          uint32_t u[32];
+#pragma unroll 1
+          for (int c = c_lo; c < c_hi; ++c) {
+            tld<16>(tS + 16 * c, u);
+            const unsigned bits = (tcd_word(vis, c >> 1) >> ((c & 1) * 16)) & 0xffffu;
+            tld_wait16(u);
+            if (DEBUG && b == 0 && step == A.dbg_step) {
+              float* dU = A.dbg + (size_t)2 * 8 * 128 * NP + (size_t)256 * 128 + (size_t)(t * 128 + row) * NP + 16 * c;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) dU[j] = __uint_as_float(u[j]);
+            }
+            const float4* cc4 = (const float4*)(c0s + 16 * c);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 cc = cc4[j4];
+              const float ca[4] = {cc.x, cc.y, cc.z, cc.w};
+              uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
+              if (SAMPLE)
+                rnd = tcd_philox(make_uint4((uint32_t)(4 * c + j4), (uint32_t)step, (uint32_t)(r0 + gc), (uint32_t)b),
+                                 make_uint2((uint32_t)A.seed, (uint32_t)(A.seed >> 32)));
+              const uint32_t ra[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int j = 4 * j4 + jj;
+                float z = __uint_as_float(u[j]) + ca[jj];          // EXACT: 10 tanh(z / sqrt(128)); else the
+                if (EXACT) z = clip_tanh10(z * kT2InvSqrtH);        // monotone pre-activation itself
+                if (SAMPLE) z += tcd_gumbel(ra[jj]);
+                if ((bits >> j) & 1u) z = -INFINITY;
+                if (LOGITS && lo_out != nullptr && valid && 16 * c + j < N) lo_out[16 * c + j] = z;
+                if (z > bj[jj]) { bj[jj] = z; kj[jj] = 16 * c + j; }
+              }
+            }
+          }
+          best = bj[0];
+          idx = kj[0];
+#pragma unroll
+          for (int j = 1; j < 4; ++j)
+            if (bj[j] > best || (bj[j] == best && kj[j] < idx)) { best = bj[j]; idx = kj[j]; }
+        };
+        if (LOGITS || SAMPLE) {
+          pass(std::true_type{});
+        } else {
+          pass(std::false_type{});
+          if (__any_sync(0xffffffffu, valid && best * kT2InvSqrtH > 3.0f)) {
+            pass(std::true_type{});
+          } else {
+            best = (best == -INFINITY) ? best : clip_tanh10(best * kT2InvSqrtH);   // candidates are exchanged as clipped logits
+          }
+        }
+        tick(4);
+        int a;
+        if (part != 0) {
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(tX + 4 + 2 * part), "r"(__float_as_uint(best)),
+                       "r"((uint32_t)idx)
+                       : "memory");
+          tc::st_wait();
+          tc::fence_before();
+          trio_sync();                // candidates published
+          trio_sync();                // part 0 has published the chosen node
+          tc::fence_after();
+          uint32_t av;
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(av) : "r"(tX + 10) : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(av)::"memory");
+          a = (int)av;
+        } else {
+          trio_sync();
+          tc::fence_after();
+          uint32_t z1, i1, z2, i2;
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(z1), "=r"(i1), "=r"(z2), "=r"(i2)
+                       : "r"(tX + 6)
+                       : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(z1), "+r"(i1), "+r"(z2), "+r"(i2)::"memory");
+          if (__uint_as_float(z1) > best) { best = __uint_as_float(z1); idx = (int)i1; }     // ties keep the lower part's key
+          if (__uint_as_float(z2) > best) { best = __uint_as_float(z2); idx = (int)i2; }
+          // ---- state update (train_path_solver.py:45-72); the chosen node goes to the other two warps
+          a = A.forced_pi ? A.forced_pi[((size_t)b * GT + r0 + gc) * N + cnt] : idx;
+          if ((unsigned)a >= (unsigned)N) a = cur;     // a NaN row has no candidate: stay in range (the row is flagged)
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tX + 10), "r"((uint32_t)a) : "memory");
+          tc::st_wait();
+          tc::fence_before();
+          trio_sync();
+        }
+        visit(a);
+        tc::fence_before();
+        if (step + 1 < n_steps) gather_q();
+        tick(5);
+      }
+      // ---- reward = -(closed tour length - fixed edge)   (train_path_solver.py:109-149)
+      if (valid && part == 0) {
+        const float2* xb = (const float2*)A.x + (size_t)b * N;
+        float len = 0.f;
+        float2 p0 = __ldg(&xb[pirow[0]]);
+        const float2 pfirst = p0;
+        for (int i = 1; i <= N; ++i) {
+          const float2 c = (i == N) ? pfirst : __ldg(&xb[pirow[i]]);
+          const float dx = p0.x - c.x, dy = p0.y - c.y;
+          len += sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+          p0 = c;
+        }
+        const float2 ps = __ldg(&xb[src]), pt = __ldg(&xb[tgt]);
+        const float dx = ps.x - pt.x, dy = ps.y - pt.y;
+        const float fixed = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+        A.reward[(size_t)b * GT + r0 + g] = bad ? __int_as_float(0x7fc00000) : -(len - fixed);
+      }
+      if (DEBUG && b == 0 && lane == 0) {
+        float* dT = A.dbg + (size_t)2 * 8 * 128 * NP + (size_t)256 * 128 + (size_t)256 * NP + sw * 8;
+        for (int i = 0; i < 6; ++i) dT[i] = (float)tph[i];
+      }
+    }
+  }
+
+  tc::fence_before();
+  __syncthreads();
+  if (warp == 3) {
+    tc::fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int t2_np_of(int N) { return (N + 15) / 16 * 16; }
+
+bool decode_tc2_supported(int N, int G) { return t2_np_of(N) <= 208 && t2_np_of(N) >= 48 && G <= 256; }
+size_t decode_tc2_pack_bytes(int Bp, int N) {
+  return align_up((size_t)Bp * t2_img_bytes(t2_np_of(N)), 256) + 1024 + align_up((size_t)Bp * H * 4, 256);
+}
+size_t decode_tc2_dbg_floats(int N) {
+  const int NP = t2_np_of(N);
+  return (size_t)2 * 8 * 128 * NP + (size_t)256 * 128 + (size_t)256 * NP + 256;
+}
+
+// CTAs per instance: 1 unless the launch would leave most SMs idle (then the rows are cut into 128-, 64- or 32-row
+// parts as long as all CTAs still fit in one wave; HTSP_DECODE_SPLIT = 1 | 2 | 4 | 8 overrides) or the instance has
+// more than 224 rows (a two-tile CTA has three lane quarters in tile 1).
+static void t2_choose_split(int Bp, int G, bool debug, int& split, int& rows_per_cta) {
+  split = 1;
+  rows_per_cta = G;
+  if (G > 224) {
+    split = 2;
+    rows_per_cta = 128;
+  }
+  if (debug || G <= 32) return;
+  int dev = 0, n_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0)
+    n_sm = 148;
+  const char* env = getenv("HTSP_DECODE_SPLIT");
+  const int forced = env ? atoi(env) : 0;
+  for (int want = 8; want >= 2; want >>= 1) {
+    if (forced > 0 && want != forced) continue;
+    const int rpc = ((G + want - 1) / want + 31) / 32 * 32;
+    const int parts = (G + rpc - 1) / rpc;
+    if (parts < 2) continue;
+    if (forced > 0 || (long long)Bp * parts <= n_sm) {
+      split = parts;
+      rows_per_cta = rpc;
+      return;
+    }
+  }
+}
+
+template <bool LOGITS, bool DEBUG, bool SPLIT, bool SAMPLE = false>
+static int launch_t2(const T2Args& a, int Bp, cudaStream_t s) {
+  const size_t smem = (size_t)2 * T2_TILE_STAGING + (size_t)T2_SLOTS * T2_SLOT + (size_t)a.NP * 4 + T2B_TOTAL * 8 + 16;
+  if (smem > 227 * 1024) {
+    set_error("decode_tc2: N=%d needs %zu bytes of shared memory", a.N, smem);
+    return HTSP_ERR_UNSUPPORTED;
+  }
+  HTSP_CHECK_CUDA(cudaFuncSetAttribute(decode_tc2_kernel<LOGITS, DEBUG, SPLIT, SAMPLE>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kernel_timer_begin(s);
+  decode_tc2_kernel<LOGITS, DEBUG, SPLIT, SAMPLE>
+      <<<SPLIT ? Bp * ((a.G + a.rows_per_cta - 1) / a.rows_per_cta) : Bp, T2_THREADS, smem, s>>>(a);
+  kernel_timer_end(s);
+  HTSP_CHECK_LAUNCH();
+  return HTSP_OK;
+}
+
+int launch_decode_tc2(const float* x, const float* proj, const float* qfix, const float* c0,
+                      const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp, int N,
+                      int G, const int32_t* forced_pi, int32_t* pi, float* reward,
+                      float* logits_out, void* pack_ws, float* dbg, int dbg_step, const uint64_t* sample_seed,
+                      cudaStream_t s) {
+  HTSP_REQUIRE(decode_tc2_supported(N, G), "decode_tc2 shape");
+  HTSP_REQUIRE(sample_seed == nullptr || (dbg == nullptr && logits_out == nullptr && forced_pi == nullptr),
+               "sampling rollouts take no teacher forcing, logit capture or debug dump");
+  HTSP_REQUIRE(dbg == nullptr || G <= 224, "debug dump: at most 224 rows");
+  const int NP = t2_np_of(N);
+  unsigned char* img = (unsigned char*)(((uintptr_t)pack_ws + 1023) & ~(uintptr_t)1023);
+  float* kbar = (float*)(img + align_up((size_t)Bp * t2_img_bytes(NP), 256));
+  decode_tc2_kbar_kernel<<<Bp, 128, 0, s>>>(proj, N, kbar);
+  HTSP_CHECK_LAUNCH();
+  {
+    const int items = max(NP * 32, (NP >> 2) * 128);
+    decode_tc2_pack_kernel<<<dim3((items + 255) / 256, min(Bp, 65535)), 256, 0, s>>>(proj, kbar, Bp, N, NP, img);
+    HTSP_CHECK_LAUNCH();
+  }
+  T2Args a;
+  a.x = x; a.proj = proj; a.qfix = qfix; a.c0 = c0; a.img = img;
+  a.src = src; a.tgt = tgt; a.first = first; a.forced_pi = forced_pi;
+  a.pi = pi; a.reward = reward; a.logits_out = logits_out; a.dbg = dbg;
+  a.seed = sample_seed ? *sample_seed : 0ull;
+  a.N = N; a.NP = NP; a.G = G; a.dbg_step = dbg_step;
+  int n_split = 1, rows_per_cta = G;
+  t2_choose_split(Bp, G, dbg != nullptr, n_split, rows_per_cta);
+  a.rows_per_cta = rows_per_cta;
+  const bool split = n_split > 1;
+  if (sample_seed != nullptr) return split ? launch_t2<false, false, true, true>(a, Bp, s) : launch_t2<false, false, false, true>(a, Bp, s);
+  if (dbg != nullptr) return launch_t2<false, true, false>(a, Bp, s);
+  if (logits_out != nullptr) return split ? launch_t2<true, false, true>(a, Bp, s) : launch_t2<true, false, false>(a, Bp, s);
+  return split ? launch_t2<false, false, true>(a, Bp, s) : launch_t2<false, false, false>(a, Bp, s);
+}
+
+}  // namespace htsp

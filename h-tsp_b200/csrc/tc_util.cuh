@@ -127,6 +127,38 @@ __device__ __forceinline__ void mma_ts_lo(uint32_t tmem_d, uint32_t tmem_a, uint
       "r"(tmem_a), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi)
       : "memory");
 }
+// kind::tf32 (A, B = fp32 words of which the hardware reads the top 19 bits -- measured, tools/lab_tc.cu part A)
+__host__ __device__ constexpr uint32_t idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+// high descriptor word of a K-major SWIZZLE_64B operand (rows of 64 bytes, 8-row atoms of 512 bytes)
+constexpr uint32_t kDescHi64 = (512u >> 4) | (1u << 14) | (4u << 29);
+// A: K-major SWIZZLE_128B, B: K-major SWIZZLE_64B (the per-head key blocks of decode_tc2.cu)
+__device__ __forceinline__ void mma_ss_lo_b64(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 da, db;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "mov.b64 da, {%1, %5};\n"
+      "mov.b64 db, {%2, %6};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi), "r"(kDescHi64)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem, fp32 words] * B[smem, tf32 K-major SWIZZLE_128B]^T
+__device__ __forceinline__ void mma_ts_tf32_lo(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 db;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "mov.b64 db, {%2, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %3, p;\n}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi)
+      : "memory");
+}
+__host__ __device__ __forceinline__ uint32_t sw64_off(uint32_t row, uint32_t chunk) {
+  return row * 64u + ((chunk ^ ((row >> 1) & 3u)) << 4);
+}
 __device__ __forceinline__ void commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");

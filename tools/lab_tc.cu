@@ -290,8 +290,65 @@ __device__ __forceinline__ float chunk_body(uint32_t tin, uint32_t tout, unsigne
   return csum;
 }
 
+
+// software-pipelined variants: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed (two register
+// buffers).  VARIANT 4: tf32 in place (mask, ex2, store); VARIANT 5: the x3 production arithmetic.
+template <int VARIANT>
+__device__ __forceinline__ void process16(uint32_t (&s)[16], uint32_t tout, unsigned bits, float m, float& l) {
+  uint32_t out[16];
+  if (VARIANT == 4) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) out[j] = __float_as_uint(ex2_approx(((bits >> j) & 1u) ? -INFINITY : __uint_as_float(s[j])));
+  } else {
+    float tv[16], p[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) tv[j] = ((bits >> j) & 1u) ? -INFINITY : __uint_as_float(s[j]);
+    const float2 nm = make_float2(-m, -m);
+    float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float2 d0 = __fadd2_rn(make_float2(tv[j], tv[j + 1]), nm);
+      const float2 d1 = __fadd2_rn(make_float2(tv[j + 2], tv[j + 3]), nm);
+      p[j] = ex2_approx(d0.x); p[j + 1] = ex2_approx(d0.y); p[j + 2] = ex2_approx(d1.x); p[j + 3] = ex2_approx(d1.y);
+      acc0 = __fadd2_rn(acc0, make_float2(p[j], p[j + 1]));
+      acc1 = __fadd2_rn(acc1, make_float2(p[j + 2], p[j + 3]));
+    }
+    acc0 = __fadd2_rn(acc0, acc1);
+    l += acc0.x + acc0.y;
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) split_pair(p[j], p[j + 1], out[j >> 1], out[8 + (j >> 1)]);
+  }
+  tst16(tout, out);
+}
+template <int VARIANT>
+__device__ __forceinline__ float prefetch_loop(uint32_t tS, int c_lo, int c_hi, const unsigned (&vis)[7], int reps) {
+  float l = 0.f;
+  uint32_t a[16], b[16];
+  for (int r = 0; r < reps; ++r) {
+#pragma unroll 1
+    for (int hd = 0; hd < 8; ++hd) {
+      const float m = (float)(3 + (hd & 1));
+      tld16(tS + 16 * c_lo, a);
+#pragma unroll 1
+      for (int c = c_lo; c < c_hi; c += 2) {
+        const unsigned w0 = vis_word(vis, c >> 1) >> ((c & 1) * 16), w1 = vis_word(vis, (c + 1) >> 1) >> (((c + 1) & 1) * 16);
+        tld16_wait(a);
+        if (c + 1 < c_hi) tld16(tS + 16 * (c + 1), b);
+        process16<VARIANT>(a, tS + 16 * c, w0 & 0xffffu, m, l);
+        if (c + 1 < c_hi) {
+          tld16_wait(b);
+          if (c + 2 < c_hi) tld16(tS + 16 * (c + 2), a);
+          process16<VARIANT>(b, tS + 16 * (c + 1), w1 & 0xffffu, m, l);
+        }
+      }
+    }
+  }
+  st_wait();
+  return l;
+}
+
 template <int VARIANT, int KPOLY>
-__global__ void __launch_bounds__(640, 1) lab_softmax_kernel(long long* __restrict__ cycles, float* __restrict__ sink, int reps, unsigned seed) {
+__global__ void __launch_bounds__(640, 1) lab_softmax_kernel(long long* __restrict__ cycles, float* __restrict__ sink, int reps, unsigned seed, unsigned warp_mask) {
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -309,7 +366,7 @@ __global__ void __launch_bounds__(640, 1) lab_softmax_kernel(long long* __restri
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
     const int sw = warp - 4;
     const int t = sw >> 3, half = (sw >> 2) & 1, q = warp & 3;
-    const bool active = !(t == 1 && q == 3);            // 200 rows: tile 1 has three lane quarters
+    const bool active = !(t == 1 && q == 3) && ((warp_mask >> sw) & 1u);            // 200 rows: tile 1 has three lane quarters
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const uint32_t tS = tb + lane_addr + (uint32_t)(t * NP);
     const int nch = NP >> 4, n0 = nch >> 1;
@@ -329,9 +386,12 @@ __global__ void __launch_bounds__(640, 1) lab_softmax_kernel(long long* __restri
     unsigned vis[7];
 #pragma unroll
     for (int w = 0; w < 7; ++w) vis[w] = rnd() ^ (rnd() << 7);
+    float acc = 0.f;
     asm volatile("bar.sync 1, 512;" ::: "memory");
     const long long t0 = clock64();
-    float acc = 0.f;
+    if (VARIANT == 4 || VARIANT == 5) {
+      if (active) acc = prefetch_loop<VARIANT>(tS, c_lo, c_hi, vis, reps);
+    } else
     if (active) {
       for (int r = 0; r < reps; ++r) {
 #pragma unroll 1
@@ -487,13 +547,88 @@ static void part_c() {
   cudaFree(dO); cudaFree(dS);
 }
 
+// =====================================================================================================
+// part D: kind::f16 with A in a K-major SWIZZLE_128B tile and B in a K-major SWIZZLE_64B tile (rows of 64 bytes:
+// 16-byte chunk index XOR ((row >> 1) & 3), 8-row atoms of 512 bytes) -- the layout of the per-head key blocks
+// =====================================================================================================
+__host__ __device__ __forceinline__ uint32_t sw64_off(uint32_t row, uint32_t chunk) { return row * 64u + ((chunk ^ ((row >> 1) & 3u)) << 4); }
+__global__ void __launch_bounds__(128) lab_sw64_kernel(const unsigned char* __restrict__ Aimg, const unsigned char* __restrict__ Bimg, float* __restrict__ D) {
+  __shared__ __align__(1024) unsigned char asm_[16384];
+  __shared__ __align__(1024) unsigned char bsm[4096];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 16384 / 16; i += 128) ((uint4*)asm_)[i] = ((const uint4*)Aimg)[i];
+  for (int i = tid; i < 4096 / 16; i += 128) ((uint4*)bsm)[i] = ((const uint4*)Bimg)[i];
+  if (tid == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(128) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tb = tmem_slot;
+  if (tid == 0) {
+    const uint32_t id = idesc(64, 0, 0);
+    for (int ks = 0; ks < 2; ++ks) {
+      const uint64_t ad = desc_sw128(smem_u32(asm_) + 32 * ks);
+      uint64_t bd = 0;
+      bd |= (uint64_t)(((smem_u32(bsm) + 32 * ks) >> 4) & 0x3FFF);
+      bd |= (uint64_t)((512 >> 4) & 0x3FFF) << 32;
+      bd |= (uint64_t)1 << 46;
+      bd |= (uint64_t)4 << 61;
+      mma_ss_f16(tb, ad, bd, id, ks != 0);
+    }
+    commit(smem_u32(&bar));
+  }
+  mbar_wait(smem_u32(&bar), 0);
+  fence_after();
+  uint32_t a[16];
+  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+  for (int c = 0; c < 64; c += 16) {
+    tld16(tb + lane_addr + c, a);
+    tld16_wait(a);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) D[tid * 64 + c + j] = __uint_as_float(a[j]);
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 0) { fence_after(); asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(128) : "memory"); }
+}
+static void part_d() {
+  std::vector<unsigned char> A(16384, 0), B(4096, 0);
+  std::vector<float> fa(128 * 32), fb(64 * 32);
+  for (auto& v : fa) v = __half2float(__float2half_rn(2.f * frand() - 1.f));
+  for (auto& v : fb) v = __half2float(__float2half_rn(2.f * frand() - 1.f));
+  for (int r = 0; r < 128; ++r) for (int k = 0; k < 32; ++k) { __half h = __float2half_rn(fa[r * 32 + k]); memcpy(&A[sw128_off(r, k >> 3) + (k & 7) * 2], &h, 2); }
+  for (int n = 0; n < 64; ++n) for (int k = 0; k < 32; ++k) { __half h = __float2half_rn(fb[n * 32 + k]); memcpy(&B[sw64_off(n, k >> 3) + (k & 7) * 2], &h, 2); }
+  unsigned char *dA, *dB; float* dD;
+  CK(cudaMalloc(&dA, 16384)); CK(cudaMalloc(&dB, 4096)); CK(cudaMalloc(&dD, 128 * 64 * 4));
+  CK(cudaMemcpy(dA, A.data(), 16384, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dB, B.data(), 4096, cudaMemcpyHostToDevice));
+  lab_sw64_kernel<<<1, 128>>>(dA, dB, dD);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("{\"part\": \"D\", \"error\": \"%s\"}\n", cudaGetErrorString(e)); exit(1); }
+  std::vector<float> D(128 * 64);
+  CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+  double err = 0;
+  for (int r = 0; r < 128; ++r) for (int n = 0; n < 64; ++n) {
+    double ref = 0;
+    for (int k = 0; k < 32; ++k) ref += (double)fa[r * 32 + k] * (double)fb[n * 32 + k];
+    err = fmax(err, fabs(ref - D[r * 64 + n]));
+  }
+  printf("{\"part\": \"D\", \"test\": \"A SWIZZLE_128B x B SWIZZLE_64B (64 keys x 32 halfs), two k-steps\", \"max_abs_diff\": %.3e}\n", err);
+  cudaFree(dA); cudaFree(dB); cudaFree(dD);
+}
+
 template <int VARIANT, int KPOLY>
-static void run_variant(const char* name, int reps) {
+static void run_variant(const char* name, int reps, unsigned warp_mask = 0xffffu) {
   const int grid = 148;
   long long* dC; float* dS;
   CK(cudaMalloc(&dC, grid * 16 * sizeof(long long))); CK(cudaMalloc(&dS, 4));
   for (int it = 0; it < 2; ++it) {
-    lab_softmax_kernel<VARIANT, KPOLY><<<grid, 640>>>(dC, dS, reps, 1234u + it);
+    lab_softmax_kernel<VARIANT, KPOLY><<<grid, 640>>>(dC, dS, reps, 1234u + it, warp_mask);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("{\"part\": \"B\", \"variant\": \"%s\", \"error\": \"%s\"}\n", name, cudaGetErrorString(e)); exit(1); }
   }
@@ -507,16 +642,29 @@ static void run_variant(const char* name, int reps) {
   }
   mean_max /= grid; mean_all /= n_all;
   // a scheduler with four softmax warps runs 2 x (6 + 7) = 26 chunks per head
-  printf("{\"part\": \"B\", \"variant\": \"%s\", \"clk_per_head_pass\": %.0f, \"clk_per_chunk_on_a_4_warp_scheduler\": %.1f, \"mean_warp_clk_per_head\": %.0f}\n",
-         name, mean_max / (reps * 8.0), mean_max / (reps * 8.0) / 26.0, mean_all / (reps * 8.0));
+  printf("{\"part\": \"B\", \"variant\": \"%s\", \"warp_mask\": \"0x%04x\", \"clk_per_head_pass\": %.0f, \"clk_per_chunk_on_a_4_warp_scheduler\": %.1f, \"mean_warp_clk_per_head\": %.0f}\n",
+         name, warp_mask, mean_max / (reps * 8.0), mean_max / (reps * 8.0) / 26.0, mean_all / (reps * 8.0));
   cudaFree(dC); cudaFree(dS);
 }
 
 int main(int argc, char** argv) {
   const int reps = argc > 1 ? atoi(argv[1]) : 200;
   part_a();
-  part_c();
-  if (argc > 2) return 0;
+  part_d();
+  if (argc == 5) return 0;
+  if (argc <= 3) part_c();
+  if (argc == 3) return 0;
+  if (argc > 3) {     // warp-count study: how fast is a softmax warp alone / two per scheduler / four per scheduler?
+    const unsigned masks[4] = {0x0001u, 0x0011u, 0x00ffu, 0xffffu};   // one warp; t0 halves A+B of quarter 0; tile 0; both tiles
+    for (unsigned m : masks) {
+      run_variant<0, 0>("x3 production chunk", reps, m);
+      run_variant<5, 0>("x3 chunk, next tcgen05.ld in flight", reps, m);
+      run_variant<1, 0>("tf32 in place, all MUFU", reps, m);
+      run_variant<4, 0>("tf32 in place, next tcgen05.ld in flight", reps, m);
+      run_variant<1, 4>("tf32 in place, 4/16 polynomial", reps, m);
+    }
+    return 0;
+  }
   run_variant<0, 0>("x3 production chunk", reps);
   run_variant<1, 0>("tf32 in place, all MUFU", reps);
   run_variant<1, 4>("tf32 in place, 4/16 polynomial", reps);
