@@ -42,6 +42,9 @@ constexpr int T2_SLOT = 12288;            // ring slot: one K_h^j (<= 5 KB), V_h
 constexpr int T2_TILE_STAGING = 65536;    // per row tile: [hi k0-63 | hi k64-127 | lo k0-63 | lo k64-127], 16 KB each
 constexpr int T2_OCOL = 416;              // O accumulator of tile t: columns 416 + 32 t .. + 31 ([P Vhi | P Vlo])
 constexpr int T2_XCOL = 480;              // exchange columns of tile t: 480 + 16 t: l[head & 1][part] (6), candidates (4), chosen (1)
+#ifndef T2_POLY
+#define T2_POLY 0                         // of every 16 exponentials, this many go through the FMA-pipe polynomial
+#endif
 constexpr float kT2InvSqrtH = 0.08838834764831845f;   // 1/sqrt(128)
 
 // key parts in 16-key chunks: part 0 (whose warps also drain O) is the shortest
@@ -166,7 +169,7 @@ struct T2Args {
   float* logits_out;
   float* dbg;            // DEBUG builds: [S raw 2*8*128*NP | O 256*128 | U raw 256*NP | phase cycles] of instance 0
   unsigned long long seed;
-  int N, NP, G, rows_per_cta, dbg_step;
+  int N, NP, G, rows_per_cta, dbg_step, tile1_delay;
 };
 
 // barrier slots: per row tile, then the shared ring
@@ -426,16 +429,21 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
       const int c_hi = part == 0 ? parts.cb[1] : (part == 1 ? parts.cb[2] : parts.cb[3]);
       bool bad = false;                              // softmax sum left the fp32 range (part 0 only)
 
-      unsigned vis[7];
+      // visited flags of THIS warp's keys only (bit k = key 16 c_lo + k; at most 96 keys per part); padded keys
+      // (>= N) are permanently visited
+      const int nc = c_hi - c_lo;
+      unsigned pv[3];
 #pragma unroll
-      for (int w = 0; w < 7; ++w) {           // padded keys (>= N) are permanently visited
-        const int lo = w * 32;
-        vis[w] = (lo + 32 <= N) ? 0u : ((N <= lo) ? 0xffffffffu : (0xffffffffu << (N - lo)));
+      for (int w = 0; w < 3; ++w) {
+        const int lo = 16 * c_lo + 32 * w;
+        pv[w] = (lo + 32 <= N) ? 0u : ((N <= lo) ? 0xffffffffu : (0xffffffffu << (N - lo)));
       }
       int cur = 0, cnt = 0;
       auto mark = [&](int a) {
+        const unsigned rel = (unsigned)(a - 16 * c_lo);
+        const unsigned bit = rel < 96u ? (1u << (rel & 31u)) : 0u;
 #pragma unroll
-        for (int w = 0; w < 7; ++w) vis[w] |= ((a >> 5) == w) ? (1u << (a & 31)) : 0u;
+        for (int w = 0; w < 3; ++w) pv[w] |= ((rel >> 5) == (unsigned)w) ? bit : 0u;
       };
       // visit(a) with source<->target coupling (train_path_solver.py:45-66); only part 0 records pi
       auto visit = [&](int a) {
@@ -465,26 +473,36 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
       // will read (the top 19 bits of every word)
       auto softmax_pass = [&](int step, int h) {
         float2 acc = make_float2(0.f, 0.f);
-#pragma unroll 1
-        for (int c = c_lo; c < c_hi; ++c) {
-          uint32_t s[32];
-          tld<16>(tS + 16 * c, s);
-          const unsigned bits = (tcd_word(vis, c >> 1) >> ((c & 1) * 16)) & 0xffffu;
-          tld_wait16(s);
-          if (DEBUG && b == 0 && step == A.dbg_step) {
-            float* dSd = A.dbg + ((size_t)(t * 8 + h) * 128 + row) * NP + 16 * c;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) dSd[j] = __uint_as_float(s[j]);
-          }
+        for (int i = 0; i < 6; ++i) {
+          if (i < nc) {
+            const int c = c_lo + i;
+            uint32_t s[32];
+            tld<16>(tS + 16 * c, s);
+            const unsigned bits = (pv[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
+            tld_wait16(s);
+            if (DEBUG && b == 0 && step == A.dbg_step) {
+              float* dSd = A.dbg + ((size_t)(t * 8 + h) * 128 + row) * NP + 16 * c;
 #pragma unroll
-          for (int j = 0; j < 16; j += 2) {
-            const float p0 = ex2_approx(((bits >> j) & 1u) ? -INFINITY : __uint_as_float(s[j]));
-            const float p1 = ex2_approx(((bits >> (j + 1)) & 1u) ? -INFINITY : __uint_as_float(s[j + 1]));
-            s[j] = __float_as_uint(p0);
-            s[j + 1] = __float_as_uint(p1);
-            acc = __fadd2_rn(acc, make_float2(__uint_as_float(s[j] & 0xffffe000u), __uint_as_float(s[j + 1] & 0xffffe000u)));
+              for (int j = 0; j < 16; ++j) dSd[j] = __uint_as_float(s[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              float p0, p1;
+              if (j < T2_POLY) {      // FMA-pipe polynomial for some of the exponentials (MUFU.EX2 is the busiest pipe)
+                const float2 r = ex2_poly2(__uint_as_float(s[j]), __uint_as_float(s[j + 1]));
+                p0 = ((bits >> j) & 1u) ? 0.f : r.x;
+                p1 = ((bits >> (j + 1)) & 1u) ? 0.f : r.y;
+              } else {
+                p0 = ex2_approx(((bits >> j) & 1u) ? -INFINITY : __uint_as_float(s[j]));
+                p1 = ex2_approx(((bits >> (j + 1)) & 1u) ? -INFINITY : __uint_as_float(s[j + 1]));
+              }
+              s[j] = __float_as_uint(p0);
+              s[j + 1] = __float_as_uint(p1);
+              acc = __fadd2_rn(acc, make_float2(__uint_as_float(s[j] & 0xffffe000u), __uint_as_float(s[j + 1] & 0xffffe000u)));
+            }
+            tst<16>(tS + 16 * c, s);
           }
-          tst<16>(tS + 16 * c, s);
         }
         return acc.x + acc.y;
       };
@@ -536,6 +554,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
         if (lane == 0) tc::mbar_arrive(TBAR(t, T2B_QFULL));
       };
 
+      if (t == 1 && A.tile1_delay > 0) {      // row tile 1 starts late: its head loop interleaves with tile 0's
+        const long long t0c = clock64();
+        while (clock64() - t0c < (long long)A.tile1_delay) {}
+      }
       // step 0: no decoder call (train_path_solver.py:256-257)
       visit(first);
       gather_q();
@@ -633,10 +655,12 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
 #pragma unroll
           for (int j = 0; j < 4; ++j) { bj[j] = -INFINITY; kj[j] = 0x7fffffff; }
           uint32_t u[32];
-#pragma unroll 1
-          for (int c = c_lo; c < c_hi; ++c) {
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            if (i >= nc) continue;
+            const int c = c_lo + i;
             tld<16>(tS + 16 * c, u);
-            const unsigned bits = (tcd_word(vis, c >> 1) >> ((c & 1) * 16)) & 0xffffu;
+            const unsigned bits = (pv[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
             tld_wait16(u);
             if (DEBUG && b == 0 && step == A.dbg_step) {
               float* dU = A.dbg + (size_t)2 * 8 * 128 * NP + (size_t)256 * 128 + (size_t)(t * 128 + row) * NP + 16 * c;
@@ -838,6 +862,7 @@ int launch_decode_tc2(const float* x, const float* proj, const float* qfix, cons
   a.pi = pi; a.reward = reward; a.logits_out = logits_out; a.dbg = dbg;
   a.seed = sample_seed ? *sample_seed : 0ull;
   a.N = N; a.NP = NP; a.G = G; a.dbg_step = dbg_step;
+  a.tile1_delay = getenv("HTSP_TILE1_DELAY") ? atoi(getenv("HTSP_TILE1_DELAY")) : 0;
   int n_split = 1, rows_per_cta = G;
   t2_choose_split(Bp, G, dbg != nullptr, n_split, rows_per_cta);
   a.rows_per_cta = rows_per_cta;

@@ -213,7 +213,7 @@ class B200PathSolver(torch.nn.Module):
         S = dbg[:nS].reshape(2, 8, 128, NP)
         O = dbg[nS:nS + 256 * 128].reshape(256, 128)
         U = dbg[nS + 256 * 128:nS + 256 * 128 + 256 * NP].reshape(256, NP)
-        self.last_debug_cycles = dbg[nS + 256 * 128 + 256 * NP:].reshape(32, 8)[:18, :6]
+        self.last_debug_cycles = dbg[nS + 256 * 128 + 256 * NP:].reshape(32, 8)[:, :6]
         return pi, reward, S, O, U
 
     def select_best(self, reward: torch.Tensor, pi: torch.Tensor, n_aug: int):

@@ -622,6 +622,100 @@ static void part_d() {
   cudaFree(dA); cudaFree(dB); cudaFree(dD);
 }
 
+// =====================================================================================================
+// part E: do tcgen05.mma instructions issued CONCURRENTLY by several threads into the SAME accumulator lose updates?
+// Three issuing threads (warps 0-2) each add n_mma products of small integers (exact in fp32 in any order) to one
+// 32-column accumulator; a fourth configuration uses one thread for the same work.  Repeated `reps` times.
+// =====================================================================================================
+__global__ void __launch_bounds__(128) lab_shared_acc_kernel(int n_issuers, int n_mma, int reps, int* __restrict__ mismatches, float* __restrict__ last) {
+  __shared__ __align__(1024) unsigned char bsm[4096];
+  __shared__ uint64_t bar_go, bar_done;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // B [32 rows n x 32 keys] tf32: b(n, k) = (n + k) % 3 (0, 1, 2); A [128 x 32]: a(r, k) = 1 + ((r + k) & 1)
+  for (int i = tid; i < 32 * 32; i += 128) {
+    const int n = i >> 5, k = i & 31;
+    *(float*)(bsm + sw128_off(n, k >> 2) + (k & 3) * 4) = (float)((n + k) % 3);
+  }
+  if (tid == 0) { mbar_init(smem_u32(&bar_go), 128); mbar_init(smem_u32(&bar_done), n_issuers); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(128) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tb = tmem_slot;
+  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+  uint32_t a[16];
+  for (int c = 0; c < 32; c += 16) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = __float_as_uint((float)(1 + ((tid + c + j) & 1)));
+    tst16(tb + lane_addr + c, a);
+  }
+  st_wait();
+  int bad = 0;
+  for (int r = 0; r < reps; ++r) {
+    // zero the accumulator (columns 64-95), then release the issuers together
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = 0u;
+    tst16(tb + lane_addr + 64, a);
+    tst16(tb + lane_addr + 80, a);
+    st_wait();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    if (lane == 0 && warp < n_issuers) {
+      const uint32_t id = idesc(32, 2, 2);
+      const int per = n_mma / n_issuers;
+      for (int i = 0; i < per; ++i) {
+        const int ks = (i + warp) & 3;
+        mma_ts_tf32(tb + 64, tb + 8 * ks, desc_sw128(smem_u32(bsm) + 32 * ks), id, 1);
+      }
+      commit(smem_u32(&bar_done));
+    }
+    mbar_wait(smem_u32(&bar_done), r & 1);
+    fence_after();
+    // expected: sum over issued k-steps of sum_{k in step} a(r,k) b(n,k)
+    for (int c = 0; c < 32; c += 16) {
+      tld16(tb + lane_addr + 64 + c, a);
+      tld16_wait(a);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int n = c + j;
+        float ref = 0.f;
+        for (int w = 0; w < n_issuers; ++w)
+          for (int i = 0; i < n_mma / n_issuers; ++i) {
+            const int ks = (i + w) & 3;
+            for (int k = 8 * ks; k < 8 * ks + 8; ++k) ref += (float)(1 + ((tid + k) & 1)) * (float)((n + k) % 3);
+          }
+        if (__uint_as_float(a[j]) != ref) ++bad;
+        if (r == reps - 1 && tid == 5 && n == 3) { last[0] = __uint_as_float(a[j]); last[1] = ref; }
+      }
+    }
+    fence_before();
+    __syncthreads();
+  }
+  atomicAdd(mismatches, bad);
+  if (warp == 0) { fence_after(); asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(128) : "memory"); }
+}
+static void part_e() {
+  int* dM; float* dL;
+  CK(cudaMalloc(&dM, 4)); CK(cudaMalloc(&dL, 8));
+  for (int n_issuers = 1; n_issuers <= 3; n_issuers += 2) {
+    CK(cudaMemset(dM, 0, 4));
+    lab_shared_acc_kernel<<<148, 128>>>(n_issuers, 48, 200, dM, dL);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("{\"part\": \"E\", \"error\": \"%s\"}\n", cudaGetErrorString(e)); exit(1); }
+    int m; float l[2];
+    CK(cudaMemcpy(&m, dM, 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(l, dL, 8, cudaMemcpyDeviceToHost));
+    printf("{\"part\": \"E\", \"test\": \"%d thread(s) issue 48 accumulating tf32 MMAs into one accumulator, 200 rounds x 148 CTAs\", \"mismatching_elements\": %d, \"sample_value\": %.1f, \"sample_expected\": %.1f}\n",
+           n_issuers, m, l[0], l[1]);
+  }
+  cudaFree(dM); cudaFree(dL);
+}
+
 template <int VARIANT, int KPOLY>
 static void run_variant(const char* name, int reps, unsigned warp_mask = 0xffffu) {
   const int grid = 148;
@@ -651,6 +745,7 @@ int main(int argc, char** argv) {
   const int reps = argc > 1 ? atoi(argv[1]) : 200;
   part_a();
   part_d();
+  part_e();
   if (argc == 5) return 0;
   if (argc <= 3) part_c();
   if (argc == 3) return 0;

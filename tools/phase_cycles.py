@@ -23,7 +23,12 @@ first = torch.randperm(a.n, generator=g)[:a.g]
 emb = s.encode(x)
 s.rollout_debug(x, emb, src, tgt, first, None, 3)
 cyc = (s.last_debug_cycles.cpu() / (a.n - 2)).round().long().tolist()
-out = {"mode": a.mode, "N": a.n, "G": a.g, "instances": a.instances,
-       "softmax_warps": {f"t{w >> 3}.half{(w >> 2) & 1}.q{w & 3}": cyc[w] for w in range(16)},
-       "issuers": {f"tile{t}": cyc[16 + t] for t in range(2)}}
+if a.mode == "fast":     # decode_tc2.cu: 24 softmax warps (tile, key part, lane quarter), issuers in rows 24, 25
+    out = {"mode": a.mode, "N": a.n, "G": a.g, "instances": a.instances,
+           "softmax_warps": {f"t{w // 12}.part{(w % 12) >> 2}.q{w & 3}": cyc[w] for w in range(24)},
+           "issuers": {f"tile{t}": cyc[24 + t] for t in range(2)}}
+else:
+    out = {"mode": a.mode, "N": a.n, "G": a.g, "instances": a.instances,
+           "softmax_warps": {f"t{w >> 3}.half{(w >> 2) & 1}.q{w & 3}": cyc[w] for w in range(16)},
+           "issuers": {f"tile{t}": cyc[16 + t] for t in range(2)}}
 print(json.dumps(out))
