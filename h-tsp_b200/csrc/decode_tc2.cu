@@ -23,7 +23,10 @@
 //
 // Warps (896 threads): 0, 1 = MMA issuers of row tiles 0, 1 (parts served in the fixed order 0, 1, 2); 2 = operand
 // producer (ONE ring of 8 x 12 KB for both tiles: every K / V / K2 block is fetched once per CTA and step, released
-// by both issuers); 3 = TMEM allocation; 4-27 = softmax warps (tile, part, lane quarter = warp % 4).
+// by both issuers); 3 = TMEM allocation; 4-27 = softmax warps (tile, part, lane quarter = warp % 4).  Warps 3, 19, 23,
+// 27 (the last three are the softmax warps of lane quarter 3 of tile 1, which has no rows: G <= 224) are issue
+// helpers: the logit MMAs U and the first scores S_0 of key parts 1 and 2 write disjoint accumulators, so they are
+// issued by their own threads in parallel (a tcgen05.mma costs its issuing thread ~60 cycles whatever its shape).
 // Precision: logits within 1e-3 of the fp32 reference (P carries 10 mantissa bits, as a single fp16 would; V, Q, K,
 // K2 and O keep their hi/lo splits); a row whose softmax sum leaves the fp32 range returns a NaN reward.
 #include <stdlib.h>
@@ -42,6 +45,9 @@ constexpr int T2_SLOT = 12288;            // ring slot: one K_h^j (<= 5 KB), V_h
 constexpr int T2_TILE_STAGING = 65536;    // per row tile: [hi k0-63 | hi k64-127 | lo k0-63 | lo k64-127], 16 KB each
 constexpr int T2_OCOL = 416;              // O accumulator of tile t: columns 416 + 32 t .. + 31 ([P Vhi | P Vlo])
 constexpr int T2_XCOL = 480;              // exchange columns of tile t: 480 + 16 t: l[head & 1][part] (6), candidates (4), chosen (1)
+#ifndef T2_GATHER_ROWS
+#define T2_GATHER_ROWS 4                  // query rows in flight per gather round (6 spills: 23.0 vs 22.65 ms per 592 instances)
+#endif
 #ifndef T2_POLY
 #define T2_POLY 0                         // of every 16 exponentials, this many go through the FMA-pipe polynomial
 #endif
@@ -215,7 +221,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
       tc::mbar_init(TBAR(t, T2B_OFULL), 1);
       tc::mbar_init(TBAR(t, T2B_OREADY), warps_t);
       tc::mbar_init(TBAR(t, T2B_QFULL), T2_PARTS * warps_t);
-      tc::mbar_init(TBAR(t, T2B_UFULL), 1);
+      tc::mbar_init(TBAR(t, T2B_UFULL), T2_PARTS);           // one commit per key part (issuer + two helpers)
     }
     for (int s = 0; s < T2_SLOTS; ++s) {
       tc::mbar_init(RBAR(T2B_FULL + s), 1);
@@ -242,6 +248,65 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
   // K2_i^j for i = 0..3, j = 0,1,2
   constexpr int PER_STEP = 3 + 7 * 6 + 3 + 12;
 
+  // ================================================================== issue helper of (row tile t, key part j = 1, 2)
+  // S_0^j at the start of a step and the logit MMAs U^j at its end: both wait on barriers that order them after
+  // everything they depend on, and they write the score columns of part j only
+  auto run_helper = [&](const int t, const int j) {
+    if (t >= n_tiles) return;
+    const uint32_t stg = tc::smem_u32(staging) + t * T2_TILE_STAGING;
+    const uint32_t ring0 = tc::smem_u32(ring);
+    const int cbj = j == 1 ? parts.cb[1] : parts.cb[2], cej = j == 1 ? parts.cb[2] : parts.cb[3];
+    const uint32_t dSj = tmem_base + (uint32_t)(t * NP + 16 * cbj);
+    const uint32_t idK = tc::idesc_f16(16 * (cej - cbj));
+    auto land = [&](uint32_t it) {
+      const uint32_t s = it % T2_SLOTS, use = it / T2_SLOTS;
+      tc::mbar_wait(RBAR(T2B_FULL + s), use & 1);
+      tc::fence_after();
+      return s;
+    };
+    for (int step = 0; step < n_steps; ++step) {
+      const uint32_t base = (uint32_t)step * (uint32_t)PER_STEP;
+      {
+        const uint32_t sk = land(base + (uint32_t)j);              // K_0^j
+        tc::mbar_wait(TBAR(t, T2B_QFULL), step & 1);
+        tc::fence_after();
+        const uint32_t a_hi = stg >> 4, a_lo = a_hi + 2048;
+        const uint32_t b_hi = (ring0 + sk * T2_SLOT) >> 4, b_lo = b_hi + 2;
+        if (tc::elect_one()) {
+          tc::mma_ss_lo_b64(dSj, a_hi, b_hi, idK, 0);
+          tc::mma_ss_lo_b64(dSj, a_hi, b_lo, idK, 1);
+          tc::mma_ss_lo_b64(dSj, a_lo, b_hi, idK, 1);
+          tc::commit(TBAR(t, T2B_SFULL + j));
+          tc::commit(RBAR(T2B_EMPTY + sk));
+        }
+        __syncwarp();
+      }
+      for (int i = 0; i < 4; ++i) {
+        const int half = i & 1;
+        const uint32_t o_hi = (stg >> 4) + half * 1024, o_lo = o_hi + 2048;
+        // (the parity of a ring barrier only tells the current use from the previous one: a stage may be waited for
+        // once the stage eight positions earlier has been consumed by this tile -- true after OREADY, not before)
+        if (i == 0) {
+          tc::mbar_wait(TBAR(t, T2B_OREADY), step & 1);
+          tc::fence_after();
+        }
+        const uint32_t sk = land(base + (uint32_t)(48 + 3 * i + j));
+        const uint32_t kb = (ring0 + sk * T2_SLOT) >> 4;
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            tc::mma_ss_lo(dSj, o_hi + kk * 2, kb + kk * 2, idK, (i | kk) != 0);
+            if (i < 2) tc::mma_ss_lo(dSj, o_lo + kk * 2, kb + kk * 2, idK, 1);
+          }
+          tc::commit(RBAR(T2B_EMPTY + sk));
+        }
+        __syncwarp();
+      }
+      if (tc::elect_one()) tc::commit(TBAR(t, T2B_UFULL));
+      __syncwarp();
+    }
+  };
+
   if (warp < 2) {
     // ================================================================== MMA issuer of row tile t = warp
     const int t = warp;
@@ -258,7 +323,6 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
         idK[j] = tc::idesc_f16(16 * (parts.cb[j + 1] - parts.cb[j]));
         kk8[j] = 2 * (parts.cb[j + 1] - parts.cb[j]);
       }
-      uint32_t it = 0;
       long long tph[6] = {0, 0, 0, 0, 0, 0};   // DEBUG: 0 ring wait, 1 wait P, 2 issue, 3 wait Q, 4 wait O staged, 5 logits
       long long tlast = DEBUG ? clock64() : 0;
       auto tick = [&](int ph) {
@@ -268,13 +332,12 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
           tlast = now;
         }
       };
-      auto take = [&]() {                      // next ring slot, in stream order
+      auto land = [&](uint32_t it) {            // wait for stage `it` of the stream; returns its ring slot
         const uint32_t s = it % T2_SLOTS, use = it / T2_SLOTS;
         tick(2);
         tc::mbar_wait(RBAR(T2B_FULL + s), use & 1);
         tc::fence_after();
         tick(0);
-        ++it;
         return s;
       };
       auto release = [&](uint32_t s) {
@@ -308,23 +371,20 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
         __syncwarp();
       };
       for (int step = 0; step < n_steps; ++step) {
-        uint32_t k0[T2_PARTS];
-#pragma unroll
-        for (int j = 0; j < T2_PARTS; ++j) k0[j] = take();
+        const uint32_t base = (uint32_t)step * (uint32_t)PER_STEP;
+        const uint32_t k0 = land(base);           // K_0^0 (the helpers issue S_0 of parts 1 and 2)
         tc::mbar_wait(TBAR(t, T2B_QFULL), step & 1);
         tc::fence_after();
         tick(3);
-#pragma unroll
-        for (int j = 0; j < T2_PARTS; ++j) {
-          issue_S(0, j, k0[j]);
-          release(k0[j]);
-        }
+        issue_S(0, 0, k0);
+        release(k0);
         for (int h = 0; h < NH; ++h) {
           const uint32_t par = (uint32_t)(step * NH + h) & 1u;
 #pragma unroll
           for (int j = 0; j < T2_PARTS; ++j) {
-            const uint32_t sv = take();                               // V_h^j
-            const uint32_t sk = (h + 1 < NH) ? take() : 0u;           // K_{h+1}^j
+            const uint32_t nv = base + (h + 1 < NH ? (uint32_t)(3 + 6 * h + 2 * j) : (uint32_t)(45 + j));
+            const uint32_t sv = land(nv);                               // V_h^j
+            const uint32_t sk = (h + 1 < NH) ? land(nv + 1) : 0u;       // K_{h+1}^j
             tick(2);
             tc::mbar_wait(TBAR(t, T2B_PFULL + j), par);
             tc::fence_after();
@@ -337,30 +397,26 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
             }
           }
         }
-        // pointer logits U = O K2^T into the (consumed) score columns, part by part
+        // pointer logits U = O K2^T into the (consumed) score columns of part 0 (parts 1, 2: helpers)
         for (int i = 0; i < 4; ++i) {
           const int half = i & 1;                    // O / K2 columns 64*half .. +63
           const uint32_t o_hi = (stg >> 4) + half * 1024, o_lo = o_hi + 2048;
-#pragma unroll
-          for (int j = 0; j < T2_PARTS; ++j) {
-            const uint32_t sk = take();
-            if (i == 0 && j == 0) {
-              tc::mbar_wait(TBAR(t, T2B_OREADY), step & 1);
-              tc::fence_after();
-              tick(4);
-            }
-            const uint32_t kb = (ring0 + sk * T2_SLOT) >> 4;
-            const uint32_t d = dS + (uint32_t)(16 * parts.cb[j]);
-            if (tc::elect_one()) {
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                tc::mma_ss_lo(d, o_hi + kk * 2, kb + kk * 2, idK[j], (i | kk) != 0);
-                if (i < 2) tc::mma_ss_lo(d, o_lo + kk * 2, kb + kk * 2, idK[j], 1);
-              }
-              tc::commit(RBAR(T2B_EMPTY + sk));
-            }
-            __syncwarp();
+          const uint32_t sk = land(base + (uint32_t)(48 + 3 * i));
+          if (i == 0) {
+            tc::mbar_wait(TBAR(t, T2B_OREADY), step & 1);
+            tc::fence_after();
+            tick(4);
           }
+          const uint32_t kb = (ring0 + sk * T2_SLOT) >> 4;
+          if (tc::elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              tc::mma_ss_lo(dS, o_hi + kk * 2, kb + kk * 2, idK[0], (i | kk) != 0);
+              if (i < 2) tc::mma_ss_lo(dS, o_lo + kk * 2, kb + kk * 2, idK[0], 1);
+            }
+            tc::commit(RBAR(T2B_EMPTY + sk));
+          }
+          __syncwarp();
         }
         if (tc::elect_one()) tc::commit(TBAR(t, T2B_UFULL));
         __syncwarp();
@@ -407,6 +463,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
         tc::bulk_g2s(tc::smem_u32(ring + (size_t)s * T2_SLOT), imgb + off, bytes, RBAR(T2B_FULL + s));
       }
     }
+  } else if (warp == 3) {
+    run_helper(0, 1);
+  } else if (warp == 19 || warp == 23 || warp == 27) {
+    run_helper(warp == 19 ? 0 : 1, warp == 19 ? 2 : (warp == 23 ? 1 : 2));
   } else if (warp >= 4) {
     // ================================================================== softmax / state warps
     const int sw = warp - 4;
@@ -522,23 +582,23 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
       // query rows -> A tile (fp16 hi/lo, K-major SWIZZLE_128B):
       // q = ((q_graph+q_source+q_target) + q_first) + q_last (models.py:413), 1/sqrt(dk)*log2(e) folded in.
       // The three warps of a row quarter gather a third of its rows each; lane l carries columns 4l..4l+3 of every
-      // row; 4 rows (8 L2 loads) are in flight at a time.
+      // row; T2_GATHER_ROWS rows (two L2 loads each) are in flight at a time.
       auto gather_q = [&]() {
         const uint32_t sub = (uint32_t)(lane >> 4) * 16384u + (uint32_t)(lane & 1) * 8u;
         const uint32_t chunk = (uint32_t)(lane & 15) >> 1;
         const int nrows = min(32, rows_t - q * 32);
         const int r_beg = min(nrows, (32 * part) / 3), r_end = min(nrows, (32 * (part + 1)) / 3);
 #pragma unroll 1
-        for (int rr = r_beg; rr < r_end; rr += 4) {
-          float4 ql[4], qf[4];
+        for (int rr = r_beg; rr < r_end; rr += T2_GATHER_ROWS) {
+          float4 ql[T2_GATHER_ROWS], qf[T2_GATHER_ROWS];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < T2_GATHER_ROWS; ++i) {
             const int cr = __shfl_sync(0xffffffffu, cur, (rr + i) & 31), fr = __shfl_sync(0xffffffffu, first, (rr + i) & 31);
             ql[i] = __ldg((const float4*)(projb + (size_t)cr * PROJ + 2 * H) + lane);
             qf[i] = __ldg((const float4*)(projb + (size_t)fr * PROJ + 3 * H) + lane);
           }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < T2_GATHER_ROWS; ++i) {
             if (rr + i < r_end) {
               uint32_t h0, l0, h1, l1;
               split2(((qfix4.x + qf[i].x) + ql[i].x) * kScoreScale, ((qfix4.y + qf[i].y) + ql[i].y) * kScoreScale, h0, l0);

@@ -27,7 +27,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import htsp_b200  # noqa: E402,F401
 from htsp_b200 import B200PathSolver, B200RLSolver, sharding  # noqa: E402
-from htsp_b200.vec_env import B200VecEnv  # noqa: E402
+from htsp_b200.evaluate import construct_tours  # noqa: E402
 from htsp_b200.weights import synthetic_state_dict  # noqa: E402
 from htsp_b200.upper_policy import B200UpperPolicy, synthetic_policy_state_dict  # noqa: E402
 
@@ -75,51 +75,18 @@ def main():
     shard = a.shard_solver and world > 1
     g = torch.Generator().manual_seed(a.seed + (0 if shard else 7919 * rank))   # own instances per rank unless sharded
     x = torch.rand(a.envs, a.cities, 2, generator=g).to(dev)
-    env = B200VecEnv(k=40, frag_len=200, max_new_nodes=190, max_improvement_step=0)
     torch.manual_seed(a.seed)
     # warm-up on a small instance (library load, workspace allocation, first-launch overheads)
-    w = B200VecEnv(k=40, frag_len=200, max_new_nodes=190, max_improvement_step=0)
-    w.reset(torch.rand(2, 600, 2, generator=g).to(dev))
-    ws = w.state.state
-    while not w.done:
-        ws, _, _ = w.step(w.random_action() if policy is None else policy(ws), hook)
+    construct_tours(torch.rand(2, 600, 2, generator=g).to(dev), hook, policy)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    t0 = time.perf_counter()
-    state = env.reset(x)
-    torch.cuda.synchronize()
-    t_reset = time.perf_counter() - t0
-    steps = 0
-    t_pol = t_frag = t_solve = t_score = 0.0
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-    while not env.done:
-        ev[4].record()
-        act = env.random_action() if policy is None else policy(state)
-        ev[0].record()
-        active = ~env.dones
-        idx = torch.nonzero(active).squeeze(1)
-        frag, _, _, _ = env.fragments(act, active)
-        ev[1].record()
-        if shard:
-            paths, _ = sharding.solve_sharded(hook, env.x.index_select(0, idx), frag.index_select(0, idx))
-            status = torch.zeros(1, dtype=torch.int32, device=dev)
-        else:
-            paths, _, status, _ = hook.solve_device(env.x.index_select(0, idx), frag.index_select(0, idx), None)
-        ev[2].record()
-        s = env.state
-        s._paths.zero_(); s._path_len.zero_()
-        s._paths.index_copy_(0, idx, paths)
-        s._path_len.index_fill_(0, idx, env.frag_len)
-        state, _ = s.step_device(check=True)
-        ev[3].record()
-        torch.cuda.synchronize()
-        assert bool((status == 0).all())
-        t_pol += ev[4].elapsed_time(ev[0])
-        t_frag += ev[0].elapsed_time(ev[1]); t_solve += ev[1].elapsed_time(ev[2]); t_score += ev[2].elapsed_time(ev[3])
-        steps += 1
-    total = time.perf_counter() - t0
-    lens = env.state.cur_len
+    res = construct_tours(x, hook, policy, shard_solver=shard)
+    total, steps = res["seconds"], res["env_steps"]
+    bd = res["breakdown_ms"]
+    t_reset, t_pol, t_frag, t_solve, t_score = (bd["knn_reset"] / 1e3, bd["upper_policy"], bd["fragment_selection"],
+                                                bd["path_solver_hook"], bd["scoring"])
+    lens = res["lengths"].to(dev)
     if world > 1:
         tt = torch.tensor([total], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -129,9 +96,6 @@ def main():
             dist.all_gather_into_tensor(all_lens, lens.contiguous())
             lens = all_lens
     lens = lens.cpu()
-    for e in range(a.envs):
-        t = env.state.current_tour(e)
-        assert len(t) == a.cities and len(set(t)) == a.cities
     opt = OPTIMA.get(a.cities)
     n_total = a.envs if shard else a.envs * world
     if world > 1:
