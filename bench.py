@@ -43,25 +43,28 @@ def algorithmic_flops(N: int, G: int, L: int):
     return enc, reset, dec
 
 
-def k3_dram_traffic(args, B, N, G, L):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one rollout-kernel launch, from the committed
-    `ncu --set full` capture of this very command line (profiles/r01_decode_tc_x3_cfg2_dram_traffic.txt);
-    only quoted for the configuration that capture was taken on, otherwise null."""
-    if (args.mode, B, N, G, L) == ("x3", 4096, 200, 200, 6) and os.environ.get("HTSP_DECODE_IMPL") != "mma":
-        return 3.439671e9 + 0.736127e9
-    return None
-
-
-def k3_pipe_utilisation(args, N, G, L):
-    """What actually limits the rollout kernel (it is NOT the tensor pipe): pipe utilisations of the committed
-    `ncu --set full` capture of the default kernel (profiles/r01_decode_tc_x3_final_raw_summary.txt, 296
-    instances of the same shape); quoted for that kernel and shape only, otherwise null."""
-    if (args.mode, N, G, L) == ("x3", 200, 200, 6) and os.environ.get("HTSP_DECODE_IMPL") != "mma":
-        return {"issue_slots_pct": 59.2, "alu_pct": 44.5, "xu_mufu_pct": 34.4, "tensor_pct": 21.5, "fma_pct": 17.9,
-                "l2_hit_pct": 98.9, "note": "bound by the softmax between the MMAs (issue + MUFU.EX2 + dependency "
-                "latency with one instance per SM in TMEM), see DESIGN.md section 5",
-                "source": "profiles/r01_decode_tc_x3_final_raw_summary.txt"}
-    return None
+def ncu_constants(args, B, N, G, L):
+    """Numbers that only a profiler can give (DRAM traffic of one rollout-kernel launch, pipe utilisations) come from
+    profiles/r02_ncu_constants.json, written by tools/ncu_constants.py from a committed `ncu --set full` capture together
+    with the git head and the command line it was taken at; they are quoted only for the configuration of that capture
+    (mode, shape), otherwise null."""
+    path = os.path.join(ROOT, "profiles", "r02_ncu_constants.json")
+    try:
+        with open(path) as f:
+            table = json.load(f)
+    except Exception:
+        return None, None
+    impl = os.environ.get("HTSP_DECODE_IMPL", "")
+    for e in table.get("captures", []):
+        if (e.get("mode"), e.get("nodes"), e.get("group"), e.get("layers"), e.get("decode_impl", "")) == \
+                (args.mode, N, G, L, impl):
+            traffic = None
+            if e.get("dram_bytes_per_instance") is not None:
+                traffic = float(e["dram_bytes_per_instance"]) * B
+            pipes = dict(e.get("pipes", {}))
+            pipes.update({"source": e.get("source"), "git_head": e.get("git_head"), "instances": e.get("instances")})
+            return traffic, pipes
+    return None, None
 
 
 def load_peaks():
@@ -204,7 +207,7 @@ def cpu_oracle_throughput(N, G, L, sample_B, threads=None, repeats=1):
     return sample_B / best, torch.get_num_threads(), best
 
 
-def gpu_eager_port_throughput(N, G, L, sample_B=256):
+def gpu_eager_port_throughput(N, G, L, sample_B=256, allow_tf32=False):
     """Context for the ">20x the reference's single-GPU PyTorch throughput" target (BASELINE.md): the
     oracle port -- the reference's op sequence as eager PyTorch / ATen kernels, fp32, TF32 off -- on THIS
     GPU, on a bounded sample.  The port has no per-step host syncs and no O(t) list growth, so it is an
@@ -213,7 +216,7 @@ def gpu_eager_port_throughput(N, G, L, sample_B=256):
     from htsp_b200.weights import synthetic_state_dict
     from oracle import path_solver_oracle as po
     tf32 = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = allow_tf32       # torch 1.10 (the reference's pin) defaults to TF32 ON
     dev = torch.device("cuda")
     sd = {k: v.to(dev) for k, v in synthetic_state_dict(1234, L).items()}
     x = make_inputs(sample_B, N, 99).to(dev)
@@ -245,6 +248,12 @@ def run_reference(args):
     from oracle import path_solver_oracle as po
     N, G, L = args.nodes, args.group, args.layers
     sB = args.ref_sample
+    # torchrun exports OMP_NUM_THREADS=1: the reference arm uses every host core it can, whatever launched it
+    try:
+        n_threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n_threads = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n_threads))
     sd = synthetic_state_dict(1234, L)
     src = torch.zeros(sB, 1, dtype=torch.long)
     tgt = torch.full((sB, 1), N - 1, dtype=torch.long)

@@ -175,10 +175,15 @@ static bool use_tc2_kernel(int N, int G, int mode) {
 extern "C" size_t htsp_decode_workspace_bytes(int Bp, int N, int G, int mode) {
   (void)G;
   if (Bp <= 0 || N <= 0) return 0;
-  size_t b = dec_proj_bytes(Bp, N) + dec_qfix_bytes(Bp) + dec_c0_bytes(Bp, N);
+  size_t b = dec_proj_bytes(Bp, N) + dec_qfix_bytes(Bp) + dec_c0_bytes(Bp, N) + 256 /* index-range flag */;
   if (mode != HTSP_MODE_FP32) b += dec_pack_bytes(Bp, N, G) + decode_prep_tc_ws_bytes(Bp, N);
   return b;
 }
+
+static int decode_dispatch(const void* blob, int n_layers, const float* x, const float* emb, float* proj, float* qfix,
+                           float* c0, const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp, int N, int G,
+                           int mode, const int32_t* forced_pi, int32_t* pi, float* reward, float* logits_out,
+                           void* pack_ws, float* dbg, int dbg_step, const uint64_t* sample_seed, cudaStream_t s);
 
 static int decode_impl(const void* blob, int n_layers, const float* x, const float* emb,
                        const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp,
@@ -200,11 +205,25 @@ static int decode_impl(const void* blob, int n_layers, const float* x, const flo
   float* proj = (float*)w; w += dec_proj_bytes(Bp, N);
   float* qfix = (float*)w; w += dec_qfix_bytes(Bp);
   float* c0 = (float*)w;   w += dec_c0_bytes(Bp, N);
+  int32_t* idx_flag = (int32_t*)w; w += 256;
   const bool tc = mode != HTSP_MODE_FP32;
   void* pack_ws = w;
   void* prep_ws = tc ? (void*)(w + dec_pack_bytes(Bp, N, G)) : nullptr;
-  int rc = launch_decode_prep(blob, n_layers, emb, src, tgt, Bp, N, proj, qfix, c0, tc, prep_ws, s);
+  // src / tgt / first / forced_pi are used as indices: the kernels clamp them, this flags the call (NaN rewards)
+  int rc = launch_decode_validate(src, tgt, first, forced_pi, Bp, N, G, idx_flag, s);
   if (rc) return rc;
+  rc = launch_decode_prep(blob, n_layers, emb, src, tgt, Bp, N, proj, qfix, c0, tc, prep_ws, s);
+  if (rc) return rc;
+  rc = decode_dispatch(blob, n_layers, x, emb, proj, qfix, c0, src, tgt, first, Bp, N, G, mode, forced_pi, pi, reward,
+                       logits_out, pack_ws, dbg, dbg_step, sample_seed, s);
+  if (rc) return rc;
+  return launch_decode_poison(reward, (size_t)Bp * G, idx_flag, s);
+}
+
+static int decode_dispatch(const void* blob, int n_layers, const float* x, const float* emb, float* proj, float* qfix,
+                           float* c0, const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp, int N, int G,
+                           int mode, const int32_t* forced_pi, int32_t* pi, float* reward, float* logits_out,
+                           void* pack_ws, float* dbg, int dbg_step, const uint64_t* sample_seed, cudaStream_t s) {
   if (sample_seed != nullptr && (mode == HTSP_MODE_FP32 || !use_tc_kernel(N, G))) {
     set_error("htsp_decode_sample: sampling rollouts are served by the tcgen05 kernel only (tensor-core mode, "
               "17 <= N <= 208, G <= 256); got mode %d, N %d, G %d", mode, N, G);

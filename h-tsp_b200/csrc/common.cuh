@@ -117,6 +117,9 @@ void kernel_timer_end(cudaStream_t s);    // records the armed stop event and di
   } while (0)
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+// caller-supplied indices never address memory unchecked: kernels clamp them, decode_validate_kernel / K1 flag them
+// (the results of a flagged call are NaN), see ADVICE round 1
+__host__ __device__ inline int clamp_index(long long i, int n) { return i < 0 ? 0 : (i >= n ? n - 1 : (int)i); }
 
 // ---- internal launchers (one per .cu) --------------------------------------------------
 // encoder_f32.cu
@@ -147,6 +150,10 @@ size_t decode_prep_tc_ws_bytes(int Bp, int N);
 int launch_decode_prep(const void* blob, int n_layers, const float* emb, const int32_t* src,
                        const int32_t* tgt, int Bp, int N, float* proj, float* qfix, float* c0,
                        bool tensor_cores, void* tc_ws, cudaStream_t s);
+// flag[0] |= 1 if any src / tgt / first / forced_pi entry is outside [0, N); poison: reward := NaN when flagged
+int launch_decode_validate(const int32_t* src, const int32_t* tgt, const int32_t* first, const int32_t* forced_pi,
+                           int Bp, int N, int G, int32_t* flag, cudaStream_t s);
+int launch_decode_poison(float* reward, size_t n, const int32_t* flag, cudaStream_t s);
 // decode_f32.cu
 int launch_decode_f32(const float* blob, int n_layers, const float* x, const float* emb,
                       const float* proj, const float* qfix, const int32_t* src,

@@ -40,7 +40,7 @@ decode_f32_kernel(const float* __restrict__ x, const float* __restrict__ emb,
   int* cur = (int*)(vis + RB * NW);          // [RB]
   int* cnt = cur + RB;                       // [RB]
 
-  const int src = src_a[b], tgt = tgt_a[b];
+  const int src = clamp_index(src_a[b], N), tgt = clamp_index(tgt_a[b], N);
   const float* projb = proj + (size_t)b * N * PROJ;
   const float* embb = emb + (size_t)b * N * H;
 
@@ -52,7 +52,7 @@ decode_f32_kernel(const float* __restrict__ x, const float* __restrict__ emb,
     const int r = tid, g = g0 + r;
     int c = 0, n = 0;
     if (g < G) {
-      int a = first[g];
+      int a = clamp_index(first[g], N);
       tour[r * N + n++] = a; vis[r * NW + (a >> 5)] |= 1u << (a & 31); c = a;
       if (a == src) { tour[r * N + n++] = tgt; vis[r * NW + (tgt >> 5)] |= 1u << (tgt & 31); c = tgt; }
       else if (a == tgt) { tour[r * N + n++] = src; vis[r * NW + (src >> 5)] |= 1u << (src & 31); c = src; }
@@ -61,7 +61,7 @@ decode_f32_kernel(const float* __restrict__ x, const float* __restrict__ emb,
   }
   for (int i = tid; i < RB * H; i += DF_THREADS) {
     const int r = i / H, c = i % H, g = min(g0 + r, G - 1);
-    qrow[i] = __ldg(&qfix[(size_t)b * H + c]) + __ldg(&projb[(size_t)first[g] * PROJ + 3 * H + c]);
+    qrow[i] = __ldg(&qfix[(size_t)b * H + c]) + __ldg(&projb[(size_t)clamp_index(first[g], N) * PROJ + 3 * H + c]);
   }
   __syncthreads();
 
@@ -186,11 +186,13 @@ decode_f32_kernel(const float* __restrict__ x, const float* __restrict__ emb,
       }
       if (lane == 0) {
         int n = cnt[r];
-        int a = (forced_pi != nullptr) ? forced_pi[((size_t)b * G + g) * N + n] : bi;
+        int a = (forced_pi != nullptr) ? clamp_index(forced_pi[((size_t)b * G + g) * N + min(n, N - 1)], N) : bi;
         int c = a;
-        tour[r * N + n++] = a; vis[r * NW + (a >> 5)] |= 1u << (a & 31);
-        if (a == src) { tour[r * N + n++] = tgt; vis[r * NW + (tgt >> 5)] |= 1u << (tgt & 31); c = tgt; }
-        else if (a == tgt) { tour[r * N + n++] = src; vis[r * NW + (src >> 5)] |= 1u << (src & 31); c = src; }
+        // (n < N always holds for a valid tour; a flagged forced tour that repeats nodes must not write past the row)
+        if (n < N) tour[r * N + n++] = a;
+        vis[r * NW + (a >> 5)] |= 1u << (a & 31);
+        if (a == src) { if (n < N) tour[r * N + n++] = tgt; vis[r * NW + (tgt >> 5)] |= 1u << (tgt & 31); c = tgt; }
+        else if (a == tgt) { if (n < N) tour[r * N + n++] = src; vis[r * NW + (src >> 5)] |= 1u << (src & 31); c = src; }
         cur[r] = c; cnt[r] = n;
       }
     }

@@ -152,7 +152,7 @@ __global__ void __launch_bounds__((NWARPS + 1) * 32, 1) decode_mma_kernel(const 
   uint64_t* bars = (uint64_t*)(((uintptr_t)(vis + 16 * NWARPS * VSTRIDE) + 15) & ~(uintptr_t)15);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + MM_STAGES);
 
-  const int src = A.src[b], tgt = A.tgt[b];
+  const int src = clamp_index(A.src[b], A.N), tgt = clamp_index(A.tgt[b], A.N);
   const float* projb = A.proj + (size_t)b * N * PROJ;
   const unsigned char* imgb = A.img + (size_t)b * img_bytes(NP);
 
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__((NWARPS + 1) * 32, 1) decode_mma_kernel(const 
     }
   };
   // step 0: no decoder call (train_path_solver.py:256-257)
-  const int fA = A.first[min(gA, G - 1)], fB = A.first[min(gB, G - 1)];
+  const int fA = clamp_index(A.first[min(gA, G - 1)], A.N), fB = clamp_index(A.first[min(gB, G - 1)], A.N);
   if (okA) visit(visA, piA, curA, cntA, fA);
   if (okB) visit(visB, piB, curB, cntB, fB);
   __syncwarp();
@@ -483,8 +483,8 @@ __global__ void __launch_bounds__((NWARPS + 1) * 32, 1) decode_mma_kernel(const 
     }
     // ---- state update (train_path_solver.py:45-72); all quad lanes hold identical values
     __syncwarp();
-    if (okA) visit(visA, piA, curA, cntA, A.forced_pi ? A.forced_pi[((size_t)b * G + gA) * N + cntA] : idxA);
-    if (okB) visit(visB, piB, curB, cntB, A.forced_pi ? A.forced_pi[((size_t)b * G + gB) * N + cntB] : idxB);
+    if (okA) visit(visA, piA, curA, cntA, A.forced_pi ? clamp_index(A.forced_pi[((size_t)b * G + gA) * N + min(cntA, N - 1)], N) : idxA);
+    if (okB) visit(visB, piB, curB, cntB, A.forced_pi ? clamp_index(A.forced_pi[((size_t)b * G + gB) * N + min(cntB, N - 1)], N) : idxB);
     __syncwarp();
   }
   // ---- reward = -(closed tour length - fixed edge)   (train_path_solver.py:109-149)

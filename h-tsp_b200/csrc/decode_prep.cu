@@ -7,6 +7,7 @@
 //                                        used by the tensor-core modes only)
 //   qfix[b]  = (Wq_graph mean_n(emb) + Wq_source emb[src]) + Wq_target emb[tgt]   (models.py:378-392)
 //   c0[b,n]  = bc . emb[b,n]            (bias term of the folded pointer logits)
+#include <algorithm>
 #include "common.cuh"
 
 namespace htsp {
@@ -37,8 +38,8 @@ decode_prep_kernel(const float* __restrict__ emb, const float* __restrict__ Wg,
     if (lane == 0) c0[(size_t)b * N + n] = d;
   }
   *(float4*)&part[warp][4 * lane] = acc;
-  es[t] = __ldg(&e[(size_t)src[b] * H + t]);
-  et[t] = __ldg(&e[(size_t)tgt[b] * H + t]);
+  es[t] = __ldg(&e[(size_t)clamp_index(src[b], N) * H + t]);
+  et[t] = __ldg(&e[(size_t)clamp_index(tgt[b], N) * H + t]);
   __syncthreads();
   mean[t] = ((part[0][t] + part[1][t]) + (part[2][t] + part[3][t])) / (float)N;
   __syncthreads();
@@ -83,6 +84,44 @@ int launch_decode_prep(const void* blobv, int n_layers, const float* emb, const 
   if (rc) return rc;
   decode_prep_kernel<<<Bp, 128, 0, s>>>(emb, blob + d.wg, blob + d.ws, blob + d.wt, blob + d.bc,
                                         src, tgt, N, qfix, c0);
+  HTSP_CHECK_LAUNCH();
+  return HTSP_OK;
+}
+
+// Range check of everything the rollout kernels use as an index (they clamp; a flagged call returns NaN rewards)
+__global__ void decode_validate_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ tgt,
+                                       const int32_t* __restrict__ first, const int32_t* __restrict__ forced_pi,
+                                       int Bp, int N, int G, int32_t* __restrict__ flag) {
+  const size_t n_forced = forced_pi ? (size_t)Bp * G * N : 0;
+  const size_t total = (size_t)2 * Bp + G + n_forced;
+  bool bad = false;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int v;
+    if (i < (size_t)Bp) v = src[i];
+    else if (i < (size_t)2 * Bp) v = tgt[i - Bp];
+    else if (i < (size_t)2 * Bp + G) v = first[i - 2 * (size_t)Bp];
+    else v = forced_pi[i - 2 * (size_t)Bp - G];
+    bad = bad || v < 0 || v >= N;
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+__global__ void decode_poison_kernel(float* __restrict__ reward, size_t n, const int32_t* __restrict__ flag) {
+  if (*flag == 0) return;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    reward[i] = __int_as_float(0x7fc00000);
+}
+int launch_decode_validate(const int32_t* src, const int32_t* tgt, const int32_t* first, const int32_t* forced_pi,
+                           int Bp, int N, int G, int32_t* flag, cudaStream_t s) {
+  HTSP_CHECK_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t), s));
+  const size_t total = (size_t)2 * Bp + G + (forced_pi ? (size_t)Bp * G * N : 0);
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 2048);
+  decode_validate_kernel<<<blocks, 256, 0, s>>>(src, tgt, first, forced_pi, Bp, N, G, flag);
+  HTSP_CHECK_LAUNCH();
+  return HTSP_OK;
+}
+int launch_decode_poison(float* reward, size_t n, const int32_t* flag, cudaStream_t s) {
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, 1024);
+  decode_poison_kernel<<<blocks, 256, 0, s>>>(reward, n, flag);
   HTSP_CHECK_LAUNCH();
   return HTSP_OK;
 }

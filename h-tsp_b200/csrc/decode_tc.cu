@@ -439,8 +439,8 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
       const uint32_t tO = tmem_base + lane_addr + (uint32_t)(TCD_OCOL + 32 * t);
       const uint32_t tX = tmem_base + lane_addr + (uint32_t)(TCD_XCOL + 16 * t);
       unsigned char* stg = staging + t * TCD_TILE_STAGING;
-      const int src = A.src[b], tgt = A.tgt[b];
-      const int first = A.first[r0 + gc];
+      const int src = clamp_index(A.src[b], N), tgt = clamp_index(A.tgt[b], N);
+      const int first = clamp_index(A.first[r0 + gc], N);
       int32_t* pirow = A.pi + ((size_t)b * GT + r0 + gc) * N;
       const int nch = NP >> 4, n0 = nch >> 1;
       const int c_lo = half ? n0 : 0, c_hi = half ? nch : n0;
@@ -458,13 +458,13 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
       };
       // visit(a) with source<->target coupling (train_path_solver.py:45-66); only the primary records pi
       auto visit = [&](int a) {
-        if (valid && half == 0) pirow[cnt] = a;
+        if (valid && half == 0 && cnt < N) pirow[cnt] = a;
         mark(a);
         cnt++;
         cur = a;
         const int partner = (a == src) ? tgt : ((a == tgt) ? src : -1);
         if (partner >= 0) {
-          if (valid && half == 0) pirow[cnt] = partner;
+          if (valid && half == 0 && cnt < N) pirow[cnt] = partner;
           mark(partner);
           cnt++;
           cur = partner;
@@ -828,7 +828,7 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
           asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(bz), "+r"(bi)::"memory");
           if (__uint_as_float(bz) > best) idx = (int)bi;     // ties keep the primary's (lower) key
           // ---- state update (train_path_solver.py:45-72); the chosen node goes to the secondary warp
-          a = A.forced_pi ? A.forced_pi[((size_t)b * GT + r0 + gc) * N + cnt] : idx;
+          a = A.forced_pi ? clamp_index(A.forced_pi[((size_t)b * GT + r0 + gc) * N + min(cnt, N - 1)], N) : idx;
           asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tX + 8), "r"((uint32_t)a) : "memory");
           tc::st_wait();
           tc::fence_before();

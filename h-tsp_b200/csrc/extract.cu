@@ -46,12 +46,14 @@ extract_normalize_kernel(const float2* __restrict__ data, const long long* __res
   __shared__ float red[4][kExtractThreads / 32];
   float2 v[kExtractPerThread];
   float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+  bool bad = false;
 #pragma unroll
   for (int i = 0; i < kExtractPerThread; ++i) {
     int j = tid + i * kExtractThreads;
     if (j < N) {
-      long long idx = __ldg(&fragment[(size_t)b * N + j]);
-      v[i] = __ldg(&data[(size_t)b * Ntot + idx]);
+      const long long idx = __ldg(&fragment[(size_t)b * N + j]);
+      bad = bad || idx < 0 || idx >= Ntot;       // the reference's torch.gather raises; here the subproblem returns NaN
+      v[i] = __ldg(&data[(size_t)b * Ntot + clamp_index(idx, Ntot)]);
       mnx = fminf(mnx, v[i].x); mxx = fmaxf(mxx, v[i].x);
       mny = fminf(mny, v[i].y); mxy = fmaxf(mxy, v[i].y);
     }
@@ -69,7 +71,8 @@ extract_normalize_kernel(const float2* __restrict__ data, const long long* __res
   }
   // s = 0.9 / max(dx, dy): torch evaluates `scalar / tensor` as reciprocal(tensor) * scalar (two
   // roundings); x' = s*(x - min) + 0.05 as separate ops, no FMA contraction (h_tsp.py:188-191)
-  const float s = __fmul_rn(__frcp_rn(fmaxf(__fsub_rn(mxx, mnx), __fsub_rn(mxy, mny))), 0.9f);
+  float s = __fmul_rn(__frcp_rn(fmaxf(__fsub_rn(mxx, mnx), __fsub_rn(mxy, mny))), 0.9f);
+  if (__syncthreads_or(bad)) s = __int_as_float(0x7fc00000);    // out-of-range fragment ids: scale, coordinates and length are NaN
   if (tid == 0) scale[b] = s;
 #pragma unroll
   for (int i = 0; i < kExtractPerThread; ++i) {

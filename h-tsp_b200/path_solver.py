@@ -264,6 +264,11 @@ class B200PathSolver(torch.nn.Module):
         G = int(group_size)
         assert G <= self.cfg.graph_size
         n_aug = 8 if "x8Aug" in val_type else 1
+        for name, t in (("source_nodes", source_nodes), ("target_nodes", target_nodes)):
+            # host tensors are checked here (the reference's gather raises IndexError); device tensors are not read
+            # back: the kernels clamp every index and a flagged call returns NaN lengths (htsp_decode)
+            if not t.is_cuda and t.numel() and (int(t.min()) < 0 or int(t.max()) >= N):
+                raise IndexError(f"{name} outside [0, {N})")
         src = source_nodes.reshape(-1).to(dev)
         tgt = target_nodes.reshape(-1).to(dev)
         if n_aug == 8:

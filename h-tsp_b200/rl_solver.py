@@ -119,8 +119,14 @@ class B200RLSolver(LowLevelSolver):
         B, N = paths.shape
         st = host[B * N:]
         # the reference asserts these per path (h_tsp.py:218-224)
+        lens = lengths.cpu().numpy()
+        if np.isnan(lens).any():
+            # the kernels clamp every caller-supplied index and flag the call instead of faulting (the reference's
+            # torch.gather raises IndexError for the same input, h_tsp.py:176-182)
+            raise IndexError("fragment ids outside [0, Ntot) (or POMO starts outside [0, N)) in subproblem(s) "
+                             f"{np.nonzero(np.isnan(lens))[0].tolist()}")
         assert bool((st == 0).all()), f"invalid path(s) returned by the rollout, status={st.tolist()}"
-        return host[:B * N].reshape(B, N).tolist(), lengths.cpu().numpy()
+        return host[:B * N].reshape(B, N).tolist(), lens
 
 
 def make_reference_subclass(h_tsp_module, low_level_model: B200PathSolver, sample_size: int = 200):

@@ -60,3 +60,23 @@ def test_solver_refuses_without_the_cuda_library(monkeypatch, tmp_path):
     monkeypatch.setattr(_abi, "LIB_PATH", str(tmp_path / "missing.so"))
     with pytest.raises(_abi.HtspError):
         _abi.lib()
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not mounted")
+def test_make_reference_subclass_is_a_reference_rlsolver():
+    """the drop-in object must pass `isinstance(solver, h_tsp.RLSolver)` (VecEnv.step,
+    h_tsp.py:764) against the UNMODIFIED reference class and resolve `solve` to the B200 method (no CUDA needed:
+    construction and method resolution only)."""
+    h_tsp = ref_loader.load_h_tsp_module()
+    from htsp_b200 import rl_solver
+    from htsp_b200.path_solver import B200PathSolver
+
+    model = B200PathSolver.__new__(B200PathSolver)      # no device work: only the type is inspected
+    solver = rl_solver.make_reference_subclass(h_tsp, model, sample_size=1)
+    assert isinstance(solver, h_tsp.RLSolver) and isinstance(solver, h_tsp.LowLevelSolver)
+    assert isinstance(solver, rl_solver.B200RLSolver)
+    mro = type(solver).__mro__
+    assert mro.index(rl_solver.B200RLSolver) < mro.index(h_tsp.RLSolver)
+    assert type(solver).solve is rl_solver.B200RLSolver.solve
+    assert type(solver).solve is not h_tsp.RLSolver.solve
+    assert solver._sample_size == 2 and solver._solver_model is model      # max(sample_size, 2), h_tsp.py:168

@@ -103,7 +103,9 @@ def test_teacher_forced_logits_match_golden_n200(solvers, golden, mode):
                                     (1, 230, 230),
                                     # tcgen05 kernel edges: largest N (NP = 208, second row tile of 80 rows),
                                     # odd chunk counts (NP = 144), smallest NP (32), one row, G = 129
-                                    (1, 208, 208), (2, 130, 130), (3, 17, 17), (2, 64, 1), (1, 150, 129)])
+                                    (1, 208, 208), (2, 130, 130), (3, 17, 17), (2, 64, 1), (1, 150, 129),
+                                    # the benchmark's own shape (config 2: N = G = 200), two instances
+                                    (2, 200, 200)])
 def test_teacher_forced_logits_match_oracle(solvers, sd6, mode, Bp, N, G):
     s = solvers[mode]
     g = torch.Generator().manual_seed(N + G)
@@ -146,8 +148,10 @@ def test_greedy_rollout_is_tie_aware_identical(solvers, sd6, mode, Bp, N, G):
         free = po.rollout(sd6, x, src, tgt, first)
     same = (free.pi == pi).all(dim=2).float().mean().item()
     print(f"[{mode}] rows identical to the oracle's free run: {same:.3f}; worst regret {worst:.2e}")
-    if mode == "fp32":      # longer rollouts meet more near-ties (each bounded by the regret check above)
-        assert same >= (0.9 if N <= 200 else 0.5)
+    # longer rollouts meet more near-ties (each bounded by the regret check above); the floors are below the
+    # measured fractions (fp32 0.9-1.0; x3 0.75-1.0; fast 0.5-1.0, 0.35 at N = 500 on the mma.sync kernel)
+    floor = {"fp32": 0.9 if N <= 200 else 0.5, "x3": 0.7 if N <= 200 else 0.4, "fast": 0.4 if N <= 200 else 0.2}[mode]
+    assert same >= floor, f"{mode}: only {same:.3f} of the rows follow the oracle's free run"
     # reward of the tours actually produced, recomputed by the oracle: 1e-5 relative
     assert rel_err(reward, forced.reward) <= 1e-5
 
@@ -200,10 +204,9 @@ def test_peaked_policies(built_lib, mode, seed, n_layers):
     assert torch.equal(torch.isinf(got), torch.isinf(want))
     err = float((got[fin] - want[fin]).abs().max())
     # operand magnitudes are 3-5x the seed-1234/6-layer case and the fp32-class bounds scale with them
-    # (measured: fp32 6.5e-5, x3 1.1e-4 / 3.4e-4).  `fast` on the tcgen05 kernel (single-fp16 softmax
-    # probabilities) measures 7.8e-4 / 9.6e-4 here: inside the 1e-3 budget but close to it, which is why x3 is
-    # the default (the mma.sync kernel's `fast`, single-fp16 glimpse scores, reaches 6e-3 / 9e-3 on these weights).
-    tol = {"fp32": 2.5e-4, "x3": 5e-4, "fast": 2e-3}[mode]
+    # (measured: fp32 6.5e-5, x3 1.1e-4 / 3.4e-4).  `fast` (decode_tc2.cu: softmax probabilities with 10 mantissa
+    # bits, kind::tf32) must stay inside north_star's 1e-3 for bf16-class arithmetic on these weights too.
+    tol = {"fp32": 2.5e-4, "x3": 5e-4, "fast": 1e-3}[mode]
     print(f"[{mode}] seed {seed} L={n_layers}: max |z| {float(want[fin].abs().max()):.3f}, max |dz| = {err:.2e}")
     assert err <= tol
     pi2, reward2, _ = s.rollout(xc, emb, src, tgt, first)
@@ -371,7 +374,18 @@ def test_l3_custom_endpoints(built_lib, golden):
     x = T(golden["l3_x"])
     length, pi = s(x.cuda(), T(golden["l3_src"]).long().cuda(), T(golden["l3_tgt"]).long().cuda(),
                    val_type="noAug_nTraj", return_pi=True, group_size=20)
-    np.testing.assert_allclose(length.cpu().numpy(), golden["l3_length"], rtol=2e-3)
+    if not np.allclose(length.cpu().numpy(), golden["l3_length"], rtol=1e-5, atol=0):
+        # another equally greedy tour: every decision is an oracle arg-max within the fp32 tolerance and the returned
+        # result is the reference's selection rule applied to those rollouts
+        first = T(golden["l3_first"]).long()
+        src_l, tgt_l = T(golden["l3_src"]).long().reshape(-1), T(golden["l3_tgt"]).long().reshape(-1)
+        xc = x.cuda()
+        r_pi, r_rew, _ = s.rollout(xc, s.encode(xc), src_l, tgt_l, first)
+        with torch.no_grad():
+            tie_aware_check(sd3, x, src_l, tgt_l, first, r_pi.cpu().long(), 2 * LOGIT_TOL["fp32"])
+        sel_r, sel_pi = po.select_best(r_rew.cpu(), r_pi.cpu().long(), "noAug_nTraj")
+        np.testing.assert_allclose(length.cpu().numpy(), -sel_r.numpy(), rtol=1e-6)
+        assert np.array_equal(pi.cpu().numpy(), sel_pi.squeeze().numpy())
     for b in range(2):
         p = pi[b].cpu().tolist()
         assert sorted(p) == list(range(20))
@@ -382,7 +396,7 @@ def test_l3_custom_endpoints(built_lib, golden):
 
 # ---------------------------------------------------------------- hook
 @pytest.mark.parametrize("mode", MODES)
-def test_hook_matches_golden(solvers, golden, mode):
+def test_hook_matches_golden(solvers, golden, sd6, mode):
     from htsp_b200 import B200RLSolver, FragmentBuffer
     s = solvers[mode]
     hook = B200RLSolver(s, sample_size=6)
@@ -399,10 +413,105 @@ def test_hook_matches_golden(solvers, golden, mode):
     frag = golden["hook_fragment"]
     for b, p in enumerate(paths):
         assert p[0] == frag[b][0] and p[-1] == frag[b][-1] and sorted(p) == sorted(frag[b].tolist())
-    if np.array_equal(np.array(paths), golden["hook_paths"]):
-        np.testing.assert_allclose(lens, golden["hook_lengths"], rtol=1e-5)
-    else:
-        np.testing.assert_allclose(lens, golden["hook_lengths"], rtol=2e-3)
+    same = [list(p) == list(q) for p, q in zip(paths, golden["hook_paths"].tolist())]
+    if any(same):        # untouched subproblems agree with the reference to 1e-5
+        np.testing.assert_allclose(lens[np.array(same)], golden["hook_lengths"][np.array(same)], rtol=1e-5)
+    if not all(same):
+        # A near-tie sent a rollout down another branch.  Prove that the hook still returned what the reference's
+        # own rules give for equally greedy rollouts: every decision of every rollout is an oracle arg-max within
+        # the mode's tolerance, and the selected path is select_best + orient_path of those rollouts.
+        data, frag = T(golden["hook_data"]), T(golden["hook_fragment"]).long()
+        first = T(golden["hook_first"]).long()
+        x_new, scale = po.extract_normalize(data, frag)
+        xa = po.augment_8fold(x_new)
+        Ba, N = xa.shape[0], xa.shape[1]
+        sa, ta = torch.zeros(Ba, dtype=torch.long), torch.full((Ba,), N - 1)
+        xc = xa.cuda()
+        r_pi, r_rew, _ = s.rollout(xc, s.encode(xc), sa, ta, first)
+        with torch.no_grad():
+            tie_aware_check(sd6, xa, sa, ta, first, r_pi.cpu().long(), 2 * LOGIT_TOL[mode])
+        sel_r, sel_pi = po.select_best(r_rew.cpu(), r_pi.cpu().long(), "x8Aug_2Traj")
+        for b in range(len(paths)):
+            want = frag[b][torch.from_numpy(po.orient_path(sel_pi.reshape(len(paths), N)[b].numpy()).copy())].tolist()
+            assert paths[b] == want
+            np.testing.assert_allclose(lens[b], float(-sel_r.reshape(-1)[b] / scale.reshape(-1)[b]), rtol=1e-5)
+
+
+def test_drop_in_subclass_is_dispatched_like_vecenv_step(solvers, golden):
+    """VecEnv.step picks the lower-level solver by `isinstance(solver, RLSolver)` and calls
+    `solver.solve(data, fragments, frag_buffer)` (h_tsp.py:764-767).  make_reference_subclass must return an object
+    that passes that test against the module it is given and resolves `solve` to the B200 method.  The reference
+    module itself cannot travel to the GPU box: a stand-in module with the reference's RLSolver surface
+    (h_tsp.py:165-228) is used here; tests/test_host_logic.py checks the same against the real h_tsp.RLSolver."""
+    import types
+    from htsp_b200 import B200RLSolver, FragmentBuffer, make_reference_subclass
+    from htsp_b200.rl_solver import LowLevelSolver as B200Base
+
+    class RefLowLevelSolver:                      # h_tsp.py:34-37
+        def solve(self, x, fragment):
+            raise NotImplementedError
+
+    class RefRLSolver(RefLowLevelSolver):         # h_tsp.py:165-169
+        def __init__(self, low_level_model, sample_size=200):
+            self._solver_model = low_level_model
+            self._sample_size = max(sample_size, 2)
+
+        def solve(self, data, fragment, frag_buffer):
+            raise AssertionError("the reference's CPU/PyTorch path must not run")
+
+    h_tsp = types.SimpleNamespace(RLSolver=RefRLSolver, LowLevelSolver=RefLowLevelSolver)
+    s = solvers["x3"]
+    solver = make_reference_subclass(h_tsp, s, sample_size=6)
+    assert isinstance(solver, h_tsp.RLSolver) and isinstance(solver, B200RLSolver) and isinstance(solver, B200Base)
+    assert type(solver).solve is B200RLSolver.solve and solver._sample_size == 6
+    fb = FragmentBuffer(8, 50, 2)
+    s.first_action_override = T(golden["hook_first"])
+    try:
+        data, fragments = T(golden["hook_data"]).cuda(), T(golden["hook_fragment"]).cuda()
+        if isinstance(solver, h_tsp.RLSolver):                       # the dispatch of h_tsp.py:764
+            paths, lens = solver.solve(data, fragments, fb)
+        else:
+            raise AssertionError("not dispatched as an RLSolver")
+        want_paths, want_lens = B200RLSolver(s, sample_size=6).solve(data, fragments, None)
+    finally:
+        s.first_action_override = None
+    assert paths == want_paths and np.array_equal(lens, want_lens)
+    assert np.array_equal(fb.frag_buffer[:3].numpy(), golden["hook_x_new"])
+
+
+def test_out_of_range_indices_do_not_fault(solvers):
+    """caller-supplied indices (fragment ids, endpoints, POMO starts, forced tours) must never address
+    memory unchecked.  The kernels clamp them and flag the call: the hook raises IndexError (as the reference's
+    torch.gather does), the raw rollout returns NaN rewards, and the CUDA context stays usable."""
+    from htsp_b200 import B200RLSolver
+    s = solvers["x3"]
+    g = torch.Generator().manual_seed(3)
+    data = torch.rand(2, 300, 2, generator=g)
+    frag = torch.stack([torch.randperm(300, generator=g)[:40] for _ in range(2)])
+    hook = B200RLSolver(s, sample_size=4)
+    bad = frag.clone()
+    bad[1, 7] = 300                                   # one past the end
+    with pytest.raises(IndexError):
+        hook.solve(data.cuda(), bad.cuda(), None)
+    bad[1, 7] = -5
+    with pytest.raises(IndexError):
+        hook.solve(data.cuda(), bad.cuda(), None)
+    paths, lens = hook.solve(data.cuda(), frag.cuda(), None)          # the context is still fine
+    assert np.isfinite(lens).all() and sorted(paths[1]) == sorted(frag[1].tolist())
+    x = torch.rand(2, 40, 2, generator=g).cuda()
+    emb = s.encode(x)
+    src, tgt = torch.zeros(2, dtype=torch.long), torch.full((2,), 39)
+    for mode in ("fp32", "x3", "fast"):
+        m = solvers[mode]
+        for first in (torch.tensor([3, 40, 5]), torch.tensor([-1, 2, 3])):
+            pi, rew, _ = m.rollout(x, emb, src, tgt, first)
+            assert bool(torch.isnan(rew).all()) and int(pi.min()) >= 0 and int(pi.max()) < 40
+        pi, rew, _ = m.rollout(x, emb, torch.tensor([0, 41]), tgt, torch.tensor([3, 4, 5]))
+        assert bool(torch.isnan(rew).all())
+        pi, rew, _ = m.rollout(x, emb, src, tgt, torch.tensor([3, 4, 5]))
+        assert bool(torch.isfinite(rew).all())
+    with pytest.raises(IndexError):
+        s(x, torch.tensor([[0], [40]]), tgt.reshape(2, 1), val_type="noAug_nTraj", group_size=4)
 
 
 def test_hook_b1_and_training_flag(solvers):
@@ -600,10 +709,14 @@ def test_tcgen05_kernel_intermediates(solvers, sd6, mode, N, G, step):
     P = torch.softmax((Sref / log2e).masked_fill(vis[None], float("-inf")), dim=-1)
     Oref = torch.einsum("hgn,nhd->ghd", P, V.reshape(N, 8, 16)).reshape(G, 128)
     Uref = Oref @ K2.T
-    # scores / outputs are O(1..10): split-fp16 products (x3) keep ~1e-5; `fast` rounds Q and K of the
-    # glimpse scores to single fp16 (2^-11 relative)
-    tol_s = {"x3": 5e-5, "fast": 2e-2}[mode]
-    tol_o = {"x3": 5e-5, "fast": 5e-3}[mode]
+    # scores / outputs are O(1..10): split-fp16 products keep ~1e-5 in both modes; `fast` (decode_tc2.cu) centres
+    # the keys of every head (S differs from the reference's by a per-row constant that the softmax cancels) and
+    # carries the probabilities with 10 mantissa bits (kind::tf32 reads the top 19 bits of the fp32 words)
+    if mode == "fast" and N >= 33:
+        Sgot = Sgot - Sgot.mean(dim=-1, keepdim=True)
+        Sref = Sref - Sref.mean(dim=-1, keepdim=True)
+    tol_s = {"x3": 5e-5, "fast": 1e-4}[mode]
+    tol_o = {"x3": 5e-5, "fast": 2e-3}[mode]
     assert float((Sgot - Sref).abs().max()) <= tol_s
     assert float((O[:G].double() - Oref).abs().max()) <= tol_o
     assert float((U[:G, :N].double() - Uref).abs().max()) <= 4 * tol_o
