@@ -458,13 +458,13 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
       };
       // visit(a) with source<->target coupling (train_path_solver.py:45-66); only the primary records pi
       auto visit = [&](int a) {
-        if (valid && half == 0 && cnt < N) pirow[cnt] = a;
+        if (valid && half == 0 && (!(LOGITS || DEBUG) || cnt < N)) pirow[cnt] = a;     // (a forced tour may repeat nodes)
         mark(a);
         cnt++;
         cur = a;
         const int partner = (a == src) ? tgt : ((a == tgt) ? src : -1);
         if (partner >= 0) {
-          if (valid && half == 0 && cnt < N) pirow[cnt] = partner;
+          if (valid && half == 0 && (!(LOGITS || DEBUG) || cnt < N)) pirow[cnt] = partner;
           mark(partner);
           cnt++;
           cur = partner;
@@ -828,7 +828,7 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
           asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(bz), "+r"(bi)::"memory");
           if (__uint_as_float(bz) > best) idx = (int)bi;     // ties keep the primary's (lower) key
           // ---- state update (train_path_solver.py:45-72); the chosen node goes to the secondary warp
-          a = A.forced_pi ? clamp_index(A.forced_pi[((size_t)b * GT + r0 + gc) * N + min(cnt, N - 1)], N) : idx;
+          a = ((LOGITS || DEBUG) && A.forced_pi) ? clamp_index(A.forced_pi[((size_t)b * GT + r0 + gc) * N + min(cnt, N - 1)], N) : idx;   // teacher forcing: LOGITS / DEBUG kernels only
           asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tX + 8), "r"((uint32_t)a) : "memory");
           tc::st_wait();
           tc::fence_before();
@@ -973,7 +973,7 @@ int launch_decode_tc(const float* x, const float* proj, const float* qfix, const
     return split ? launch_tcd<false, false, false, true, true>(a, Bp, s) : launch_tcd<false, false, false, false, true>(a, Bp, s);
   }
   if (dbg != nullptr) return a.fast ? launch_tcd<false, true, true, false>(a, Bp, s) : launch_tcd<false, true, false, false>(a, Bp, s);
-  if (logits_out != nullptr) {
+  if (logits_out != nullptr || forced_pi != nullptr) {     // teacher forcing is served by the LOGITS kernels
     if (a.fast) return split ? launch_tcd<true, false, true, true>(a, Bp, s) : launch_tcd<true, false, true, false>(a, Bp, s);
     return split ? launch_tcd<true, false, false, true>(a, Bp, s) : launch_tcd<true, false, false, false>(a, Bp, s);
   }

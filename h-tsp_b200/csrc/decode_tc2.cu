@@ -507,13 +507,13 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
       };
       // visit(a) with source<->target coupling (train_path_solver.py:45-66); only part 0 records pi
       auto visit = [&](int a) {
-        if (valid && part == 0 && cnt < N) pirow[cnt] = a;
+        if (valid && part == 0 && (!(LOGITS || DEBUG) || cnt < N)) pirow[cnt] = a;     // (a forced tour may repeat nodes)
         mark(a);
         cnt++;
         cur = a;
         const int partner = (a == src) ? tgt : ((a == tgt) ? src : -1);
         if (partner >= 0) {
-          if (valid && part == 0 && cnt < N) pirow[cnt] = partner;
+          if (valid && part == 0 && (!(LOGITS || DEBUG) || cnt < N)) pirow[cnt] = partner;
           mark(partner);
           cnt++;
           cur = partner;
@@ -795,7 +795,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
           if (__uint_as_float(z1) > best) { best = __uint_as_float(z1); idx = (int)i1; }     // ties keep the lower part's key
           if (__uint_as_float(z2) > best) { best = __uint_as_float(z2); idx = (int)i2; }
           // ---- state update (train_path_solver.py:45-72); the chosen node goes to the other two warps
-          a = A.forced_pi ? clamp_index(A.forced_pi[((size_t)b * GT + r0 + gc) * N + min(cnt, N - 1)], N) : idx;
+          a = ((LOGITS || DEBUG) && A.forced_pi) ? clamp_index(A.forced_pi[((size_t)b * GT + r0 + gc) * N + min(cnt, N - 1)], N) : idx;   // teacher forcing: LOGITS / DEBUG kernels only
           if ((unsigned)a >= (unsigned)N) a = cur;     // a NaN row has no candidate: stay in range (the row is flagged)
           asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tX + 10), "r"((uint32_t)a) : "memory");
           tc::st_wait();
@@ -932,7 +932,8 @@ int launch_decode_tc2(const float* x, const float* proj, const float* qfix, cons
   const bool split = n_split > 1;
   if (sample_seed != nullptr) return split ? launch_t2<false, false, true, true>(a, Bp, s) : launch_t2<false, false, false, true>(a, Bp, s);
   if (dbg != nullptr) return launch_t2<false, true, false>(a, Bp, s);
-  if (logits_out != nullptr) return split ? launch_t2<true, false, true>(a, Bp, s) : launch_t2<true, false, false>(a, Bp, s);
+  if (logits_out != nullptr || forced_pi != nullptr)      // teacher forcing is served by the LOGITS kernels
+    return split ? launch_t2<true, false, true>(a, Bp, s) : launch_t2<true, false, false>(a, Bp, s);
   return split ? launch_t2<false, false, true>(a, Bp, s) : launch_t2<false, false, false>(a, Bp, s);
 }
 

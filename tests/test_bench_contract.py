@@ -25,6 +25,18 @@ def test_reference_arm_prints_the_contract_line():
     assert e2e == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
+def test_reference_arm_uses_every_host_core_under_torchrun_defaults():
+    """torchrun exports OMP_NUM_THREADS=1: round 1's N > 1 reference numbers were one-thread artefacts.  The reference
+    arm sets its own thread count."""
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--ref-sample", "2", "--nodes", "40", "--group", "8", "--layers", "2"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][0])
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+
+
 def test_b200_arm_refuses_without_a_gpu():
     """No CPU fallback: on a box without CUDA the product arm must fail loudly, not time something else."""
     import torch
