@@ -195,12 +195,14 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
   const int n_steps = N - 2;
   const int n_tiles = G > 128 ? 2 : 1;
   const T2Parts parts = t2_parts(NP);
+  constexpr int PER_STEP = 3 + 7 * 6 + 3 + 12;   // ring stages of one decode step
 
   unsigned char* staging = smem;                                         // 2 x 64 KB
   unsigned char* ring = smem + 2 * T2_TILE_STAGING;                      // T2_SLOTS x 12 KB
   float* c0s = (float*)(ring + (size_t)T2_SLOTS * T2_SLOT);              // [NP]
   uint64_t* bars = (uint64_t*)(c0s + NP);
   uint32_t* tmem_slot = (uint32_t*)(bars + T2B_TOTAL);
+  uint2* stage_tab = (uint2*)(tmem_slot + 4);                            // [PER_STEP] (image offset, bytes) of a step's stages
   const uint32_t bar0 = tc::smem_u32(bars);
   auto TBAR = [&](int t, int i) { return bar0 + 8u * (uint32_t)(t * T2B_PER_TILE + i); };
   auto RBAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
@@ -232,6 +234,36 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
   // zero the A tiles (rows that never receive a query must hold finite values)
   for (int i = tid; i < 2 * T2_TILE_STAGING / 16; i += T2_THREADS) ((uint4*)staging)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < NP; i += T2_THREADS) c0s[i] = i < N ? __ldg(&A.c0[(size_t)b * N + i]) : 0.f;
+  if (tid < PER_STEP) {
+    // stages of one decode step in stream order: K_0^{0,1,2}; per head h: V_h^j, K_{h+1}^j (h < 7) for j = 0,1,2;
+    // K2_i^j for i = 0..3, j = 0,1,2 -- (offset into the instance's image, bytes), looked up by the producer
+    const size_t szk = t2_szk(NP), szv = t2_szv(NP), szk2 = t2_szk2(NP);
+    const int c1 = parts.cb[1], c2 = parts.cb[2], c3 = parts.cb[3];
+    auto keys_of = [&](int j) { return (uint32_t)(16 * (j == 0 ? c1 : (j == 1 ? c2 - c1 : c3 - c2))); };
+    auto krow_of = [&](int j) { return (uint32_t)(16 * (j == 0 ? 0 : (j == 1 ? c1 : c2))); };
+    auto vbytes_of = [&](int j) { return (uint32_t)t2_vblocks((int)keys_of(j)) * 4096u; };
+    auto voff_of = [&](int j) { return (size_t)((j > 0 ? vbytes_of(0) : 0u) + (j > 1 ? vbytes_of(1) : 0u)); };
+    const int i = tid;
+    size_t off;
+    uint32_t bytes;
+    if (i < 3) {                                   // K_0^j
+      off = (size_t)krow_of(i) * 64;
+      bytes = keys_of(i) * 64u;
+    } else if (i < 3 + 42) {                       // heads 0..6: V_h^j, K_{h+1}^j
+      const int r = i - 3, h = r / 6, e = r - 6 * h, j = e >> 1;
+      if ((e & 1) == 0) { off = 8 * szk + (size_t)h * szv + voff_of(j); bytes = vbytes_of(j); }
+      else { off = (size_t)(h + 1) * szk + (size_t)krow_of(j) * 64; bytes = keys_of(j) * 64u; }
+    } else if (i < 48) {                           // head 7: V_7^j
+      const int j = i - 45;
+      off = 8 * szk + (size_t)7 * szv + voff_of(j);
+      bytes = vbytes_of(j);
+    } else {                                       // K2_i^j
+      const int r = i - 48, blk = r / 3, j = r - 3 * blk;
+      off = 8 * szk + 8 * szv + (size_t)blk * szk2 + (size_t)krow_of(j) * 128;
+      bytes = keys_of(j) * 128u;
+    }
+    stage_tab[i] = make_uint2((uint32_t)off, bytes);
+  }
   if (warp == 3) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)),
                  "r"(512)
@@ -246,7 +278,6 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
 
   // stages of one decode step in stream order: K_0^{0,1,2}; per head h: V_h^j, K_{h+1}^j (h < 7) for j = 0,1,2;
   // K2_i^j for i = 0..3, j = 0,1,2
-  constexpr int PER_STEP = 3 + 7 * 6 + 3 + 12;
 
   // ================================================================== issue helper of (row tile t, key part j = 1, 2)
   // S_0^j at the start of a step and the logit MMAs U^j at its end: both wait on barriers that order them after
@@ -430,37 +461,15 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
   } else if (warp == 2) {
     // ================================================================== operand producer (one stream for both tiles)
     if (lane == 0) {
-      const size_t szk = t2_szk(NP), szv = t2_szv(NP), szk2 = t2_szk2(NP);
-      const int c1 = parts.cb[1], c2 = parts.cb[2], c3 = parts.cb[3];
-      auto keys_of = [&](int j) { return (uint32_t)(16 * (j == 0 ? c1 : (j == 1 ? c2 - c1 : c3 - c2))); };
-      auto krow_of = [&](int j) { return (uint32_t)(16 * (j == 0 ? 0 : (j == 1 ? c1 : c2))); };
-      auto vbytes_of = [&](int j) { return (uint32_t)t2_vblocks((int)keys_of(j)) * 4096u; };
-      auto voff_of = [&](int j) { return (size_t)((j > 0 ? vbytes_of(0) : 0u) + (j > 1 ? vbytes_of(1) : 0u)); };
       const uint32_t total = (uint32_t)n_steps * (uint32_t)PER_STEP;
+      uint32_t i = 0;
       for (uint32_t it = 0; it < total; ++it) {
         const uint32_t s = it % T2_SLOTS, use = it / T2_SLOTS;
+        const uint2 st = stage_tab[i];
+        i = (i + 1 == (uint32_t)PER_STEP) ? 0u : i + 1;
         tc::mbar_wait(RBAR(T2B_EMPTY + s), (use & 1) ^ 1);
-        const int i = (int)(it % (uint32_t)PER_STEP);
-        size_t off;
-        uint32_t bytes;
-        if (i < 3) {                                   // K_0^j
-          off = (size_t)krow_of(i) * 64;
-          bytes = keys_of(i) * 64u;
-        } else if (i < 3 + 42) {                       // heads 0..6: V_h^j, K_{h+1}^j
-          const int r = i - 3, h = r / 6, e = r - 6 * h, j = e >> 1;
-          if ((e & 1) == 0) { off = 8 * szk + (size_t)h * szv + voff_of(j); bytes = vbytes_of(j); }
-          else { off = (size_t)(h + 1) * szk + (size_t)krow_of(j) * 64; bytes = keys_of(j) * 64u; }
-        } else if (i < 48) {                           // head 7: V_7^j
-          const int j = i - 45;
-          off = 8 * szk + (size_t)7 * szv + voff_of(j);
-          bytes = vbytes_of(j);
-        } else {                                       // K2_i^j
-          const int r = i - 48, blk = r / 3, j = r - 3 * blk;
-          off = 8 * szk + 8 * szv + (size_t)blk * szk2 + (size_t)krow_of(j) * 128;
-          bytes = keys_of(j) * 128u;
-        }
-        tc::mbar_expect_tx(RBAR(T2B_FULL + s), bytes);
-        tc::bulk_g2s(tc::smem_u32(ring + (size_t)s * T2_SLOT), imgb + off, bytes, RBAR(T2B_FULL + s));
+        tc::mbar_expect_tx(RBAR(T2B_FULL + s), st.y);
+        tc::bulk_g2s(tc::smem_u32(ring + (size_t)s * T2_SLOT), imgb + st.x, st.y, RBAR(T2B_FULL + s));
       }
     }
   } else if (warp == 3) {
@@ -560,8 +569,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
               // round to the 19 bits the tensor core reads (it would truncate: a mantissa-dependent bias that the
               // normalisation does not cancel -- 1.1e-3 instead of 0.9e-3 on the 12-layer stress weights) and sum
               // exactly those values
-              s[j] = (__float_as_uint(p0) + 0x1000u) & 0xffffe000u;
-              s[j + 1] = (__float_as_uint(p1) + 0x1000u) & 0xffffe000u;
+              s[j] = (__float_as_uint(p0) + 0x1000u) & 0xffffe000u;     // (cvt.rna.tf32.f32 does the same in one
+              s[j + 1] = (__float_as_uint(p1) + 0x1000u) & 0xffffe000u; // instruction, but on the MUFU pipe: 25.1 vs 23.8 ms)
               acc = __fadd2_rn(acc, make_float2(__uint_as_float(s[j]), __uint_as_float(s[j + 1])));
             }
             tst<16>(tS + 16 * c, s);
@@ -885,7 +894,7 @@ static void t2_choose_split(int Bp, int G, bool debug, int& split, int& rows_per
 
 template <bool LOGITS, bool DEBUG, bool SPLIT, bool SAMPLE = false>
 static int launch_t2(const T2Args& a, int Bp, cudaStream_t s) {
-  const size_t smem = (size_t)2 * T2_TILE_STAGING + (size_t)T2_SLOTS * T2_SLOT + (size_t)a.NP * 4 + T2B_TOTAL * 8 + 16;
+  const size_t smem = (size_t)2 * T2_TILE_STAGING + (size_t)T2_SLOTS * T2_SLOT + (size_t)a.NP * 4 + T2B_TOTAL * 8 + 16 + (3 + 7 * 6 + 3 + 12) * 8;
   if (smem > 227 * 1024) {
     set_error("decode_tc2: N=%d needs %zu bytes of shared memory", a.N, smem);
     return HTSP_ERR_UNSUPPORTED;

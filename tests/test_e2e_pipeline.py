@@ -60,6 +60,7 @@ def test_tsp1000_construction_matches_the_reference_pipeline(built_lib, e2e_gold
           f"{res['env_steps']} vs {int(e2e_golden['steps_run0'])} env steps")
     # same number of environment steps (the construction schedule is a function of max_new_nodes only)
     assert res["env_steps"] == int(e2e_golden["steps_run0"])
-    # Tolerance: random-init policies are near-uniform, so one flipped near-tie reroutes a 200-city fragment; measured
-    # differences are 0 ... 3 % per instance.  The bound is 6 % per instance and 3 % on the mean of the four.
-    assert rel.max() <= 0.06 and abs(got.mean() - want.mean()) / want.mean() <= 0.03
+    # Tolerance: random-init policies are near-uniform, so one flipped near-tie reroutes a 200-city fragment.  Measured
+    # (x3 and fast alike): two of the four tours have exactly the reference's length, the others differ by 0.10 % and
+    # 0.18 %, the mean by 0.07 %.  The bound is 2 % per instance and 1 % on the mean of the four.
+    assert rel.max() <= 0.02 and abs(got.mean() - want.mean()) / want.mean() <= 0.01
