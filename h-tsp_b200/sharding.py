@@ -55,8 +55,15 @@ def solve_sharded(solver, data: torch.Tensor, fragment: torch.Tensor):
     rank = dist.get_rank() if dist.is_initialized() else 0
     lo, hi = shard_range(B, rank, world)
     paths, lengths, status, _ = solver.solve_device(data[lo:hi], fragment[lo:hi], None)
-    assert bool((status == 0).all())
-    return gather_tours(paths, lengths, B)
+    # a failed shard must not leave the other ranks waiting in the collective: the status travels with the lengths
+    # (NaN) and every rank raises after the all-gather
+    lengths = torch.where(status == 0, lengths, torch.full_like(lengths, float("nan")))
+    all_paths, all_len = gather_tours(paths, lengths, B)
+    bad = torch.isnan(all_len)
+    if bool(bad.any()):
+        raise RuntimeError(f"invalid path(s) or out-of-range fragment ids in subproblem(s) "
+                           f"{torch.nonzero(bad).reshape(-1).tolist()} (reported on every rank)")
+    return all_paths, all_len
 
 
 # ---- B < ranks: shard the 8 augmentations ---------------------------------
