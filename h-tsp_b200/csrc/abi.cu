@@ -183,14 +183,15 @@ extern "C" size_t htsp_decode_workspace_bytes(int Bp, int N, int G, int mode) {
 static int decode_dispatch(const void* blob, int n_layers, const float* x, const float* emb, float* proj, float* qfix,
                            float* c0, const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp, int N, int G,
                            int mode, const int32_t* forced_pi, int32_t* pi, float* reward, float* logits_out,
-                           void* pack_ws, float* dbg, int dbg_step, const uint64_t* sample_seed, cudaStream_t s);
+                           void* pack_ws, float* dbg, int dbg_step, const uint64_t* sample_seed, float* logp,
+                           cudaStream_t s);
 
 static int decode_impl(const void* blob, int n_layers, const float* x, const float* emb,
                        const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp,
                        int N, int G, int mode, const int32_t* forced_pi, int32_t* pi,
                        float* reward, float* logits_out, void* workspace,
                        size_t workspace_bytes, float* dbg, int dbg_step, void* stream,
-                       const uint64_t* sample_seed = nullptr) {
+                       const uint64_t* sample_seed = nullptr, float* logp = nullptr) {
   HTSP_REQUIRE(blob && x && emb && src && tgt && first && pi && reward, "null pointer");
   HTSP_REQUIRE(Bp >= 0 && N >= 3 && G >= 1 && G <= N && n_layers >= 0, "bad shape");
   HTSP_REQUIRE(mode >= HTSP_MODE_FP32 && mode <= HTSP_MODE_TC_FAST, "bad mode");
@@ -215,15 +216,25 @@ static int decode_impl(const void* blob, int n_layers, const float* x, const flo
   rc = launch_decode_prep(blob, n_layers, emb, src, tgt, Bp, N, proj, qfix, c0, tc, prep_ws, s);
   if (rc) return rc;
   rc = decode_dispatch(blob, n_layers, x, emb, proj, qfix, c0, src, tgt, first, Bp, N, G, mode, forced_pi, pi, reward,
-                       logits_out, pack_ws, dbg, dbg_step, sample_seed, s);
+                       logits_out, pack_ws, dbg, dbg_step, sample_seed, logp, s);
   if (rc) return rc;
+  if (logp != nullptr) {
+    rc = launch_decode_poison(logp, (size_t)Bp * G, idx_flag, s);
+    if (rc) return rc;
+  }
   return launch_decode_poison(reward, (size_t)Bp * G, idx_flag, s);
 }
 
 static int decode_dispatch(const void* blob, int n_layers, const float* x, const float* emb, float* proj, float* qfix,
                            float* c0, const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp, int N, int G,
                            int mode, const int32_t* forced_pi, int32_t* pi, float* reward, float* logits_out,
-                           void* pack_ws, float* dbg, int dbg_step, const uint64_t* sample_seed, cudaStream_t s) {
+                           void* pack_ws, float* dbg, int dbg_step, const uint64_t* sample_seed, float* logp,
+                           cudaStream_t s) {
+  if (logp != nullptr && !use_tc2_kernel(N, G, mode)) {
+    set_error("htsp_decode_sample_logp: log-probabilities are returned by the second tcgen05 kernel only (mode fast, "
+              "33 <= N <= 208, G <= 256); got mode %d, N %d, G %d", mode, N, G);
+    return HTSP_ERR_UNSUPPORTED;
+  }
   if (sample_seed != nullptr && (mode == HTSP_MODE_FP32 || !use_tc_kernel(N, G))) {
     set_error("htsp_decode_sample: sampling rollouts are served by the tcgen05 kernel only (tensor-core mode, "
               "17 <= N <= 208, G <= 256); got mode %d, N %d, G %d", mode, N, G);
@@ -234,7 +245,7 @@ static int decode_dispatch(const void* blob, int n_layers, const float* x, const
                              N, G, forced_pi, pi, reward, logits_out, s);
   if (use_tc2_kernel(N, G, mode))
     return launch_decode_tc2(x, proj, qfix, c0, src, tgt, first, Bp, N, G, forced_pi, pi, reward, logits_out, pack_ws,
-                             dbg, dbg_step, sample_seed, s);
+                             dbg, dbg_step, sample_seed, logp, s);
   if (use_tc_kernel(N, G))
     return launch_decode_tc(x, proj, qfix, c0, src, tgt, first, Bp, N, G, mode, forced_pi, pi, reward,
                             logits_out, pack_ws, dbg, dbg_step, sample_seed, s);
@@ -258,6 +269,15 @@ extern "C" int htsp_decode_sample(const void* blob, int n_layers, const float* x
                                   void* workspace, size_t workspace_bytes, void* stream) {
   return decode_impl(blob, n_layers, x, emb, src, tgt, first, Bp, N, G, mode, nullptr, pi, reward, nullptr,
                      workspace, workspace_bytes, nullptr, 0, stream, &seed);
+}
+
+extern "C" int htsp_decode_sample_logp(const void* blob, int n_layers, const float* x, const float* emb,
+                                       const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp,
+                                       int N, int G, int mode, uint64_t seed, int32_t* pi, float* reward, float* logp,
+                                       void* workspace, size_t workspace_bytes, void* stream) {
+  HTSP_REQUIRE(logp != nullptr, "null pointer");
+  return decode_impl(blob, n_layers, x, emb, src, tgt, first, Bp, N, G, mode, nullptr, pi, reward, nullptr,
+                     workspace, workspace_bytes, nullptr, 0, stream, &seed, logp);
 }
 
 extern "C" size_t htsp_decode_debug_floats(int N) { return std::max(decode_tc_dbg_floats(N), decode_tc2_dbg_floats(N)); }

@@ -185,6 +185,6 @@ int launch_decode_tc2(const float* x, const float* proj, const float* qfix, cons
                       const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp, int N,
                       int G, const int32_t* forced_pi, int32_t* pi, float* reward,
                       float* logits_out, void* pack_ws, float* dbg, int dbg_step, const uint64_t* sample_seed,
-                      cudaStream_t s);
+                      float* logp, cudaStream_t s);
 
 }  // namespace htsp

@@ -174,6 +174,7 @@ struct T2Args {
   float* reward;
   float* logits_out;
   float* dbg;            // DEBUG builds: [S raw 2*8*128*NP | O 256*128 | U raw 256*NP | phase cycles] of instance 0
+  float* logp;           // SAMPLE: [Bp,G] sum over the decode steps of log p(sampled node), or NULL
   unsigned long long seed;
   int N, NP, G, rows_per_cta, dbg_step, tile1_delay;
 };
@@ -497,6 +498,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
       const int c_lo = part == 0 ? 0 : (part == 1 ? parts.cb[1] : parts.cb[2]);
       const int c_hi = part == 0 ? parts.cb[1] : (part == 1 ? parts.cb[2] : parts.cb[3]);
       bool bad = false;                              // softmax sum left the fp32 range (part 0 only)
+      float logp_acc = 0.f;                          // SAMPLE, part 0: sum of log p(sampled node) over the steps
 
       // visited flags of THIS warp's keys only (bit k = key 16 c_lo + k; at most 96 keys per part); padded keys
       // (>= N) are permanently visited
@@ -713,6 +715,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
         tick(3);
         float best = -INFINITY;
         int idx = 0x7fffffff;
+        float zbest = 0.f, sumexp = 0.f;       // SAMPLE with log-probabilities (train_path_solver.py:394-414)
         float* lo_out = nullptr;
         if (LOGITS && A.logits_out != nullptr)
           lo_out = A.logits_out + (((size_t)b * GT + r0 + gc) * n_steps + step) * N;
@@ -724,8 +727,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
           constexpr bool EXACT = decltype(exact_tag)::value;
           float bj[4];
           int kj[4];
+          float zj[4];                 // SAMPLE: clipped logit (without the noise) of each slot's running best
 #pragma unroll
-          for (int j = 0; j < 4; ++j) { bj[j] = -INFINITY; kj[j] = 0x7fffffff; }
+          for (int j = 0; j < 4; ++j) { bj[j] = -INFINITY; kj[j] = 0x7fffffff; zj[j] = 0.f; }
+          float se = 0.f;              // SAMPLE: sum over this warp's unvisited keys of exp(z - 10) (z <= 10: no overflow)
           uint32_t u[32];
 #pragma unroll
           for (int i = 0; i < 6; ++i) {
@@ -754,18 +759,24 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
                 const int j = 4 * j4 + jj;
                 float z = __uint_as_float(u[j]) + ca[jj];          // EXACT: 10 tanh(z / sqrt(128)); else the
                 if (EXACT) z = clip_tanh10(z * kT2InvSqrtH);        // monotone pre-activation itself
-                if (SAMPLE) z += tcd_gumbel(ra[jj]);
+                const float zc = z;                                 // SAMPLE: the policy's logit of this key
+                if (SAMPLE) {
+                  se += ((bits >> j) & 1u) ? 0.f : ex2_approx((zc - 10.f) * 1.4426950408889634f);
+                  z += tcd_gumbel(ra[jj]);
+                }
                 if ((bits >> j) & 1u) z = -INFINITY;
                 if (LOGITS && lo_out != nullptr && valid && 16 * c + j < N) lo_out[16 * c + j] = z;
-                if (z > bj[jj]) { bj[jj] = z; kj[jj] = 16 * c + j; }
+                if (z > bj[jj]) { bj[jj] = z; kj[jj] = 16 * c + j; if (SAMPLE) zj[jj] = zc; }
               }
             }
           }
           best = bj[0];
           idx = kj[0];
+          zbest = zj[0];
+          sumexp = se;
 #pragma unroll
           for (int j = 1; j < 4; ++j)
-            if (bj[j] > best || (bj[j] == best && kj[j] < idx)) { best = bj[j]; idx = kj[j]; }
+            if (bj[j] > best || (bj[j] == best && kj[j] < idx)) { best = bj[j]; idx = kj[j]; zbest = zj[j]; }
         };
         if (LOGITS || SAMPLE) {
           pass(std::true_type{});
@@ -783,6 +794,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
           asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(tX + 4 + 2 * part), "r"(__float_as_uint(best)),
                        "r"((uint32_t)idx)
                        : "memory");
+          if (SAMPLE)
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(tX + 9 + 2 * part), "r"(__float_as_uint(zbest)),
+                         "r"(__float_as_uint(sumexp))
+                         : "memory");
           tc::st_wait();
           tc::fence_before();
           trio_sync();                // candidates published
@@ -801,8 +816,22 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
                        : "r"(tX + 6)
                        : "memory");
           asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(z1), "+r"(i1), "+r"(z2), "+r"(i2)::"memory");
-          if (__uint_as_float(z1) > best) { best = __uint_as_float(z1); idx = (int)i1; }     // ties keep the lower part's key
-          if (__uint_as_float(z2) > best) { best = __uint_as_float(z2); idx = (int)i2; }
+          int win = 0;
+          if (__uint_as_float(z1) > best) { best = __uint_as_float(z1); idx = (int)i1; win = 1; }     // ties keep the lower part's key
+          if (__uint_as_float(z2) > best) { best = __uint_as_float(z2); idx = (int)i2; win = 2; }
+          if (SAMPLE) {
+            // log p(sampled node) = z - logsumexp(z over the unvisited keys) (softmax of the masked clipped logits,
+            // models.py:442; train_path_solver.py:394-414 sums the logarithms over the decode steps)
+            uint32_t e1, s1, e2, s2;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(e1), "=r"(s1), "=r"(e2), "=r"(s2)
+                         : "r"(tX + 11)
+                         : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(e1), "+r"(s1), "+r"(e2), "+r"(s2)::"memory");
+            const float zw = win == 0 ? zbest : (win == 1 ? __uint_as_float(e1) : __uint_as_float(e2));
+            const float tot = (sumexp + __uint_as_float(s1)) + __uint_as_float(s2);
+            logp_acc += (zw - 10.f) - __logf(tot);
+          }
           // ---- state update (train_path_solver.py:45-72); the chosen node goes to the other two warps
           a = ((LOGITS || DEBUG) && A.forced_pi) ? clamp_index(A.forced_pi[((size_t)b * GT + r0 + gc) * N + min(cnt, N - 1)], N) : idx;   // teacher forcing: LOGITS / DEBUG kernels only
           if ((unsigned)a >= (unsigned)N) a = cur;     // a NaN row has no candidate: stay in range (the row is flagged)
@@ -832,6 +861,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
         const float dx = ps.x - pt.x, dy = ps.y - pt.y;
         const float fixed = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
         A.reward[(size_t)b * GT + r0 + g] = bad ? __int_as_float(0x7fc00000) : -(len - fixed);
+        if (SAMPLE && A.logp != nullptr) A.logp[(size_t)b * GT + r0 + g] = bad ? __int_as_float(0x7fc00000) : logp_acc;
       }
       if (DEBUG && b == 0 && lane == 0) {
         float* dT = A.dbg + (size_t)2 * 8 * 128 * NP + (size_t)256 * 128 + (size_t)256 * NP + sw * 8;
@@ -913,8 +943,9 @@ int launch_decode_tc2(const float* x, const float* proj, const float* qfix, cons
                       const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp, int N,
                       int G, const int32_t* forced_pi, int32_t* pi, float* reward,
                       float* logits_out, void* pack_ws, float* dbg, int dbg_step, const uint64_t* sample_seed,
-                      cudaStream_t s) {
+                      float* logp, cudaStream_t s) {
   HTSP_REQUIRE(decode_tc2_supported(N, G), "decode_tc2 shape");
+  HTSP_REQUIRE(logp == nullptr || sample_seed != nullptr, "log-probabilities are those of a sampling rollout");
   HTSP_REQUIRE(sample_seed == nullptr || (dbg == nullptr && logits_out == nullptr && forced_pi == nullptr),
                "sampling rollouts take no teacher forcing, logit capture or debug dump");
   HTSP_REQUIRE(dbg == nullptr || G <= 224, "debug dump: at most 224 rows");
@@ -931,7 +962,7 @@ int launch_decode_tc2(const float* x, const float* proj, const float* qfix, cons
   T2Args a;
   a.x = x; a.proj = proj; a.qfix = qfix; a.c0 = c0; a.img = img;
   a.src = src; a.tgt = tgt; a.first = first; a.forced_pi = forced_pi;
-  a.pi = pi; a.reward = reward; a.logits_out = logits_out; a.dbg = dbg;
+  a.pi = pi; a.reward = reward; a.logits_out = logits_out; a.dbg = dbg; a.logp = logp;
   a.seed = sample_seed ? *sample_seed : 0ull;
   a.N = N; a.NP = NP; a.G = G; a.dbg_step = dbg_step;
   a.tile1_delay = getenv("HTSP_TILE1_DELAY") ? atoi(getenv("HTSP_TILE1_DELAY")) : 0;

@@ -143,7 +143,7 @@ class B200PathSolver(torch.nn.Module):
 
     def rollout(self, x: torch.Tensor, emb: torch.Tensor, src: torch.Tensor, tgt: torch.Tensor,
                 first: torch.Tensor, forced_pi: Optional[torch.Tensor] = None,
-                want_logits: bool = False, sample_seed: Optional[int] = None):
+                want_logits: bool = False, sample_seed: Optional[int] = None, want_logp: bool = False):
         """POMO rollout -> (pi [Bp,G,N] i32, reward [Bp,G] f32, logits or None): greedy, or (sample_seed
         given) every row samples its next node from the policy (htsp_decode_sample)."""
         lib = _abi.lib()
@@ -164,6 +164,17 @@ class B200PathSolver(torch.nn.Module):
                   if want_logits else None)
         nbytes = lib.htsp_decode_workspace_bytes(Bp, N, G, mode)
         ws = self._ws.get("dec", nbytes, dev)
+        if sample_seed is not None and want_logp:
+            # third return value: log-probability of every sampled tour (train_path_solver.py:394-414, forward only)
+            assert forced_pi is None and not want_logits
+            logp = torch.empty(Bp, G, dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                _abi.check(lib.htsp_decode_sample_logp(self._packed_weights().data_ptr(), self.cfg.n_layers,
+                                                       x.data_ptr(), emb.data_ptr(), src.data_ptr(), tgt.data_ptr(),
+                                                       first.data_ptr(), Bp, N, G, mode, int(sample_seed) & (2**64 - 1),
+                                                       pi.data_ptr(), reward.data_ptr(), logp.data_ptr(), ws.data_ptr(),
+                                                       ws.numel(), self._stream()), "htsp_decode_sample_logp")
+            return pi, reward, logp
         if sample_seed is not None:
             assert forced_pi is None and not want_logits
             with torch.cuda.device(dev):

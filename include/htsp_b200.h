@@ -108,6 +108,15 @@ int htsp_decode_sample(const void* blob, int n_layers, const float* x, const flo
                        int G, int mode, uint64_t seed, int32_t* pi, float* reward, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* As htsp_decode_sample, additionally returning logp [Bp,G] f32 = sum over the N-2 decode steps of
+ * log p(sampled node), p = softmax(masked 10*tanh logits): the `group_prob_list.log().sum(dim=2)` of the
+ * reference's training step (train_path_solver.py:394-414), forward only.
+ * Served by the second tcgen05 kernel (HTSP_MODE_TC_FAST, 33 <= N <= 208, G <= 256), else HTSP_ERR_UNSUPPORTED. */
+int htsp_decode_sample_logp(const void* blob, int n_layers, const float* x, const float* emb,
+                            const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp, int N,
+                            int G, int mode, uint64_t seed, int32_t* pi, float* reward, float* logp,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
 /* Test hook (tests/test_parity_gpu.py): as htsp_decode in a tensor-core mode on the tcgen05 kernel
  * (N <= 224, G <= 256), additionally dumping the intermediates of instance 0 at decode step
  * `dbg_step` into dbg [htsp_decode_debug_floats(N)] f32: raw glimpse scores S [2,8,128,NP]

@@ -279,6 +279,55 @@ def test_sampling_rollout_validity_and_distribution(built_lib, monkeypatch, mode
     assert stat_u >= df_u + 50 * (2 * df_u) ** 0.5
 
 
+def test_sampling_rollout_log_probabilities(built_lib):
+    """SURVEY 8f-4, forward half of the training step (train_path_solver.py:394-414): htsp_decode_sample_logp returns,
+    for every sampled tour, the sum over the decode steps of log p(sampled node) with p = softmax(masked clipped
+    logits).  Parity: the sampled tours are teacher-forced through the ORACLE (fp32, CPU), whose per-step logits give
+    the reference value of the same sum.  `fast` logits carry up to ~4e-4 of error each (two logits enter every term
+    and N - 2 = 38 terms are summed): the bound is 5e-3 on the sum (measured ~1e-3); the mean over rows, where the
+    errors average out, is held to 1e-3."""
+    from htsp_b200 import B200PathSolver, _abi
+    from htsp_b200.weights import synthetic_state_dict
+    sd = synthetic_state_dict(4321, 6)                      # peaked policy: log-probabilities far from -log(n)
+    s = B200PathSolver(state_dict=sd, mode="fast", device="cuda")
+    g = torch.Generator().manual_seed(11)
+    Bp, N, G = 3, 40, 33
+    x = torch.rand(Bp, N, 2, generator=g)
+    src = torch.randint(0, N, (Bp,), generator=g)
+    tgt = (src + 1 + torch.randint(0, N - 1, (Bp,), generator=g)) % N
+    first = torch.randperm(N, generator=g)[:G]
+    xc = x.cuda()
+    emb = s.encode(xc)
+    pi, rew, logp = s.rollout(xc, emb, src, tgt, first, sample_seed=777, want_logp=True)
+    pi2, rew2, none = s.rollout(xc, emb, src, tgt, first, sample_seed=777)
+    assert none is None and torch.equal(pi, pi2) and torch.equal(rew, rew2)     # the same draws with and without logp
+    pic = pi.cpu().long()
+    with torch.no_grad():
+        ref = po.rollout(sd, x, src, tgt, first, forced_pi=pic, capture_logits=True)
+    assert torch.equal(ref.pi, pic)
+    # replay: the action of step t sits at tour index `count` before the step (as tests/_util.py::tie_aware_check)
+    srcG, tgtG = src.view(Bp, 1).expand(Bp, G), tgt.view(Bp, 1).expand(Bp, G)
+    count = torch.ones(Bp, G, dtype=torch.long)
+    f = pic[:, :, 0]
+    count = count + ((f == srcG) | (f == tgtG)).long()
+    want = torch.zeros(Bp, G, dtype=torch.float64)
+    for t in range(N - 2):
+        a = pic.gather(2, count[..., None]).squeeze(2)
+        lsm = torch.log_softmax(ref.logits[t].double(), dim=-1)
+        want += lsm.gather(2, a[..., None]).squeeze(2)
+        count = count + 1 + ((a == srcG) | (a == tgtG)).long()
+    got = logp.cpu().double()
+    err = (got - want).abs()
+    print(f"[fast] sum of log p over {N - 2} steps: mean {float(want.mean()):.3f}, max |d| {float(err.max()):.2e}, "
+          f"|d mean| {float((got.mean() - want.mean()).abs()):.2e}")
+    assert float(want.abs().min()) > 1.0 and float(err.max()) <= 5e-3
+    assert float((got.mean() - want.mean()).abs()) <= 1e-3
+    # x3 has no log-probability path yet: the call must refuse, not fall back
+    s3 = B200PathSolver(state_dict=sd, mode="x3", device="cuda")
+    with pytest.raises(_abi.HtspError):
+        s3.rollout(xc, s3.encode(xc), src, tgt, first, sample_seed=777, want_logp=True)
+
+
 def test_forward_sampling_surface(solvers):
     """PathSolver.forward(greedy=False): same return shapes as the greedy call, reproducible under
     torch.manual_seed (the seed of the in-kernel generator is drawn from torch's), valid tours."""
