@@ -904,13 +904,10 @@ static void tcd_choose_split(int Bp, int G, bool debug, int& split, int& rows_pe
   split = 1;
   rows_per_cta = G;
   if (debug || G <= 32) return;
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0)
-      n_sm = 148;
-  }
+  int dev = 0, n_sm = 0;              // queried per call: the library serves several devices of one process
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0)
+    n_sm = 148;
   const char* env = getenv("HTSP_DECODE_SPLIT");
   const int forced = env ? atoi(env) : 0;
   for (int want = 8; want >= 2; want >>= 1) {

@@ -43,7 +43,12 @@ env_splice_kernel(const long long* __restrict__ new_paths, const int32_t* __rest
   for (int i = tid; i < L; i += ENV_THREADS)
     if (path[i] < 0 || path[i] >= Ntot) s_bad = ENV_ERR_RANGE;
   __syncthreads();
+  // a failed splice leaves the environment's tour as it was (the caller flips the double buffer for all environments)
+  auto keep_old_tour = [&]() {
+    for (int i = tid; i < T; i += ENV_THREADS) tout[i] = tin[i];
+  };
   if (s_bad != ENV_OK || L < 1 || L > P) {
+    keep_old_tour();
     if (tid == 0) status[e] = ENV_ERR_RANGE;
     return;
   }
@@ -53,6 +58,7 @@ env_splice_kernel(const long long* __restrict__ new_paths, const int32_t* __rest
   } else {
     const int s = ps[path[0]], en = ps[path[L - 1]];
     if (s < 0 || en < 0 || s == en) {           // h_tsp.py:293-295
+      keep_old_tour();
       if (tid == 0) status[e] = (s == en && s >= 0) ? ENV_ERR_SAME_ENDPOINT : ENV_ERR_ENDPOINT;
       return;
     }
@@ -61,6 +67,7 @@ env_splice_kernel(const long long* __restrict__ new_paths, const int32_t* __rest
   }
   const int newT = head_n + L + tail_n;
   if (newT > Ntot) {
+    keep_old_tour();
     if (tid == 0) status[e] = ENV_ERR_DUPLICATE;
     return;
   }

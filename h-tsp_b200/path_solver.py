@@ -105,7 +105,14 @@ class B200PathSolver(torch.nn.Module):
         return super()._apply(fn, *a, **k)
 
     # -- weights -------------------------------------------------------------------------
+    def _param_versions(self):
+        return tuple(int(p._version) for p in self.parameters()) + tuple(int(b._version) for b in self.buffers())
+
     def _packed_weights(self) -> torch.Tensor:
+        # in-place updates (optimizer.step on the lower model during joint training, copy_ into a parameter) bump the
+        # tensors' version counters: the packed copy is rebuilt when they moved
+        if self._blob is not None and getattr(self, "_blob_versions", None) != self._param_versions():
+            self._blob = None
         if self._blob is None:
             lib = _abi.lib()
             L = self.cfg.n_layers
@@ -120,6 +127,7 @@ class B200PathSolver(torch.nn.Module):
                 _abi.check(lib.htsp_pack_weights(arr, len(host), L, blob.data_ptr(), st),
                            "htsp_pack_weights")
             self._blob = blob
+            self._blob_versions = self._param_versions()
         return self._blob
 
     # -- stages (also used directly by the tests) ----------------------------------------

@@ -90,11 +90,15 @@ class B200VecEnv:
 
     # -- VecEnv.step (h_tsp.py:724-827) without auto-reset ----------------------------------------------
     @torch.no_grad()
-    def step(self, actions: torch.Tensor, hook, check: bool = True, shard_solver: bool = False
+    def step(self, actions: torch.Tensor, hook, check: bool = True, shard_solver: bool = False, frag_buffer=None
              ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """One environment step for every environment that is not done: fragment selection, the
         lower-level path solver (`hook.solve_device`, B200RLSolver) and the scoring step.
-        Returns (states [E,Ntot,8], rewards [E], dones [E]).
+        Returns (states [E,Ntot,8], rewards [E], dones [E]).  `frag_buffer` is handed to the hook, which calls its
+        `update_buffer` with the normalised fragments as the reference does (h_tsp.py:192).  Deviations from
+        `VecEnv.step` (h_tsp.py:783-793), documented in INTEGRATION.md: no auto-reset, no `info` dict (the fragment /
+        new-city / start-city tensors of the step are `self._fragment`, `self._new_cities`, `self._start_city`), and
+        `dones` stays True for environments that finished earlier (the reference reports False for them).
         shard_solver (under torch.distributed, every rank holding the SAME environments and actions): the
         subproblems of the step are solved by `sharding.solve_sharded` -- each rank rolls out its block, one NCCL
         all-gather of the paths -- and every rank applies the identical scoring step."""
@@ -111,7 +115,7 @@ class B200VecEnv:
             from . import sharding
             paths, _ = sharding.solve_sharded(hook, self.x.index_select(0, idx), frag.index_select(0, idx))
         else:
-            paths, _, status, _ = hook.solve_device(self.x.index_select(0, idx), frag.index_select(0, idx), None)
+            paths, _, status, _ = hook.solve_device(self.x.index_select(0, idx), frag.index_select(0, idx), frag_buffer)
             if check:
                 assert bool((status == 0).all()), "invalid path(s) returned by the rollout"
         was_done = self.construction_done.clone()

@@ -186,6 +186,27 @@ def test_b200_state_asserts_like_the_reference(built_lib):
 
 
 @pytest.mark.gpu
+def test_failed_splice_keeps_the_old_tour(built_lib):
+    """With check=False a failed splice (non-zero status) must leave that environment as it was: the double buffer is
+    flipped for all environments at once, so the kernel carries the old tour over."""
+    from htsp_b200.env_state import B200VecState
+    rng = np.random.default_rng(2)
+    x, knn, init, paths = _random_episode(60, 5, 12, rng)
+    xs = torch.from_numpy(np.stack([x, x])).cuda()
+    ks = torch.from_numpy(np.stack([knn, knn])).cuda()
+    st = B200VecState(xs, ks, [init, init], 12)
+    st.step([paths[0], paths[0]])
+    before = st.current_tour(1)
+    outside = [c for c in range(60) if c not in before]
+    good = paths[1]
+    bad = [outside[0], outside[1], before[0]]            # first endpoint is not on the tour (h_tsp.py:293-294)
+    st.step([good, bad], check=False)
+    assert st.status.cpu().tolist()[0] == 0 and st.status.cpu().tolist()[1] != 0
+    assert st.current_tour(1) == before                  # untouched
+    assert len(st.current_tour(0)) > len(before)         # the other environment advanced
+
+
+@pytest.mark.gpu
 def test_b200_state_tsp10000_properties(built_lib):
     """TSP-10000-sized instance, fragments of 200 (evaluate.py defaults): after every step the tour
     is duplicate-free, the city->position index is its inverse, the length equals the O(N^2)-free

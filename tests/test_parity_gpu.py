@@ -563,6 +563,25 @@ def test_out_of_range_indices_do_not_fault(solvers):
         s(x, torch.tensor([[0], [40]]), tgt.reshape(2, 1), val_type="noAug_nTraj", group_size=4)
 
 
+def test_packed_weights_follow_in_place_parameter_updates(built_lib):
+    """The library works on a packed copy of the weights; in-place updates of the module's parameters (optimizer.step
+    during joint training, `copy_`) must invalidate it (only load_state_dict / _apply did)."""
+    from htsp_b200 import B200PathSolver
+    from htsp_b200.weights import synthetic_state_dict
+    sd = synthetic_state_dict(1234, 2)
+    s = B200PathSolver(state_dict=sd, mode="x3", device="cuda")
+    x = torch.rand(2, 30, 2, generator=torch.Generator().manual_seed(1)).cuda()
+    e0 = s.encode(x).clone()
+    with torch.no_grad():
+        s.encoder.init_projection_layer.weight.mul_(1.25)
+    e1 = s.encode(x)
+    assert not torch.allclose(e0, e1)
+    sd2 = {k: v.clone() for k, v in sd.items()}
+    sd2["encoder.init_projection_layer.weight"] = sd2["encoder.init_projection_layer.weight"] * 1.25
+    fresh = B200PathSolver(state_dict=sd2, mode="x3", device="cuda")
+    assert torch.equal(fresh.encode(x), e1)
+
+
 def test_hook_b1_and_training_flag(solvers):
     from htsp_b200 import B200RLSolver
     s = solvers["fp32"]
