@@ -554,6 +554,7 @@ def run_b200(args):
                          "frac": achieved / tc_peak, "traffic": traffic,
                          "peak_source": f"bf16_tflops_sustained, {peak_src}",
                          "kernel_ms": kms, "kernel_share_of_step": kms / (total_ms / args.steps),
+                         "ctas_per_sm": int(lib.htsp_decode_ctas_per_sm(B, N, G, _abi.MODES[args.mode])),
                          "algorithmic_flops_per_launch": dec_f * B,
                          "pipes": pipes,
                          "mufu_floor": {"ex2_per_launch": ex2_per_instance * B, "floor_ms": mufu_floor_ms,

@@ -280,6 +280,10 @@ extern "C" int htsp_decode_sample_logp(const void* blob, int n_layers, const flo
                      workspace, workspace_bytes, nullptr, 0, stream, &seed, logp);
 }
 
+extern "C" int htsp_decode_ctas_per_sm(int Bp, int N, int G, int mode) {
+  if (Bp <= 0 || N < 3 || G < 1) return 0;
+  return use_tc2_kernel(N, G, mode) ? decode_tc2_ctas_per_sm(Bp, N, G) : 1;
+}
 extern "C" size_t htsp_decode_debug_floats(int N) { return std::max(decode_tc_dbg_floats(N), decode_tc2_dbg_floats(N)); }
 extern "C" int htsp_decode_debug(const void* blob, int n_layers, const float* x, const float* emb,
                                  const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp,

@@ -29,6 +29,12 @@
 // issued by their own threads in parallel (a tcgen05.mma costs its issuing thread ~60 cycles whatever its shape).
 // Precision: logits within 1e-3 of the fp32 reference (P carries 10 mantissa bits, as a single fp16 would; V, Q, K,
 // K2 and O keep their hi/lo splits); a row whose softmax sum leaves the fp32 range returns a NaN reward.
+//
+// Single-tile variant (template parameter ONE; launches with more CTAs than SMs): one row tile per CTA -- 512
+// threads, 256 TMEM columns, a four-slot ring, 113 KB of shared memory -- and TWO CTAs per SM, so that an SM runs two
+// decode chains whatever the number of POMO rows (instances with G <= 128 leave half of a two-tile CTA idle).
+// Same arithmetic in the same order: tours, rewards and logits are bit-identical to the two-tile CTA's.
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
@@ -41,6 +47,10 @@ namespace htsp {
 constexpr int T2_THREADS = 896;
 constexpr int T2_PARTS = 3;
 constexpr int T2_SLOTS = 8;
+// single-tile CTAs (template parameter ONE): one 128-row tile per CTA, TWO CTAs per SM -- half of everything
+constexpr int T2_THREADS_ONE = 512;
+constexpr int T2_SLOTS_ONE = 4;
+constexpr int T2_PER_STEP = 3 + 7 * 6 + 3 + 12;   // ring stages of one decode step
 constexpr int T2_SLOT = 12288;            // ring slot: one K_h^j (<= 5 KB), V_h^j (<= 12 KB) or K2_i^j (<= 10 KB) block
 constexpr int T2_TILE_STAGING = 65536;    // per row tile: [hi k0-63 | hi k64-127 | lo k0-63 | lo k64-127], 16 KB each
 constexpr int T2_OCOL = 416;              // O accumulator of tile t: columns 416 + 32 t .. + 31 ([P Vhi | P Vlo])
@@ -89,9 +99,43 @@ __host__ __device__ inline size_t t2_voff(int NP, int j) {
 __host__ __device__ inline size_t t2_szk2(int NP) { return (size_t)NP * 128; }
 __host__ __device__ inline size_t t2_img_bytes(int NP) { return 8 * t2_szk(NP) + 8 * t2_szv(NP) + 4 * t2_szk2(NP); }
 
-// mean key of every head (the centring vector): kbar[b][c] = mean_n K[b, n, c]
-__global__ void __launch_bounds__(128) decode_tc2_kbar_kernel(const float* __restrict__ proj, int N, float* __restrict__ kbar) {
+// stage i of a decode step's operand stream: K_0^{0,1,2}; per head h: V_h^j, K_{h+1}^j (h < 7) for j = 0,1,2;
+// K2_i^j for i = 0..3, j = 0,1,2 -- (offset into the instance's image, bytes), looked up by the producer
+__host__ __device__ inline uint2 t2_stage_entry(int NP, int i) {
+  const T2Parts parts = t2_parts(NP);
+  const size_t szk = t2_szk(NP), szv = t2_szv(NP), szk2 = t2_szk2(NP);
+  const int c1 = parts.cb[1], c2 = parts.cb[2], c3 = parts.cb[3];
+  auto keys_of = [&](int j) { return (uint32_t)(16 * (j == 0 ? c1 : (j == 1 ? c2 - c1 : c3 - c2))); };
+  auto krow_of = [&](int j) { return (uint32_t)(16 * (j == 0 ? 0 : (j == 1 ? c1 : c2))); };
+  auto vbytes_of = [&](int j) { return (uint32_t)t2_vblocks((int)keys_of(j)) * 4096u; };
+  auto voff_of = [&](int j) { return (size_t)((j > 0 ? vbytes_of(0) : 0u) + (j > 1 ? vbytes_of(1) : 0u)); };
+  size_t off;
+  uint32_t bytes;
+  if (i < 3) {                                   // K_0^j
+    off = (size_t)krow_of(i) * 64;
+    bytes = keys_of(i) * 64u;
+  } else if (i < 3 + 42) {                       // heads 0..6: V_h^j, K_{h+1}^j
+    const int r = i - 3, h = r / 6, e = r - 6 * h, j = e >> 1;
+    if ((e & 1) == 0) { off = 8 * szk + (size_t)h * szv + voff_of(j); bytes = vbytes_of(j); }
+    else { off = (size_t)(h + 1) * szk + (size_t)krow_of(j) * 64; bytes = keys_of(j) * 64u; }
+  } else if (i < 48) {                           // head 7: V_7^j
+    const int j = i - 45;
+    off = 8 * szk + (size_t)7 * szv + voff_of(j);
+    bytes = vbytes_of(j);
+  } else {                                       // K2_i^j
+    const int r = i - 48, blk = r / 3, j = r - 3 * blk;
+    off = 8 * szk + 8 * szv + (size_t)blk * szk2 + (size_t)krow_of(j) * 128;
+    bytes = keys_of(j) * 128u;
+  }
+  return make_uint2((uint32_t)off, bytes);
+}
+
+// mean key of every head (the centring vector): kbar[b][c] = mean_n K[b, n, c]; block 0 also writes the stage table
+// that the producers of the single-tile CTAs read (they have no shared memory to spare for it)
+__global__ void __launch_bounds__(128) decode_tc2_kbar_kernel(const float* __restrict__ proj, int N, int NP,
+                                                              float* __restrict__ kbar, uint2* __restrict__ stage_tab) {
   const int b = blockIdx.x, c = threadIdx.x;
+  if (b == 0 && c < T2_PER_STEP) stage_tab[c] = t2_stage_entry(NP, c);
   const float* pb = proj + (size_t)b * N * PROJ + c;
   float s = 0.f;
   for (int n = 0; n < N; ++n) s += __ldg(pb + (size_t)n * PROJ);
@@ -179,12 +223,28 @@ struct T2Args {
   int N, NP, G, rows_per_cta, dbg_step, tile1_delay;
 };
 
-// barrier slots: per row tile, then the shared ring
+// barrier slots: per row tile, then the shared ring (T2B_FULL, T2B_EMPTY, T2B_TOTAL depend on the variant)
 enum { T2B_SFULL = 0, T2B_PFULL = 3, T2B_OFULL = 6, T2B_OREADY = 7, T2B_QFULL = 8, T2B_UFULL = 9, T2B_PER_TILE = 10 };
-enum { T2B_FULL = 2 * T2B_PER_TILE, T2B_EMPTY = T2B_FULL + T2_SLOTS, T2B_TOTAL = T2B_EMPTY + T2_SLOTS };
+constexpr int T2_FULL_BARS = 8;     // "landed" barriers: stage `it` signals barrier it % 8 (see land() in run_helper)
+__host__ __device__ constexpr int t2_bar_total(bool one) {
+  return (one ? 1 : 2) * T2B_PER_TILE + T2_FULL_BARS + (one ? T2_SLOTS_ONE : T2_SLOTS);
+}
 
-template <bool LOGITS, bool DEBUG, bool SPLIT, bool SAMPLE>
-__global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args A) {
+// ONE: the CTA owns ONE row tile (at most 128 rows, SPLIT launches only) with 512 threads, 256 TMEM columns, a
+// four-slot ring and half the shared memory, so that TWO CTAs share an SM.  Why: a decode step is a latency chain
+// (8 x [scores -> softmax -> P V] -> logits -> arg-max -> gather) and the two tiles of a two-tile CTA walk it in
+// lock-step -- they share the operand ring -- so their softmax phases collide on the MUFU pipe and their serial tails
+// leave it idle together.  Two independent CTAs drift apart and fill each other's gaps; the price is that every
+// operand block is fetched from L2 once per tile instead of once per instance.
+template <bool LOGITS, bool DEBUG, bool SPLIT, bool SAMPLE, bool ONE>
+__global__ void __launch_bounds__(ONE ? T2_THREADS_ONE : T2_THREADS, ONE ? 2 : 1) decode_tc2_kernel(const T2Args A) {
+  static_assert(!ONE || (SPLIT && !DEBUG), "single-tile CTAs: SPLIT launches, no debug dump");
+  constexpr int T2_THREADS = ONE ? htsp::T2_THREADS_ONE : htsp::T2_THREADS;     // (shadow the two-tile constants)
+  constexpr int T2_SLOTS = ONE ? htsp::T2_SLOTS_ONE : htsp::T2_SLOTS;
+  constexpr int TILES = ONE ? 1 : 2;
+  constexpr int T2B_FULL = TILES * T2B_PER_TILE, T2B_EMPTY = T2B_FULL + T2_FULL_BARS, T2B_TOTAL = T2B_EMPTY + T2_SLOTS;
+  constexpr int T2_OCOL = ONE ? 208 : htsp::T2_OCOL, T2_XCOL = ONE ? 240 : htsp::T2_XCOL, TCOLS = ONE ? 256 : 512;
+  static_assert(T2B_TOTAL == t2_bar_total(ONE), "barrier count");
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler too
@@ -194,16 +254,17 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
   const int N = A.N, NP = A.NP, GT = A.G;
   const int G = SPLIT ? min(A.rows_per_cta, GT - r0) : A.G;   // rows of this CTA, from row r0 of the instance
   const int n_steps = N - 2;
-  const int n_tiles = G > 128 ? 2 : 1;
+  const int n_tiles = (!ONE && G > 128) ? 2 : 1;
   const T2Parts parts = t2_parts(NP);
-  constexpr int PER_STEP = 3 + 7 * 6 + 3 + 12;   // ring stages of one decode step
+  constexpr int PER_STEP = T2_PER_STEP;
 
-  unsigned char* staging = smem;                                         // 2 x 64 KB
-  unsigned char* ring = smem + 2 * T2_TILE_STAGING;                      // T2_SLOTS x 12 KB
+  unsigned char* staging = smem;                                         // TILES x 64 KB
+  unsigned char* ring = smem + TILES * T2_TILE_STAGING;                  // T2_SLOTS x 12 KB
   float* c0s = (float*)(ring + (size_t)T2_SLOTS * T2_SLOT);              // [NP]
   uint64_t* bars = (uint64_t*)(c0s + NP);
   uint32_t* tmem_slot = (uint32_t*)(bars + T2B_TOTAL);
-  uint2* stage_tab = (uint2*)(tmem_slot + 4);                            // [PER_STEP] (image offset, bytes) of a step's stages
+  uint2* stage_tab = (uint2*)(tmem_slot + 4);                            // [PER_STEP] (image offset, bytes) of a step's stages (not ONE)
+  const uint2* stage_tab_g = (const uint2*)(A.img - 1024);               // the same table in global memory (ONE)
   const uint32_t bar0 = tc::smem_u32(bars);
   auto TBAR = [&](int t, int i) { return bar0 + 8u * (uint32_t)(t * T2B_PER_TILE + i); };
   auto RBAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
@@ -212,9 +273,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
   const float* projb = A.proj + (size_t)b * N * PROJ;
 
   if ((tc::smem_u32(smem) & 1023u) != 0u) __trap();   // swizzle atoms need 1024-byte alignment
-  if (G > 224) __trap();                               // tile 1 has three lane quarters (the host splits larger instances)
+  if (G > (ONE ? 128 : 224)) __trap();                 // tile 1 has three lane quarters (the host splits larger instances)
   if (tid == 0) {
-    for (int t = 0; t < 2; ++t) {
+    for (int t = 0; t < TILES; ++t) {
       const int rows_t = min(128, G - 128 * t);
       const int warps_t = rows_t > 0 ? (rows_t + 31) / 32 : 1;
       for (int j = 0; j < T2_PARTS; ++j) {
@@ -226,48 +287,17 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
       tc::mbar_init(TBAR(t, T2B_QFULL), T2_PARTS * warps_t);
       tc::mbar_init(TBAR(t, T2B_UFULL), T2_PARTS);           // one commit per key part (issuer + two helpers)
     }
-    for (int s = 0; s < T2_SLOTS; ++s) {
-      tc::mbar_init(RBAR(T2B_FULL + s), 1);
-      tc::mbar_init(RBAR(T2B_EMPTY + s), n_tiles);      // a slot is released by every tile's issuer
-    }
+    for (int s = 0; s < T2_FULL_BARS; ++s) tc::mbar_init(RBAR(T2B_FULL + s), 1);
+    for (int s = 0; s < T2_SLOTS; ++s) tc::mbar_init(RBAR(T2B_EMPTY + s), n_tiles);      // a slot is released by every tile's issuer
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // zero the A tiles (rows that never receive a query must hold finite values)
-  for (int i = tid; i < 2 * T2_TILE_STAGING / 16; i += T2_THREADS) ((uint4*)staging)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < TILES * T2_TILE_STAGING / 16; i += T2_THREADS) ((uint4*)staging)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < NP; i += T2_THREADS) c0s[i] = i < N ? __ldg(&A.c0[(size_t)b * N + i]) : 0.f;
-  if (tid < PER_STEP) {
-    // stages of one decode step in stream order: K_0^{0,1,2}; per head h: V_h^j, K_{h+1}^j (h < 7) for j = 0,1,2;
-    // K2_i^j for i = 0..3, j = 0,1,2 -- (offset into the instance's image, bytes), looked up by the producer
-    const size_t szk = t2_szk(NP), szv = t2_szv(NP), szk2 = t2_szk2(NP);
-    const int c1 = parts.cb[1], c2 = parts.cb[2], c3 = parts.cb[3];
-    auto keys_of = [&](int j) { return (uint32_t)(16 * (j == 0 ? c1 : (j == 1 ? c2 - c1 : c3 - c2))); };
-    auto krow_of = [&](int j) { return (uint32_t)(16 * (j == 0 ? 0 : (j == 1 ? c1 : c2))); };
-    auto vbytes_of = [&](int j) { return (uint32_t)t2_vblocks((int)keys_of(j)) * 4096u; };
-    auto voff_of = [&](int j) { return (size_t)((j > 0 ? vbytes_of(0) : 0u) + (j > 1 ? vbytes_of(1) : 0u)); };
-    const int i = tid;
-    size_t off;
-    uint32_t bytes;
-    if (i < 3) {                                   // K_0^j
-      off = (size_t)krow_of(i) * 64;
-      bytes = keys_of(i) * 64u;
-    } else if (i < 3 + 42) {                       // heads 0..6: V_h^j, K_{h+1}^j
-      const int r = i - 3, h = r / 6, e = r - 6 * h, j = e >> 1;
-      if ((e & 1) == 0) { off = 8 * szk + (size_t)h * szv + voff_of(j); bytes = vbytes_of(j); }
-      else { off = (size_t)(h + 1) * szk + (size_t)krow_of(j) * 64; bytes = keys_of(j) * 64u; }
-    } else if (i < 48) {                           // head 7: V_7^j
-      const int j = i - 45;
-      off = 8 * szk + (size_t)7 * szv + voff_of(j);
-      bytes = vbytes_of(j);
-    } else {                                       // K2_i^j
-      const int r = i - 48, blk = r / 3, j = r - 3 * blk;
-      off = 8 * szk + 8 * szv + (size_t)blk * szk2 + (size_t)krow_of(j) * 128;
-      bytes = keys_of(j) * 128u;
-    }
-    stage_tab[i] = make_uint2((uint32_t)off, bytes);
-  }
+  if (!ONE && tid < PER_STEP) stage_tab[tid] = t2_stage_entry(NP, tid);
   if (warp == 3) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)),
-                 "r"(512)
+                 "r"(TCOLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -290,9 +320,15 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
     const int cbj = j == 1 ? parts.cb[1] : parts.cb[2], cej = j == 1 ? parts.cb[2] : parts.cb[3];
     const uint32_t dSj = tmem_base + (uint32_t)(t * NP + 16 * cbj);
     const uint32_t idK = tc::idesc_f16(16 * (cej - cbj));
+    // A parity wait tells the awaited use of a barrier from the previous one only: asked before the PREVIOUS use has
+    // completed it answers "done".  The stages a consumer skips (they belong to the other issuers) must therefore keep
+    // it away from that point.  Stage `it` lives in ring slot it % T2_SLOTS but signals "landed" barrier it % 8: with
+    // the four slots of the single-tile CTAs a per-slot barrier's previous use is the stage four positions back,
+    // issued just before the stage this consumer has just finished -- one L2 miss in that copy and the wait would pass
+    // early (seen as a hung ring with two CTAs per SM).  Eight positions back is a stage whose slot has been released.
     auto land = [&](uint32_t it) {
-      const uint32_t s = it % T2_SLOTS, use = it / T2_SLOTS;
-      tc::mbar_wait(RBAR(T2B_FULL + s), use & 1);
+      const uint32_t s = it % T2_SLOTS;
+      tc::mbar_wait(RBAR(T2B_FULL + it % T2_FULL_BARS), (it / T2_FULL_BARS) & 1);
       tc::fence_after();
       return s;
     };
@@ -339,9 +375,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
     }
   };
 
-  if (warp < 2) {
-    // ================================================================== MMA issuer of row tile t = warp
-    const int t = warp;
+  // ================================================================== MMA issuer of row tile t
+  auto run_issuer = [&](const int t) {
     if (t < n_tiles) {
       const uint32_t stg = tc::smem_u32(staging) + t * T2_TILE_STAGING;
       const uint32_t ring0 = tc::smem_u32(ring);
@@ -365,9 +400,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
         }
       };
       auto land = [&](uint32_t it) {            // wait for stage `it` of the stream; returns its ring slot
-        const uint32_t s = it % T2_SLOTS, use = it / T2_SLOTS;
+        const uint32_t s = it % T2_SLOTS;
         tick(2);
-        tc::mbar_wait(RBAR(T2B_FULL + s), use & 1);
+        tc::mbar_wait(RBAR(T2B_FULL + it % T2_FULL_BARS), (it / T2_FULL_BARS) & 1);
         tc::fence_after();
         tick(0);
         return s;
@@ -459,26 +494,27 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
         for (int i = 0; i < 6; ++i) dT[i] = (float)tph[i];
       }
     }
-  } else if (warp == 2) {
-    // ================================================================== operand producer (one stream for both tiles)
+  };
+  // ================================================================== operand producer (one stream for all tiles)
+  auto run_producer = [&]() {
     if (lane == 0) {
       const uint32_t total = (uint32_t)n_steps * (uint32_t)PER_STEP;
       uint32_t i = 0;
+      uint2 nxt = ONE ? __ldg(stage_tab_g) : make_uint2(0u, 0u);
       for (uint32_t it = 0; it < total; ++it) {
         const uint32_t s = it % T2_SLOTS, use = it / T2_SLOTS;
-        const uint2 st = stage_tab[i];
+        const uint2 st = ONE ? nxt : stage_tab[i];
         i = (i + 1 == (uint32_t)PER_STEP) ? 0u : i + 1;
-        tc::mbar_wait(RBAR(T2B_EMPTY + s), (use & 1) ^ 1);
-        tc::mbar_expect_tx(RBAR(T2B_FULL + s), st.y);
-        tc::bulk_g2s(tc::smem_u32(ring + (size_t)s * T2_SLOT), imgb + st.x, st.y, RBAR(T2B_FULL + s));
+        if (ONE) nxt = __ldg(stage_tab_g + i);      // (the next entry travels while this stage's slot is waited for)
+        tc::mbar_wait(RBAR(T2B_EMPTY + s), (use & 1) ^ 1, it);
+        const uint32_t fb = RBAR(T2B_FULL + it % T2_FULL_BARS);
+        tc::mbar_expect_tx(fb, st.y);
+        tc::bulk_g2s(tc::smem_u32(ring + (size_t)s * T2_SLOT), imgb + st.x, st.y, fb);
       }
     }
-  } else if (warp == 3) {
-    run_helper(0, 1);
-  } else if (warp == 19 || warp == 23 || warp == 27) {
-    run_helper(warp == 19 ? 0 : 1, warp == 19 ? 2 : (warp == 23 ? 1 : 2));
-  } else if (warp >= 4) {
-    // ================================================================== softmax / state warps
+  };
+  // ================================================================== softmax / state warps
+  auto run_softmax = [&]() {
     const int sw = warp - 4;
     const int t = sw / 12, part = (sw % 12) >> 2, q = warp & 3;
     const int rows_t = min(128, G - 128 * t);
@@ -592,7 +628,18 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
 
       const float4 qfix4 = __ldg((const float4*)(A.qfix + (size_t)b * H) + lane);
       const uint32_t trio_bar = 1u + (uint32_t)(t * 4 + q);     // named barrier of the three warps of this row quarter
-      auto trio_sync = [&]() { asm volatile("bar.sync %0, 96;" ::"r"(trio_bar) : "memory"); };
+      auto trio_sync = [&]() {
+        if constexpr (ONE) {
+          // immediate barrier numbers: with a register operand ptxas books all 16 named barriers for the CTA, and the
+          // driver then places one CTA per SM (measured: the occupancy query answers 1 whatever the shared memory)
+          if (q == 0) asm volatile("bar.sync 1, 96;" ::: "memory");
+          else if (q == 1) asm volatile("bar.sync 2, 96;" ::: "memory");
+          else if (q == 2) asm volatile("bar.sync 3, 96;" ::: "memory");
+          else asm volatile("bar.sync 4, 96;" ::: "memory");
+        } else {
+          asm volatile("bar.sync %0, 96;" ::"r"(trio_bar) : "memory");
+        }
+      };
       // query rows -> A tile (fp16 hi/lo, K-major SWIZZLE_128B):
       // q = ((q_graph+q_source+q_target) + q_first) + q_last (models.py:413), 1/sqrt(dk)*log2(e) folded in.
       // The three warps of a row quarter gather a third of its rows each; lane l carries columns 4l..4l+3 of every
@@ -868,13 +915,30 @@ __global__ void __launch_bounds__(T2_THREADS, 1) decode_tc2_kernel(const T2Args 
         for (int i = 0; i < 6; ++i) dT[i] = (float)tph[i];
       }
     }
+  };
+
+  if constexpr (ONE) {
+    // warps 0-3: issuer, issue helper of key part 2, producer, issue helper of key part 1; 4-15: softmax warps (part, lane
+    // quarter).  2 CTAs x 512 threads leave 64 registers per thread, which the softmax path fits without spills in its
+    // loops (a setmaxnreg hand-over from the role warps makes the driver count one CTA per SM: measured).
+    if (warp == 0) run_issuer(0);
+    else if (warp == 1) run_helper(0, 2);
+    else if (warp == 2) run_producer();
+    else if (warp == 3) run_helper(0, 1);
+    else run_softmax();
+  } else {
+    if (warp < 2) run_issuer(warp);
+    else if (warp == 2) run_producer();
+    else if (warp == 3) run_helper(0, 1);
+    else if (warp == 19 || warp == 23 || warp == 27) run_helper(warp == 19 ? 0 : 1, warp == 19 ? 2 : (warp == 23 ? 1 : 2));
+    else if (warp >= 4) run_softmax();
   }
 
   tc::fence_before();
   __syncthreads();
   if (warp == 3) {
     tc::fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS) : "memory");
   }
 }
 
@@ -885,7 +949,8 @@ static int t2_np_of(int N) { return (N + 15) / 16 * 16; }
 
 bool decode_tc2_supported(int N, int G) { return t2_np_of(N) <= 208 && t2_np_of(N) >= 48 && G <= 256; }
 size_t decode_tc2_pack_bytes(int Bp, int N) {
-  return align_up((size_t)Bp * t2_img_bytes(t2_np_of(N)), 256) + 1024 + align_up((size_t)Bp * H * 4, 256);
+  // [slack to a 1024-byte boundary | stage table, 1 KB | operand images | mean keys]
+  return 1024 + 1024 + align_up((size_t)Bp * t2_img_bytes(t2_np_of(N)), 256) + align_up((size_t)Bp * H * 4, 256);
 }
 size_t decode_tc2_dbg_floats(int N) {
   const int NP = t2_np_of(N);
@@ -922,21 +987,75 @@ static void t2_choose_split(int Bp, int G, bool debug, int& split, int& rows_per
   }
 }
 
-template <bool LOGITS, bool DEBUG, bool SPLIT, bool SAMPLE = false>
+// dynamic shared memory of a CTA: A tiles, ring, c0, barriers, TMEM slot (+ the stage table of the two-tile variant)
+static size_t t2_smem_bytes(int NP, bool one) {
+  return (size_t)(one ? 1 : 2) * T2_TILE_STAGING + (size_t)(one ? T2_SLOTS_ONE : T2_SLOTS) * T2_SLOT + (size_t)NP * 4 +
+         (size_t)t2_bar_total(one) * 8 + 16 + (one ? 0 : T2_PER_STEP * 8);
+}
+
+template <bool LOGITS, bool DEBUG, bool SPLIT, bool SAMPLE = false, bool ONE = false>
 static int launch_t2(const T2Args& a, int Bp, cudaStream_t s) {
-  const size_t smem = (size_t)2 * T2_TILE_STAGING + (size_t)T2_SLOTS * T2_SLOT + (size_t)a.NP * 4 + T2B_TOTAL * 8 + 16 + (3 + 7 * 6 + 3 + 12) * 8;
+  const size_t smem = t2_smem_bytes(a.NP, ONE);
   if (smem > 227 * 1024) {
     set_error("decode_tc2: N=%d needs %zu bytes of shared memory", a.N, smem);
     return HTSP_ERR_UNSUPPORTED;
   }
-  HTSP_CHECK_CUDA(cudaFuncSetAttribute(decode_tc2_kernel<LOGITS, DEBUG, SPLIT, SAMPLE>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto kern = decode_tc2_kernel<LOGITS, DEBUG, SPLIT, SAMPLE, ONE>;
+  HTSP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (ONE) HTSP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   kernel_timer_begin(s);
-  decode_tc2_kernel<LOGITS, DEBUG, SPLIT, SAMPLE>
-      <<<SPLIT ? Bp * ((a.G + a.rows_per_cta - 1) / a.rows_per_cta) : Bp, T2_THREADS, smem, s>>>(a);
+  kern<<<SPLIT ? Bp * ((a.G + a.rows_per_cta - 1) / a.rows_per_cta) : Bp, ONE ? T2_THREADS_ONE : T2_THREADS, smem, s>>>(a);
   kernel_timer_end(s);
   HTSP_CHECK_LAUNCH();
   return HTSP_OK;
+}
+
+// Single-tile CTAs, two per SM (template parameter ONE), pay off when the launch has more CTAs than SMs; they need the
+// SM to really hold two of them (checked once per device: shared memory 2 x (112.97 KB + 1 KB reserved) of 228 KB).
+// HTSP_T2_ONE = 0 | 1 overrides the choice.
+static bool t2_use_one(int Bp, int G, int NP, bool debug) {
+  if (debug) return false;
+  const char* env = getenv("HTSP_T2_ONE");
+  if (env && atoi(env) == 0) return false;
+  int dev = 0, n_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0)
+    return false;
+  static int fits[64];                 // per device: 0 unknown, 1 two CTAs per SM, -1 not
+  const int slot = dev & 63;
+  if (fits[slot] == 0) {
+    // Resource arithmetic instead of cudaOccupancyMaxActiveBlocksPerMultiprocessor: the occupancy query answers 1 for
+    // every kernel that contains tcgen05.alloc, whatever its shared memory and registers, while the hardware does
+    // place two such CTAs on an SM when each allocates at most 256 columns (measured on B200: 296 CTAs of a
+    // 256-column, 113 KB, 512-thread kernel start within 1 us of each other and finish in one wave).
+    auto kern = decode_tc2_kernel<false, false, true, false, true>;
+    const size_t smem = t2_smem_bytes(208, true);
+    int smem_sm = 0, smem_res = 0, regs_sm = 0;
+    cudaFuncAttributes fa;
+    const bool ok = cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) == cudaSuccess &&
+                    cudaDeviceGetAttribute(&smem_res, cudaDevAttrReservedSharedMemoryPerBlock, dev) == cudaSuccess &&
+                    cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev) == cudaSuccess &&
+                    cudaFuncGetAttributes(&fa, kern) == cudaSuccess;
+    if (!ok) (void)cudaGetLastError();
+    const size_t per_cta = align_up(smem + (size_t)smem_res, 1024);
+    fits[slot] = (ok && 2 * per_cta <= (size_t)smem_sm && 2 * T2_THREADS_ONE * ((fa.numRegs + 7) / 8 * 8) <= regs_sm) ? 1 : -1;
+    if (getenv("HTSP_T2_VERBOSE"))
+      fprintf(stderr, "[decode_tc2] single-tile CTAs: two per SM %s (dynamic smem %zu + reserved %d of %d per SM; regs %d x %d of %d)\n",
+              fits[slot] > 0 ? "fit" : "do NOT fit", smem, smem_res, smem_sm, ok ? fa.numRegs : -1, T2_THREADS_ONE, regs_sm);
+  }
+  if (fits[slot] < 0) return false;
+  if (env && atoi(env) != 0) return true;
+  (void)NP;
+  // Measured (B200, 1184 instances, tools/ab_rollout.py): G <= 128 -- the two-tile CTA holds ONE chain per SM -- gains
+  // 22 ... 51 % (N = G = 100: 95.3 K -> 133.7 K instances/s; N = 200, G = 128: 37.0 K -> 45.1 K; N = G = 64: 181 K ->
+  // 273 K); two-tile instances gain 0.7 - 1 % (N = G = 200: 24.82 K -> 24.99 K).  Below one CTA per SM the row-split
+  // two-tile kernels are the faster choice (one chain per SM either way, deeper ring).
+  return (long long)Bp * ((G + 127) / 128) > n_sm && (G <= 128 || Bp >= n_sm);
+}
+
+// CTAs of the rollout kernel that share an SM for such a call: 2 = single-tile CTAs, 1 = two-tile (or row-split) CTAs
+int decode_tc2_ctas_per_sm(int Bp, int N, int G) {
+  return (decode_tc2_supported(N, G) && t2_use_one(Bp, G, t2_np_of(N), false)) ? 2 : 1;
 }
 
 int launch_decode_tc2(const float* x, const float* proj, const float* qfix, const float* c0,
@@ -950,9 +1069,9 @@ int launch_decode_tc2(const float* x, const float* proj, const float* qfix, cons
                "sampling rollouts take no teacher forcing, logit capture or debug dump");
   HTSP_REQUIRE(dbg == nullptr || G <= 224, "debug dump: at most 224 rows");
   const int NP = t2_np_of(N);
-  unsigned char* img = (unsigned char*)(((uintptr_t)pack_ws + 1023) & ~(uintptr_t)1023);
+  unsigned char* img = (unsigned char*)(((uintptr_t)pack_ws + 1023) & ~(uintptr_t)1023) + 1024;   // (the stage table sits in the KB before)
   float* kbar = (float*)(img + align_up((size_t)Bp * t2_img_bytes(NP), 256));
-  decode_tc2_kbar_kernel<<<Bp, 128, 0, s>>>(proj, N, kbar);
+  decode_tc2_kbar_kernel<<<Bp, 128, 0, s>>>(proj, N, NP, kbar, (uint2*)(img - 1024));
   HTSP_CHECK_LAUNCH();
   {
     const int items = max(NP * 32, (NP >> 2) * 128);
@@ -967,6 +1086,12 @@ int launch_decode_tc2(const float* x, const float* proj, const float* qfix, cons
   a.N = N; a.NP = NP; a.G = G; a.dbg_step = dbg_step;
   a.tile1_delay = getenv("HTSP_TILE1_DELAY") ? atoi(getenv("HTSP_TILE1_DELAY")) : 0;
   int n_split = 1, rows_per_cta = G;
+  if (t2_use_one(Bp, G, NP, dbg != nullptr)) {
+    a.rows_per_cta = min(G, 128);
+    if (sample_seed != nullptr) return launch_t2<false, false, true, true, true>(a, Bp, s);
+    if (logits_out != nullptr || forced_pi != nullptr) return launch_t2<true, false, true, false, true>(a, Bp, s);
+    return launch_t2<false, false, true, false, true>(a, Bp, s);
+  }
   t2_choose_split(Bp, G, dbg != nullptr, n_split, rows_per_cta);
   a.rows_per_cta = rows_per_cta;
   const bool split = n_split > 1;

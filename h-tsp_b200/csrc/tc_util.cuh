@@ -21,8 +21,46 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+#ifdef HTSP_DEBUG_WAIT
+// lab builds (-DHTSP_DEBUG_WAIT): every warp records which barrier it is waiting for; a wait that times out prints the
+// records of its CTA's warps and then lets the kernel run to its end
+__device__ int g_wait_abort = 0;
+__device__ int g_wait_victim = -1;
+__device__ int g_prog[512 * 32];
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t tag = 0) {
+  uint32_t done = 0;
+  const int me = (int)(blockIdx.x & 511) * 32 + ((int)threadIdx.x >> 5);
+  if ((threadIdx.x & 31) == 0) *(volatile int*)&g_prog[me] = 0x10000 | ((int)(bar - 116544u) / 8 << 4) | (int)parity;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if ((spin & 0xfffu) == 0xfffu && *(volatile int*)&g_wait_abort) return;
+    if (spin == (1u << 17)) {
+      if (atomicAdd(&g_wait_victim, 1) < 6) {
+        printf("[wait timeout] block %d warp %d lane %d barrier %d parity %u tag %u\n", (int)blockIdx.x, (int)threadIdx.x >> 5,
+               (int)threadIdx.x & 31, (int)(bar - 116544u) / 8, parity, tag);
+        for (int w = 0; w < 16; ++w) {
+          const int v = *(volatile int*)&g_prog[(int)(blockIdx.x & 511) * 32 + w];
+          printf("   block %d warp %d: state 0x%x (waiting %d, barrier %d, parity %d)\n", (int)blockIdx.x, w, v, v >> 16, (v >> 4) & 0xfff, v & 1);
+        }
+      }
+    }
+    if (spin > (1u << 20)) {
+      atomicAdd(&g_wait_abort, 1);
+      return;
+    }
+  }
+  if ((threadIdx.x & 31) == 0) *(volatile int*)&g_prog[me] = 0x20000 | ((int)(bar - 116544u) / 8 << 4) | (int)parity;   // passed
+}
+#else
 // bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t tag = 0) {
+  (void)tag;       // (lab builds print it)
   uint32_t done = 0;
   for (uint32_t spin = 0; !done; ++spin) {
     asm volatile(
@@ -35,6 +73,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (spin > (1u << 21)) __trap();
   }
 }
+#endif
 // one lane of a converged warp (the others get false)
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;

@@ -117,6 +117,11 @@ int htsp_decode_sample_logp(const void* blob, int n_layers, const float* x, cons
                             int G, int mode, uint64_t seed, int32_t* pi, float* reward, float* logp,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* How many CTAs of the rollout kernel share an SM for an htsp_decode call of this shape on the current device: 2 when
+ * mode HTSP_MODE_TC_FAST runs its single-tile CTAs (more CTAs than SMs; HTSP_T2_ONE = 0 | 1 overrides), else 1; 0 for
+ * an invalid shape.  The result does not depend on it (bit-identical); bench.py and the tests report it.          */
+int htsp_decode_ctas_per_sm(int Bp, int N, int G, int mode);
+
 /* Test hook (tests/test_parity_gpu.py): as htsp_decode in a tensor-core mode on the tcgen05 kernel
  * (N <= 224, G <= 256), additionally dumping the intermediates of instance 0 at decode step
  * `dbg_step` into dbg [htsp_decode_debug_floats(N)] f32: raw glimpse scores S [2,8,128,NP]

@@ -848,6 +848,37 @@ def test_row_split_launch_is_bit_identical(solvers, monkeypatch, mode, Bp, N, G)
         assert torch.equal(torch.nan_to_num(lg0, neginf=-1e30), torch.nan_to_num(lg1, neginf=-1e30)), f"parts={parts}"
 
 
+@pytest.mark.parametrize("Bp,N,G", [(3, 200, 200), (2, 130, 130), (5, 64, 40), (2, 200, 129), (2, 100, 100), (1, 200, 256)])
+def test_single_tile_ctas_are_bit_identical(solvers, monkeypatch, Bp, N, G):
+    """Full-occupancy launches of mode fast run single-tile CTAs, two per SM (template parameter ONE of
+    csrc/decode_tc2.cu: 512 threads, 256 TMEM columns, four-slot ring, stage table in global memory).  The arithmetic
+    and the accumulation order are those of the two-tile CTA: greedy tours, rewards, teacher-forced logits, sampled
+    tours and their log-probabilities must not change by a bit."""
+    s = solvers["fast"]
+    g = torch.Generator().manual_seed(91 + Bp + N + G)
+    x = torch.rand(Bp, N, 2, generator=g)
+    src = torch.randint(0, N, (Bp,), generator=g)
+    tgt = (src + 1 + torch.randint(0, N - 1, (Bp,), generator=g)) % N
+    first = torch.randperm(N, generator=g)[:G]
+    xc = x.cuda()
+    emb = s.encode(xc)
+    from htsp_b200 import _abi
+    out = {}
+    for one in ("0", "1"):
+        monkeypatch.setenv("HTSP_T2_ONE", one)
+        assert _abi.lib().htsp_decode_ctas_per_sm(Bp, N, G, _abi.MODES["fast"]) == 1 + int(one)   # the variant really runs
+        pi, rew, _ = s.rollout(xc, emb, src, tgt, first)
+        _, _, lg = s.rollout(xc, emb, src, tgt, first, forced_pi=pi, want_logits=True)
+        spi, srew, slogp = s.rollout(xc, emb, src, tgt, first, sample_seed=99, want_logp=True)
+        out[one] = (pi, rew, torch.nan_to_num(lg, neginf=-1e30), spi, srew, slogp)
+    monkeypatch.delenv("HTSP_T2_ONE")
+    names = ("tours", "rewards", "teacher-forced logits", "sampled tours", "sampled rewards", "log-probabilities")
+    for name, a, b in zip(names, out["0"], out["1"]):
+        assert torch.equal(a, b), name
+    pic = out["1"][0].cpu().long()
+    assert bool((pic.sort(dim=-1).values == torch.arange(N)).all()) and bool((pic[:, :, 0] == first).all())
+
+
 # ---------------------------------------------------------------- multi-GPU: augmentation sharding (8e)
 @pytest.mark.parametrize("world", [2, 3, 8])
 def test_aug_sharding_equals_single_gpu_hook(solvers, world):
