@@ -135,6 +135,9 @@ int launch_linear_tc(const __half* xhi, const __half* xlo, const __half* whi, co
                      const float* bn_beta, bool relu, float* y32, __half* yhi, __half* ylo, int M,
                      int Nout, int K, cudaStream_t s);
 int launch_split_f16(const float* x, __half* hi, __half* lo, size_t n, cudaStream_t s);
+int launch_ff_fused_tc(const __half* xhi, const __half* xlo, const float* x32, const __half* w1hi, const __half* w1lo,
+                       const float* b1, const __half* w2hi, const __half* w2lo, const float* b2, const float* bn_alpha,
+                       const float* bn_beta, float* y32, __half* yhi, __half* ylo, int M, cudaStream_t s);
 // encoder_tc.cu
 size_t encode_tc_ws_bytes(int Bp, int N);
 int launch_encode_tc(const void* blob, int n_layers, const float* x, int Bp, int N, float* emb,

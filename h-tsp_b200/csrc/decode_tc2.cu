@@ -921,11 +921,19 @@ __global__ void __launch_bounds__(ONE ? T2_THREADS_ONE : T2_THREADS, ONE ? 2 : 1
     // warps 0-3: issuer, issue helper of key part 2, producer, issue helper of key part 1; 4-15: softmax warps (part, lane
     // quarter).  2 CTAs x 512 threads leave 64 registers per thread, which the softmax path fits without spills in its
     // loops (a setmaxnreg hand-over from the role warps makes the driver count one CTA per SM: measured).
+#ifdef T2_ONE_ISSUER_WARP3
+    if (warp == 3) run_issuer(0);
+    else if (warp == 1) run_helper(0, 2);
+    else if (warp == 2) run_producer();
+    else if (warp == 0) run_helper(0, 1);
+    else run_softmax();
+#else
     if (warp == 0) run_issuer(0);
     else if (warp == 1) run_helper(0, 2);
     else if (warp == 2) run_producer();
     else if (warp == 3) run_helper(0, 1);
     else run_softmax();
+#endif
   } else {
     if (warp < 2) run_issuer(warp);
     else if (warp == 2) run_producer();
@@ -1088,6 +1096,8 @@ int launch_decode_tc2(const float* x, const float* proj, const float* qfix, cons
   int n_split = 1, rows_per_cta = G;
   if (t2_use_one(Bp, G, NP, dbg != nullptr)) {
     a.rows_per_cta = min(G, 128);
+    if (getenv("HTSP_T2_ROWS") && atoi(getenv("HTSP_T2_ROWS")) >= 32 && atoi(getenv("HTSP_T2_ROWS")) <= 128 && 2 * atoi(getenv("HTSP_T2_ROWS")) >= G)
+      a.rows_per_cta = atoi(getenv("HTSP_T2_ROWS"));     // (experiment: rows of the first CTA of a two-CTA instance)
     if (sample_seed != nullptr) return launch_t2<false, false, true, true, true>(a, Bp, s);
     if (logits_out != nullptr || forced_pi != nullptr) return launch_t2<true, false, true, false, true>(a, Bp, s);
     return launch_t2<false, false, true, false, true>(a, Bp, s);

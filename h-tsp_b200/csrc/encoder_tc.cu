@@ -2,6 +2,7 @@
 // tcgen05 (gemm_tc.cu, split-fp16 x3) and the bias / ReLU / residual / eval-BatchNorm epilogues fused.
 // Activations travel between layers as fp32 (residual stream) plus the fp16 hi/lo split the next
 // GEMM's TMA loads consume.  The [N x N] self-attention runs on mma.sync tensor cores (enc_attention_mma.cu) for N <= 208.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace htsp {
@@ -32,6 +33,8 @@ int launch_encode_tc(const void* blob, int n_layers, const float* x, int Bp, int
   __half* f_hi = (__half*)w;   w += M * FF * 2;
   __half* f_lo = (__half*)w;   w += M * FF * 2;
   int rc;
+  const char* ffe = getenv("HTSP_FF_FUSED");
+  const bool ff_fused = !(ffe != nullptr && atoi(ffe) == 0);
   if ((rc = launch_init_proj(fb, x, emb, M, s))) return rc;
   if ((rc = launch_split_f16(emb, h_hi, h_lo, M * H, s))) return rc;
   for (int l = 0; l < n_layers; ++l) {
@@ -51,6 +54,13 @@ int launch_encode_tc(const void* blob, int n_layers, const float* x, int Bp, int
     // x = norm1(x + combine(attn))  (models.py:34-35)
     if ((rc = launch_linear_tc(a_hi, a_lo, hb + oh.wo_hi, hb + oh.wo_lo, fb + o.bo, emb, fb + o.bn1a,
                                fb + o.bn1b, false, h1, h1_hi, h1_lo, (int)M, H, H, s))) return rc;
+    // feed_forward: Linear -> ReLU -> Linear, x = norm2(x + ff)  (models.py:22-26,36-37) in one kernel: the hidden
+    // activation stays on the SM (HTSP_FF_FUSED=0 keeps the two GEMM launches: same bits, A/B comparisons)
+    if (ff_fused) {
+      if ((rc = launch_ff_fused_tc(h1_hi, h1_lo, h1, hb + oh.w1_hi, hb + oh.w1_lo, fb + o.b1, hb + oh.w2_hi, hb + oh.w2_lo,
+                                   fb + o.b2, fb + o.bn2a, fb + o.bn2b, emb, h_hi, h_lo, (int)M, s))) return rc;
+      continue;
+    }
     // feed_forward: Linear -> ReLU -> Linear  (models.py:22-26,36)
     if ((rc = launch_linear_tc(h1_hi, h1_lo, hb + oh.w1_hi, hb + oh.w1_lo, fb + o.b1, nullptr, nullptr,
                                nullptr, true, nullptr, f_hi, f_lo, (int)M, FF, H, s))) return rc;

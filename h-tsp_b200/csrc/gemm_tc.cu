@@ -365,6 +365,296 @@ gemm_x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fused feed-forward block of an encoder layer (rl4cop/models/models.py:22-26, 36-37):
+//     Y = BN2( X + relu(X W1^T + b1) W2^T + b2 ),   X [M,128], W1 [512,128], W2 [128,512]
+// in ONE kernel: the [M,512] hidden activation (fp16 hi/lo: 2 KB per row written by FF1 and read back by FF2, 3.4 GB
+// of HBM traffic per layer at config 2) never leaves the SM.  Per 128-row tile the hidden units are processed in
+// eight chunks of 64:
+//     acc1[c&1] (TMEM, 64 columns)  = X W1[64c..64c+63]^T                 24 MMAs (K = 128: 8 k16 steps x 3 split products)
+//     H (shared, K-major SWIZZLE_128B, fp16 hi/lo) = split(relu(acc1 + b1))    epilogue-1 warps, row = TMEM lane
+//     acc2 (TMEM, 128 columns)     += H W2[:, 64c..64c+63]^T               12 MMAs (K = 64)
+// and after the last chunk the epilogue-2 warps apply b2 / residual / BatchNorm and write fp32 + fp16 hi/lo rows.
+// The MMAs, their order and the epilogue arithmetic are those of the two unfused launches: the result is bit-identical.
+// Warps: 0 TMA producer (X tile once per tile; W1 chunks through two stages, W2 chunks through one), 1 MMA issuer
+// (GEMM1 of chunk c is issued before GEMM2 of chunk c-1, so the tensor pipe has work while epilogue 1 runs), 2-9
+// epilogue 1 (lane quarter x 32-column half), 10-17 epilogue 2 (lane quarter x two 32-column chunks; overlaps the next
+// tile through the second acc2 buffer).
+constexpr int FF_CH = 64, FF_NCH = FF / FF_CH;
+constexpr int FF_A_BYTES = 4 * GT_TILE_BYTES;        // X tile: hi k0-63 | hi k64-127 | lo k0-63 | lo k64-127
+constexpr int FF_W1_TILE = FF_CH * GT_BK * 2;        // [64 hidden x 64 k] halves = 8 KB
+constexpr int FF_W1_BYTES = 4 * FF_W1_TILE;          // hi k0 | hi k1 | lo k0 | lo k1
+constexpr int FF_W2_BYTES = 2 * GT_TILE_BYTES;       // [128 out x 64 k] hi | lo
+constexpr int FF_H_BYTES = 2 * GT_TILE_BYTES;        // [128 rows x 64 k] hi | lo
+constexpr int FF_E1_WARPS = 8, FF_E2_WARPS = 8;
+constexpr int FF_THREADS = 64 + 32 * (FF_E1_WARPS + FF_E2_WARPS);
+constexpr int FF_EPI_BYTES = FF_E2_WARPS * 32 * 16 * 4;
+constexpr int FF_NBARS = 20;
+constexpr size_t FF_SMEM_BYTES = 1024 + (size_t)FF_A_BYTES + 2 * FF_W1_BYTES + FF_W2_BYTES + FF_H_BYTES + FF_EPI_BYTES + 256;
+static_assert(FF_SMEM_BYTES <= 227 * 1024, "fused feed-forward: shared memory");
+
+struct FfArgs {
+  const float* b1;         // [512]
+  const float* b2;         // [128]
+  const float* residual;   // [M,128] fp32 (= X)
+  const float* bn_alpha;   // [128]
+  const float* bn_beta;
+  float* y32;              // [M,128]
+  __half* yhi;             // [M,128]
+  __half* ylo;
+  int M;
+};
+
+__global__ void __launch_bounds__(FF_THREADS, 1)
+ff_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
+                   const __grid_constant__ CUtensorMap tmW1_hi, const __grid_constant__ CUtensorMap tmW1_lo,
+                   const __grid_constant__ CUtensorMap tmW2_hi, const __grid_constant__ CUtensorMap tmW2_lo,
+                   const FfArgs E) {
+  extern __shared__ unsigned char gt_smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)gt_smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = smem;
+  unsigned char* sW1 = sA + FF_A_BYTES;               // two stages
+  unsigned char* sW2 = sW1 + 2 * FF_W1_BYTES;
+  unsigned char* sH = sW2 + FF_W2_BYTES;
+  float* epi_smem = (float*)(sH + FF_H_BYTES);
+  uint64_t* bars = (uint64_t*)((unsigned char*)epi_smem + FF_EPI_BYTES);
+  uint32_t* tmem_slot = (uint32_t*)(bars + FF_NBARS);
+  const uint32_t b0 = gt_smem_u32(bars);
+  // barrier slots
+  const uint32_t a_full = b0, a_empty = b0 + 8, w1_full = b0 + 16 /*[2]*/, w1_empty = b0 + 32 /*[2]*/, w2_full = b0 + 48,
+                 w2_empty = b0 + 56, acc1_full = b0 + 64 /*[2]*/, acc1_empty = b0 + 80 /*[2]*/, h_full = b0 + 96,
+                 h_empty = b0 + 104, acc2_full = b0 + 112 /*[2]*/, acc2_empty = b0 + 128 /*[2]*/;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m = (E.M + GT_BM - 1) / GT_BM;
+
+  if (threadIdx.x == 0) {
+    gt_mbar_init(a_full, 1); gt_mbar_init(a_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      gt_mbar_init(w1_full + 8 * i, 1); gt_mbar_init(w1_empty + 8 * i, 1);
+      gt_mbar_init(acc1_full + 8 * i, 1); gt_mbar_init(acc1_empty + 8 * i, FF_E1_WARPS);
+      gt_mbar_init(acc2_full + 8 * i, 1); gt_mbar_init(acc2_empty + 8 * i, FF_E2_WARPS);
+    }
+    gt_mbar_init(w2_full, 1); gt_mbar_init(w2_empty, 1);
+    gt_mbar_init(h_full, FF_E1_WARPS); gt_mbar_init(h_empty, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(gt_smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  gt_fence_before();
+  __syncthreads();
+  gt_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_acc1 = tmem_base, tmem_acc2 = tmem_base + 2 * FF_CH;     // acc1: 2 x 64 columns, acc2: 2 x 128
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t tl = 0, cw = 0;
+      for (int m_blk = blockIdx.x; m_blk < num_m; m_blk += gridDim.x, ++tl) {
+        gt_mbar_wait(a_empty, (tl & 1) ^ 1);
+        gt_mbar_expect_tx(a_full, FF_A_BYTES);
+        const uint32_t dA = gt_smem_u32(sA);
+        gt_tma_2d(dA + 0 * GT_TILE_BYTES, &tmX_hi, 0, m_blk * GT_BM, a_full);
+        gt_tma_2d(dA + 1 * GT_TILE_BYTES, &tmX_hi, GT_BK, m_blk * GT_BM, a_full);
+        gt_tma_2d(dA + 2 * GT_TILE_BYTES, &tmX_lo, 0, m_blk * GT_BM, a_full);
+        gt_tma_2d(dA + 3 * GT_TILE_BYTES, &tmX_lo, GT_BK, m_blk * GT_BM, a_full);
+        // W1 chunks run one chunk ahead of the W2 chunks: W2 has ONE buffer, which is free only when GEMM 2 of the
+        // previous chunk has completed, and nothing may queue behind that wait but the W2 load itself
+        auto load_w1 = [&](uint32_t cwi, int c) {
+          const uint32_t s = cwi & 1, use = cwi >> 1;
+          gt_mbar_wait(w1_empty + 8 * s, (use & 1) ^ 1);
+          gt_mbar_expect_tx(w1_full + 8 * s, FF_W1_BYTES);
+          const uint32_t d1 = gt_smem_u32(sW1 + (size_t)s * FF_W1_BYTES);
+          gt_tma_2d(d1 + 0 * FF_W1_TILE, &tmW1_hi, 0, c * FF_CH, w1_full + 8 * s);
+          gt_tma_2d(d1 + 1 * FF_W1_TILE, &tmW1_hi, GT_BK, c * FF_CH, w1_full + 8 * s);
+          gt_tma_2d(d1 + 2 * FF_W1_TILE, &tmW1_lo, 0, c * FF_CH, w1_full + 8 * s);
+          gt_tma_2d(d1 + 3 * FF_W1_TILE, &tmW1_lo, GT_BK, c * FF_CH, w1_full + 8 * s);
+        };
+        for (int c = 0; c < FF_NCH; ++c, ++cw) {
+          if (c == 0) load_w1(cw, 0);
+          if (c + 1 < FF_NCH) load_w1(cw + 1, c + 1);
+          gt_mbar_wait(w2_empty, (cw & 1) ^ 1);
+          gt_mbar_expect_tx(w2_full, FF_W2_BYTES);
+          const uint32_t d2 = gt_smem_u32(sW2);
+          gt_tma_2d(d2, &tmW2_hi, c * FF_CH, 0, w2_full);
+          gt_tma_2d(d2 + GT_TILE_BYTES, &tmW2_lo, c * FF_CH, 0, w2_full);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc1 = (1u << 4) | ((uint32_t)(FF_CH >> 3) << 17) | ((uint32_t)(GT_BM >> 4) << 24);
+      const uint32_t idesc2 = (1u << 4) | ((uint32_t)(GT_BN >> 3) << 17) | ((uint32_t)(GT_BM >> 4) << 24);
+      const uint32_t aA = gt_smem_u32(sA), aW2 = gt_smem_u32(sW2), aH = gt_smem_u32(sH);
+      uint32_t tl = 0, cw = 0, cg = 0;
+      // acc2 (+)= H W2_c^T for the chunk whose H tile and W2 tile are in shared memory
+      auto gemm2 = [&](uint32_t acc2, bool first) {
+        gt_mbar_wait(w2_full, cg & 1);
+        gt_mbar_wait(h_full, cg & 1);
+        gt_fence_after();
+#pragma unroll
+        for (int k = 0; k < GT_BK / 16; ++k) {
+          const uint64_t a_hi = gt_desc(aH + k * 32), a_lo = gt_desc(aH + GT_TILE_BYTES + k * 32);
+          const uint64_t b_hi = gt_desc(aW2 + k * 32), b_lo = gt_desc(aW2 + GT_TILE_BYTES + k * 32);
+          gt_mma(acc2, a_hi, b_hi, idesc2, !(first && k == 0));
+          gt_mma(acc2, a_hi, b_lo, idesc2, 1);
+          gt_mma(acc2, a_lo, b_hi, idesc2, 1);
+        }
+        gt_commit(h_empty);
+        gt_commit(w2_empty);
+        ++cg;
+      };
+      for (int m_blk = blockIdx.x; m_blk < num_m; m_blk += gridDim.x, ++tl) {
+        const uint32_t b2 = tl & 1;
+        gt_mbar_wait(acc2_empty + 8 * b2, ((tl >> 1) & 1) ^ 1);
+        gt_mbar_wait(a_full, tl & 1);
+        gt_fence_after();
+        const uint32_t acc2 = tmem_acc2 + b2 * GT_BN;
+        for (int c = 0; c < FF_NCH; ++c, ++cw) {
+          const uint32_t s = cw & 1, use = cw >> 1;
+          gt_mbar_wait(w1_full + 8 * s, use & 1);
+          gt_mbar_wait(acc1_empty + 8 * s, (use & 1) ^ 1);
+          gt_fence_after();
+          const uint32_t acc1 = tmem_acc1 + s * FF_CH;
+          const uint32_t aW1 = gt_smem_u32(sW1 + (size_t)s * FF_W1_BYTES);
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+            for (int k = 0; k < GT_BK / 16; ++k) {
+              const uint64_t a_hi = gt_desc(aA + (0 + kb) * GT_TILE_BYTES + k * 32);
+              const uint64_t a_lo = gt_desc(aA + (2 + kb) * GT_TILE_BYTES + k * 32);
+              const uint64_t b_hi = gt_desc(aW1 + (0 + kb) * FF_W1_TILE + k * 32);
+              const uint64_t b_lo = gt_desc(aW1 + (2 + kb) * FF_W1_TILE + k * 32);
+              gt_mma(acc1, a_hi, b_hi, idesc1, (kb | k) != 0);
+              gt_mma(acc1, a_hi, b_lo, idesc1, 1);
+              gt_mma(acc1, a_lo, b_hi, idesc1, 1);
+            }
+          gt_commit(w1_empty + 8 * s);
+          gt_commit(acc1_full + 8 * s);
+          if (c == FF_NCH - 1) gt_commit(a_empty);       // the X tile may be replaced by the next one
+          if (c >= 1) gemm2(acc2, c == 1);
+        }
+        gemm2(acc2, false);
+        gt_commit(acc2_full + 8 * b2);
+      }
+    }
+  } else if (warp < 2 + FF_E1_WARPS) {
+    // ------------------------------------------------------------------ epilogue 1: acc1 -> relu -> H (fp16 hi/lo, A operand of GEMM 2)
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const uint32_t row = (uint32_t)(q * 32 + lane);
+    uint32_t ce = 0;
+    for (int m_blk = blockIdx.x; m_blk < num_m; m_blk += gridDim.x) {
+      for (int c = 0; c < FF_NCH; ++c, ++ce) {
+        const uint32_t s = ce & 1, use = ce >> 1;
+        gt_mbar_wait(acc1_full + 8 * s, use & 1);
+        gt_fence_after();
+        uint32_t r[32];
+        gt_tmem_ld32(tmem_acc1 + s * FF_CH + half * 32 + ((uint32_t)(q * 32) << 16), r);
+        gt_fence_before();
+        __syncwarp();
+        if (lane == 0) gt_mbar_arrive(acc1_empty + 8 * s);
+        uint32_t hi[16], lo[16];
+        const float* bp = E.b1 + c * FF_CH + half * 32;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float4 bb = __ldg((const float4*)(bp + 4 * k));
+          const float v0 = fmaxf(__uint_as_float(r[4 * k]) + bb.x, 0.f), v1 = fmaxf(__uint_as_float(r[4 * k + 1]) + bb.y, 0.f);
+          const float v2 = fmaxf(__uint_as_float(r[4 * k + 2]) + bb.z, 0.f), v3 = fmaxf(__uint_as_float(r[4 * k + 3]) + bb.w, 0.f);
+          split2p(v0, v1, hi[2 * k], lo[2 * k]);
+          split2p(v2, v3, hi[2 * k + 1], lo[2 * k + 1]);
+        }
+        gt_mbar_wait(h_empty, (ce & 1) ^ 1);             // GEMM 2 of the previous chunk has read H
+        const uint32_t hb = gt_smem_u32(sH) + row * 128u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t off = (((uint32_t)(4 * half + j)) ^ (row & 7u)) << 4;     // K-major SWIZZLE_128B
+          gt_sts128(hb + off, hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+          gt_sts128(hb + GT_TILE_BYTES + off, lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) gt_mbar_arrive(h_full);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue 2: acc2 -> + b2 + residual -> BatchNorm -> fp32 and fp16 hi/lo rows
+    const int q = warp & 3, cgp = (warp - 2 - FF_E1_WARPS) >> 2;
+    const uint32_t tr = gt_smem_u32(epi_smem) + (uint32_t)(warp - 2 - FF_E1_WARPS) * (32 * 16 * 4);
+    const uint32_t wr_row = tr + (uint32_t)lane * 64, wr_x = (uint32_t)(lane >> 1) & 3;
+    const int rsub = lane >> 2, slot = lane & 3;
+    uint32_t tl = 0;
+    for (int m_blk = blockIdx.x; m_blk < num_m; m_blk += gridDim.x, ++tl) {
+      const uint32_t b2 = tl & 1;
+      const int rowb = m_blk * GT_BM + q * 32;
+      gt_mbar_wait(acc2_full + 8 * b2, (tl >> 1) & 1);
+      gt_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int col0 = (2 * cgp + cc) * 32;
+        uint32_t r[32];
+        gt_tmem_ld32(tmem_acc2 + b2 * GT_BN + col0 + ((uint32_t)(q * 32) << 16), r);
+        if (cc == 1) {       // both chunks of this warp are in registers: hand the accumulator back
+          gt_fence_before();
+          __syncwarp();
+          if (lane == 0) gt_mbar_arrive(acc2_empty + 8 * b2);
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const float4 b4 = __ldg((const float4*)(E.b2 + col0 + hh * 16 + slot * 4));
+          const float4 al4 = __ldg((const float4*)(E.bn_alpha + col0 + hh * 16 + slot * 4));
+          const float4 be4 = __ldg((const float4*)(E.bn_beta + col0 + hh * 16 + slot * 4));
+          float4 res[4];
+#pragma unroll
+          for (int pp = 0; pp < 4; ++pp) {
+            const int rw = rowb + pp * 8 + rsub;
+            res[pp] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rw < E.M) res[pp] = __ldg((const float4*)(E.residual + (size_t)rw * H + col0 + hh * 16 + slot * 4));
+          }
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            gt_sts128(wr_row + (((uint32_t)j ^ wr_x) << 4), r[hh * 16 + 4 * j], r[hh * 16 + 4 * j + 1],
+                      r[hh * 16 + 4 * j + 2], r[hh * 16 + 4 * j + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int pp = 0; pp < 4; ++pp) {
+            const int rl = pp * 8 + rsub;
+            const int rw = rowb + rl;
+            const float4 t4 = gt_lds128(tr + (uint32_t)rl * 64 + ((((uint32_t)slot) ^ (((uint32_t)rl >> 1) & 3)) << 4));
+            float v[4] = {t4.x, t4.y, t4.z, t4.w};
+            if (rw < E.M) {
+              const size_t off = (size_t)rw * H + col0 + hh * 16 + slot * 4;
+              v[0] += b4.x; v[1] += b4.y; v[2] += b4.z; v[3] += b4.w;
+              const float4 x = res[pp];
+              v[0] = x.x + v[0]; v[1] = x.y + v[1]; v[2] = x.z + v[2]; v[3] = x.w + v[3];
+              v[0] = fmaf(v[0], al4.x, be4.x); v[1] = fmaf(v[1], al4.y, be4.y);
+              v[2] = fmaf(v[2], al4.z, be4.z); v[3] = fmaf(v[3], al4.w, be4.w);
+              *(float4*)(E.y32 + off) = make_float4(v[0], v[1], v[2], v[3]);
+              __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+              const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+              __half2 l0 = __floats2half2_rn(v[0] - f0.x, v[1] - f0.y);
+              __half2 l1 = __floats2half2_rn(v[2] - f1.x, v[3] - f1.y);
+              *(uint2*)(E.yhi + off) = make_uint2(*(uint32_t*)&h0, *(uint32_t*)&h1);
+              *(uint2*)(E.ylo + off) = make_uint2(*(uint32_t*)&l0, *(uint32_t*)&l1);
+            }
+          }
+        }
+      }
+    }
+  }
+  gt_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    gt_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 // fp32 -> fp16 hi/lo split (x = hi + lo), used where a producer kernel only writes fp32
 __global__ void split_f16_kernel(const float* __restrict__ x, __half* __restrict__ hi,
                                  __half* __restrict__ lo, size_t n4) {
@@ -499,6 +789,50 @@ int launch_linear_tc(const __half* xhi, const __half* xlo, const __half* whi, co
   const int tiles = ((M + GT_BM - 1) / GT_BM) * (Nout / GT_BN);
   const int grid = tiles < 148 ? tiles : 148;
   gemm_x3_tc_kernel<<<grid, GT_THREADS, GT_SMEM_BYTES, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, my_hi, my_lo, e);
+  HTSP_CHECK_LAUNCH();
+  return HTSP_OK;
+}
+
+// row-major fp16 matrix [rows, K] -> boxes of box_rows rows x 64 halves (128 B), SWIZZLE_128B
+static int make_map_rows(CUtensorMap* m, const __half* ptr, int rows, int K, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return HTSP_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)GT_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)ptr, gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%d K=%d box_rows=%d", (int)r, rows, K, box_rows);
+    return HTSP_ERR_CUDA;
+  }
+  return HTSP_OK;
+}
+
+// Y = BN( X + relu(X W1^T + b1) W2^T + b2 ): X [M,128] as fp16 hi/lo + fp32 (the residual), W1 [512,128], W2 [128,512]
+int launch_ff_fused_tc(const __half* xhi, const __half* xlo, const float* x32, const __half* w1hi, const __half* w1lo,
+                       const float* b1, const __half* w2hi, const __half* w2lo, const float* b2, const float* bn_alpha,
+                       const float* bn_beta, float* y32, __half* yhi, __half* ylo, int M, cudaStream_t s) {
+  HTSP_REQUIRE(M > 0 && xhi && xlo && x32 && y32 && yhi && ylo, "ff_fused shape");
+  CUtensorMap mx_hi, mx_lo, m1_hi, m1_lo, m2_hi, m2_lo;
+  int rc;
+  if ((rc = make_map(&mx_hi, xhi, M, H))) return rc;
+  if ((rc = make_map(&mx_lo, xlo, M, H))) return rc;
+  if ((rc = make_map_rows(&m1_hi, w1hi, FF, H, FF_CH))) return rc;
+  if ((rc = make_map_rows(&m1_lo, w1lo, FF, H, FF_CH))) return rc;
+  if ((rc = make_map(&m2_hi, w2hi, H, FF))) return rc;
+  if ((rc = make_map(&m2_lo, w2lo, H, FF))) return rc;
+  FfArgs e;
+  e.b1 = b1; e.b2 = b2; e.residual = x32; e.bn_alpha = bn_alpha; e.bn_beta = bn_beta;
+  e.y32 = y32; e.yhi = yhi; e.ylo = ylo; e.M = M;
+  HTSP_CHECK_CUDA(cudaFuncSetAttribute(ff_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM_BYTES));
+  const int tiles = (M + GT_BM - 1) / GT_BM;
+  ff_fused_tc_kernel<<<tiles < 148 ? tiles : 148, FF_THREADS, FF_SMEM_BYTES, s>>>(mx_hi, mx_lo, m1_hi, m1_lo, m2_hi, m2_lo, e);
   HTSP_CHECK_LAUNCH();
   return HTSP_OK;
 }

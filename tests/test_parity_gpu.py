@@ -67,6 +67,24 @@ def test_encoder_matches_oracle(solvers, sd6, mode, Bp, N):
     assert float((got - want).abs().max()) <= tol
 
 
+@pytest.mark.parametrize("Bp,N", [(1, 200), (3, 50), (9, 137), (40, 200), (2, 500)])
+def test_fused_feed_forward_is_bit_identical(solvers, monkeypatch, Bp, N):
+    """The encoder's feed-forward block runs as ONE kernel (csrc/gemm_tc.cu, ff_fused_tc_kernel: the [M,512] hidden
+    activation stays in shared memory / TMEM); HTSP_FF_FUSED=0 keeps the two GEMM launches.  Same MMAs in the same
+    order, same epilogue arithmetic: the embeddings must not change by a bit (row counts that are not multiples of
+    the 128-row tile included)."""
+    g = torch.Generator().manual_seed(Bp * 31 + N)
+    x = torch.rand(Bp, N, 2, generator=g).cuda()
+    s = solvers["x3"]
+    monkeypatch.setenv("HTSP_FF_FUSED", "0")
+    want = s.encode(x).clone()
+    monkeypatch.setenv("HTSP_FF_FUSED", "1")
+    got = s.encode(x).clone()
+    monkeypatch.delenv("HTSP_FF_FUSED")
+    assert torch.equal(got, want)
+    assert torch.equal(s.encode(x), want)      # the default is the fused kernel
+
+
 def test_encoder_matches_golden(solvers, golden):
     x = T(golden["n200_x"]).cuda()
     got = solvers["fp32"].encode(x)[:, :8].cpu().numpy()
