@@ -58,19 +58,32 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_
   if ((threadIdx.x & 31) == 0) *(volatile int*)&g_prog[me] = 0x20000 | ((int)(bar - 116544u) / 8 << 4) | (int)parity;   // passed
 }
 #else
-// bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU
+// bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU.  The polling loops of the
+// waiting warps are a quarter of all issued instructions of the rollout kernels (ncu, profiles/r02_decode_tc2_*) and
+// compete with the softmax warps for issue slots; probing MORE often per counter update makes it worse (measured on
+// decode_tc2, 1184 instances: 1 probe per iteration 46.4 ms, 4 probes 46.85 ms, 8 probes 47.8 ms), a __nanosleep
+// back-off or a suspend-time hint adds wake-up latency to the decode chain (-0.4 % / -1 %): one probe it stays.
+__device__ __forceinline__ bool mbar_probe(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t tag = 0) {
   (void)tag;       // (lab builds print it)
-  uint32_t done = 0;
-  for (uint32_t spin = 0; !done; ++spin) {
-    asm volatile(
-        "{\n.reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (spin > (1u << 21)) __trap();
+  for (uint32_t spin = 0;; ++spin) {
+#ifndef HTSP_WAIT_PROBES
+#define HTSP_WAIT_PROBES 1
+#endif
+#pragma unroll
+    for (int i = 0; i < HTSP_WAIT_PROBES; ++i)
+      if (mbar_probe(bar, parity)) return;
+    if (spin > (1u << 21) / HTSP_WAIT_PROBES) __trap();
   }
 }
 #endif
