@@ -81,6 +81,9 @@ class B200RLSolver(LowLevelSolver):
         N = fragment.shape[1]
         G = self._sample_size
         n_aug = 8 if "x8Aug" in self.val_type else 1
+        if B == 0:      # an empty shard (sharding.solve_sharded with fewer active subproblems than ranks): nothing to launch
+            return (torch.empty(0, N, dtype=torch.int64, device=dev), torch.empty(0, dtype=torch.float32, device=dev),
+                    torch.empty(0, dtype=torch.int32, device=dev), torch.empty(0, N, 2, dtype=torch.float32, device=dev))
         x_new = torch.empty(B, N, 2, dtype=torch.float32, device=dev)
         scale = torch.empty(B, dtype=torch.float32, device=dev)
         x_aug = torch.empty(n_aug * B, N, 2, dtype=torch.float32, device=dev)

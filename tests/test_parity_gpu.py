@@ -897,6 +897,18 @@ def test_single_tile_ctas_are_bit_identical(solvers, monkeypatch, Bp, N, G):
     assert bool((pic.sort(dim=-1).values == torch.arange(N)).all()) and bool((pic[:, :, 0] == first).all())
 
 
+def test_hook_accepts_an_empty_shard(solvers):
+    """sharding.solve_sharded hands a rank an EMPTY block when an environment step has fewer active subproblems than
+    ranks (the end of a TSP-10000 construction on 8 GPUs): the hook returns empty tensors and launches nothing."""
+    from htsp_b200 import B200RLSolver
+    hook = B200RLSolver(solvers["fast"], sample_size=10)
+    data = torch.rand(3, 300, 2).cuda()
+    frag = torch.stack([torch.randperm(300)[:40] for _ in range(3)]).cuda()
+    paths, lengths, status, x_new = hook.solve_device(data[3:], frag[3:], None)
+    assert paths.shape == (0, 40) and lengths.shape == (0,) and status.shape == (0,) and x_new.shape == (0, 40, 2)
+    assert paths.dtype == torch.int64 and paths.is_cuda
+
+
 # ---------------------------------------------------------------- multi-GPU: augmentation sharding (8e)
 @pytest.mark.parametrize("world", [2, 3, 8])
 def test_aug_sharding_equals_single_gpu_hook(solvers, world):
