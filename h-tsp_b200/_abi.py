@@ -27,6 +27,8 @@ SIGNATURES = {
     "htsp_augment8": (_i, [_vp, _i, _i, _vp, _vp]),
     "htsp_encode_workspace_bytes": (_sz, [_i, _i, _i]),
     "htsp_encode": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "htsp_encode_train_workspace_bytes": (_sz, [_i, _i, _i]),
+    "htsp_encode_train": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "htsp_decode_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "htsp_decode": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp,
                          _vp, _sz, _vp]),

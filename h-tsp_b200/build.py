@@ -12,7 +12,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libhtsp_b200.so")
 STAMP = os.path.join(PKG_DIR, ".libhtsp_b200.stamp")
 SOURCES = ["abi.cu", "extract.cu", "encoder_f32.cu", "decode_prep.cu", "decode_f32.cu",
-           "decode_mma.cu", "decode_tc.cu", "decode_tc2.cu", "select.cu", "env_state.cu", "env_fragment.cu", "upper_policy.cu", "gemm_tc.cu", "encoder_tc.cu", "enc_attention_mma.cu"]
+           "decode_mma.cu", "decode_tc.cu", "decode_tc2.cu", "select.cu", "env_state.cu", "env_fragment.cu", "upper_policy.cu", "gemm_tc.cu", "encoder_tc.cu", "enc_attention_mma.cu", "bn_train.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--use_fast_math=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
               "-cudart", "static"]

@@ -148,6 +148,28 @@ extern "C" int htsp_encode(const void* blob, int n_layers, const float* x, int B
                            (cudaStream_t)stream);
 }
 
+extern "C" size_t htsp_encode_train_workspace_bytes(int Bp, int N, int mode) {
+  if (Bp <= 0 || N <= 0 || mode == HTSP_MODE_FP32) return 0;
+  return encode_tc_train_ws_bytes(Bp, N);
+}
+
+extern "C" int htsp_encode_train(const void* blob, int n_layers, const float* bn_gamma_beta, const float* x, int Bp, int N,
+                                 int mode, float* emb, float* bn_batch_stats, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+  HTSP_REQUIRE(blob && x && emb && bn_gamma_beta && bn_batch_stats, "null pointer");
+  HTSP_REQUIRE(Bp >= 1 && N >= 1 && (size_t)Bp * N >= 2 && n_layers >= 0, "bad shape");
+  if (mode != HTSP_MODE_TC_X3 && mode != HTSP_MODE_TC_FAST) {
+    set_error("htsp_encode_train: train-mode BatchNorm is served by the tensor-core encoder (mode x3 / fast), got mode %d", mode);
+    return HTSP_ERR_UNSUPPORTED;
+  }
+  if (workspace == nullptr || workspace_bytes < htsp_encode_train_workspace_bytes(Bp, N, mode)) {
+    set_error("htsp_encode_train: workspace too small (%zu < %zu)", workspace_bytes,
+              htsp_encode_train_workspace_bytes(Bp, N, mode));
+    return HTSP_ERR_WORKSPACE;
+  }
+  return launch_encode_tc(blob, n_layers, x, Bp, N, emb, workspace, (cudaStream_t)stream, bn_gamma_beta, bn_batch_stats);
+}
+
 static size_t dec_proj_bytes(int Bp, int N) { return align_up((size_t)Bp * N * PROJ * 4, 256); }
 static size_t dec_qfix_bytes(int Bp) { return align_up((size_t)Bp * H * 4, 256); }
 static size_t dec_c0_bytes(int Bp, int N) { return align_up((size_t)Bp * N * 4, 256); }

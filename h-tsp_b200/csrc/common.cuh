@@ -140,8 +140,14 @@ int launch_ff_fused_tc(const __half* xhi, const __half* xlo, const float* x32, c
                        const float* bn_beta, float* y32, __half* yhi, __half* ylo, int M, cudaStream_t s);
 // encoder_tc.cu
 size_t encode_tc_ws_bytes(int Bp, int N);
+size_t encode_tc_train_ws_bytes(int Bp, int N);
+size_t bn_train_ws_bytes(size_t M);
+int launch_bn_train(const float* z, size_t M, const float* gamma, const float* beta, float* stats, float* y32,
+                    __half* yhi, __half* ylo, void* ws, cudaStream_t s);
+// bn_gb / bn_stats: NULL = eval-mode BatchNorm (running statistics folded into the blob); else train mode: device
+// [L][4][128] gamma1 | beta1 | gamma2 | beta2 in, batch mean1 | biased var1 | mean2 | biased var2 out
 int launch_encode_tc(const void* blob, int n_layers, const float* x, int Bp, int N, float* emb,
-                     void* ws, cudaStream_t s);
+                     void* ws, cudaStream_t s, const float* bn_gb = nullptr, float* bn_stats = nullptr);
 int launch_init_proj(const float* blob, const float* x, float* emb, size_t M, cudaStream_t s);
 int launch_enc_attention(const float* qkv, float* out, __half* ohi, __half* olo, int Bp, int N,
                          cudaStream_t s);

@@ -14,8 +14,14 @@ size_t encode_tc_ws_bytes(int Bp, int N) {
   return align_up(M * (512 + 1536 + 512 + 512 + 512 + 2048), 256) + 1024;
 }
 
+// train mode: + z [M,128] fp32 (the pre-normalisation sums) and the statistics partials
+size_t encode_tc_train_ws_bytes(int Bp, int N) {
+  const size_t M = (size_t)Bp * N;
+  return encode_tc_ws_bytes(Bp, N) + align_up(M * H * 4, 256) + bn_train_ws_bytes(M) + 256;
+}
+
 int launch_encode_tc(const void* blob, int n_layers, const float* x, int Bp, int N, float* emb,
-                     void* ws, cudaStream_t s) {
+                     void* ws, cudaStream_t s, const float* bn_gb, float* bn_stats) {
   const size_t M = (size_t)Bp * N;
   const float* fb = (const float*)blob;
   const __half* hb = blob_halfs(blob, n_layers);
@@ -32,9 +38,18 @@ int launch_encode_tc(const void* blob, int n_layers, const float* x, int Bp, int
   __half* h1_lo = (__half*)w;  w += M * H * 2;
   __half* f_hi = (__half*)w;   w += M * FF * 2;
   __half* f_lo = (__half*)w;   w += M * FF * 2;
+  const bool train = bn_gb != nullptr;        // batch statistics (PathSolver.training_step): see bn_train.cu
+  HTSP_REQUIRE(train == (bn_stats != nullptr), "train-mode BatchNorm needs both the affine parameters and the statistics output");
+  float* z = nullptr;
+  void* bn_ws = nullptr;
+  if (train) {
+    w = (char*)(((uintptr_t)w + 255) & ~(uintptr_t)255);
+    z = (float*)w;             w += align_up(M * H * 4, 256);
+    bn_ws = w;
+  }
   int rc;
   const char* ffe = getenv("HTSP_FF_FUSED");
-  const bool ff_fused = !(ffe != nullptr && atoi(ffe) == 0);
+  const bool ff_fused = !(ffe != nullptr && atoi(ffe) == 0) && !train;
   if ((rc = launch_init_proj(fb, x, emb, M, s))) return rc;
   if ((rc = launch_split_f16(emb, h_hi, h_lo, M * H, s))) return rc;
   for (int l = 0; l < n_layers; ++l) {
@@ -52,6 +67,12 @@ int launch_encode_tc(const void* blob, int n_layers, const float* x, int Bp, int
       if ((rc = launch_enc_attention(qkv, nullptr, a_hi, a_lo, Bp, N, s))) return rc;
     }
     // x = norm1(x + combine(attn))  (models.py:34-35)
+    if (train) {
+      if ((rc = launch_linear_tc(a_hi, a_lo, hb + oh.wo_hi, hb + oh.wo_lo, fb + o.bo, emb, nullptr, nullptr, false, z,
+                                 nullptr, nullptr, (int)M, H, H, s))) return rc;
+      if ((rc = launch_bn_train(z, M, bn_gb + ((size_t)l * 4 + 0) * H, bn_gb + ((size_t)l * 4 + 1) * H,
+                                bn_stats + ((size_t)l * 4 + 0) * H, h1, h1_hi, h1_lo, bn_ws, s))) return rc;
+    } else
     if ((rc = launch_linear_tc(a_hi, a_lo, hb + oh.wo_hi, hb + oh.wo_lo, fb + o.bo, emb, fb + o.bn1a,
                                fb + o.bn1b, false, h1, h1_hi, h1_lo, (int)M, H, H, s))) return rc;
     // feed_forward: Linear -> ReLU -> Linear, x = norm2(x + ff)  (models.py:22-26,36-37) in one kernel: the hidden
@@ -65,6 +86,13 @@ int launch_encode_tc(const void* blob, int n_layers, const float* x, int Bp, int
     if ((rc = launch_linear_tc(h1_hi, h1_lo, hb + oh.w1_hi, hb + oh.w1_lo, fb + o.b1, nullptr, nullptr,
                                nullptr, true, nullptr, f_hi, f_lo, (int)M, FF, H, s))) return rc;
     // x = norm2(x + ff)  (models.py:36-37)
+    if (train) {
+      if ((rc = launch_linear_tc(f_hi, f_lo, hb + oh.w2_hi, hb + oh.w2_lo, fb + o.b2, h1, nullptr, nullptr, false, z,
+                                 nullptr, nullptr, (int)M, H, FF, s))) return rc;
+      if ((rc = launch_bn_train(z, M, bn_gb + ((size_t)l * 4 + 2) * H, bn_gb + ((size_t)l * 4 + 3) * H,
+                                bn_stats + ((size_t)l * 4 + 2) * H, emb, h_hi, h_lo, bn_ws, s))) return rc;
+      continue;
+    }
     if ((rc = launch_linear_tc(f_hi, f_lo, hb + oh.w2_hi, hb + oh.w2_lo, fb + o.b2, h1, fb + o.bn2a,
                                fb + o.bn2b, false, emb, h_hi, h_lo, (int)M, H, FF, s))) return rc;
   }

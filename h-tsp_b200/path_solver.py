@@ -134,13 +134,41 @@ class B200PathSolver(torch.nn.Module):
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def encode(self, x: torch.Tensor) -> torch.Tensor:
-        """MHAEncoder.forward (models.py:55-60): [Bp,N,2] -> [Bp,N,128]."""
+    def encode(self, x: torch.Tensor, train: bool = False, update_running_stats: bool = True) -> torch.Tensor:
+        """MHAEncoder.forward (models.py:55-60): [Bp,N,2] -> [Bp,N,128].  train=True runs the BatchNorm1d layers as
+        `model.train()` does (batch statistics, htsp_encode_train) and, like torch, moves running_mean / running_var
+        (momentum 0.1, unbiased variance) and num_batches_tracked; the batch statistics of the call are kept in
+        `self.last_bn_batch_stats` [L,4,128] (mean1, biased var1, mean2, biased var2)."""
         lib = _abi.lib()
         x = x.to(self.device, torch.float32).contiguous()
         Bp, N, _ = x.shape
         mode = _abi.MODES[self.mode]
         emb = torch.empty(Bp, N, EMBED_DIM, dtype=torch.float32, device=self.device)
+        if train:
+            L = self.cfg.n_layers
+            layers = self.encoder.attn_layers
+            gb = torch.stack([torch.stack([l.norm1.weight, l.norm1.bias, l.norm2.weight, l.norm2.bias])
+                              for l in layers]).detach().to(self.device, torch.float32).contiguous()
+            stats = torch.empty(L, 4, EMBED_DIM, dtype=torch.float32, device=self.device)
+            nbytes = lib.htsp_encode_train_workspace_bytes(Bp, N, mode)
+            if nbytes == 0:
+                raise NotImplementedError("train-mode BatchNorm is served by the tensor-core encoder (mode x3 / fast)")
+            ws = self._ws.get("enc", nbytes, self.device)
+            with torch.cuda.device(self.device):
+                _abi.check(lib.htsp_encode_train(self._packed_weights().data_ptr(), L, gb.data_ptr(), x.data_ptr(),
+                                                 Bp, N, mode, emb.data_ptr(), stats.data_ptr(), ws.data_ptr(),
+                                                 ws.numel(), self._stream()), "htsp_encode_train")
+            self.last_bn_batch_stats = stats
+            if update_running_stats:
+                M = Bp * N
+                with torch.no_grad():
+                    for i, l in enumerate(layers):
+                        for j, bn in enumerate((l.norm1, l.norm2)):
+                            m = bn.momentum if bn.momentum is not None else 0.1
+                            bn.running_mean.mul_(1 - m).add_(stats[i, 2 * j], alpha=m)
+                            bn.running_var.mul_(1 - m).add_(stats[i, 2 * j + 1] * (M / (M - 1)), alpha=m)
+                            bn.num_batches_tracked += 1
+            return emb
         nbytes = lib.htsp_encode_workspace_bytes(Bp, N, mode)
         ws = self._ws.get("enc", nbytes, self.device)
         with torch.cuda.device(self.device):
@@ -312,6 +340,44 @@ class B200PathSolver(torch.nn.Module):
         if return_pi:
             return -max_reward, best_pi.squeeze()
         return -max_reward
+
+    # -- PathSolver.training_step, forward half (train_path_solver.py:352-434) ----------------
+    @torch.no_grad()
+    def training_step_forward(self, batch: torch.Tensor, group_size: Optional[int] = None, norm_reward: bool = False,
+                              source_nodes: Optional[torch.Tensor] = None, target_nodes: Optional[torch.Tensor] = None):
+        """Everything `training_step` computes before `loss.backward()`: random endpoints (:362-366), the encoder with
+        TRAIN-mode BatchNorm (batch statistics, running statistics updated), a sampling rollout from `randperm` starts
+        that also returns the log-probability of every sampled tour (htsp_decode_sample_logp), the advantage
+        (:402-410), `loss = (-advantage * log_prob).mean()` and the logged scalars.  Returns a dict with the tensors
+        (reward, log_prob, advantage [B,G], pi [B,G,N]) and the scalars.  The backward pass is not built
+        (DESIGN.md section 7): this is the forward half, for evaluation of a training batch and for parity."""
+        if self.mode != "fast":
+            raise NotImplementedError("training_step_forward needs mode='fast' (log-probabilities come from the second tcgen05 kernel)")
+        dev = self.device
+        batch = batch.to(dev, torch.float32).contiguous()
+        B, N, _ = batch.shape
+        G = int(group_size or self.cfg.group_size)
+        assert G <= self.cfg.graph_size and G <= N
+        if source_nodes is None or target_nodes is None:
+            order = torch.argsort(torch.rand(B, N, device=dev))             # :362-366
+            source_nodes, target_nodes = order[:, 0], order[:, 1]
+        first = self.draw_first_action(N, G)                                # :374
+        seed = int(torch.randint(0, 2**62, (1,)).item())
+        emb = self.encode(batch, train=self.training)
+        pi, reward, logp = self.rollout(batch, emb, source_nodes.reshape(-1), target_nodes.reshape(-1), first,
+                                        sample_seed=seed, want_logp=True)
+        r = reward
+        if G != 1:
+            adv = r - r.mean(dim=1, keepdim=True)
+            if norm_reward:
+                adv = adv / (r.std(dim=1, keepdim=True) + 1e-5)
+        else:
+            adv = r
+        loss = (-adv * logp).mean()
+        return {"loss": loss, "length": float(-r.max(dim=1).values.mean()), "advantage": adv, "log_prob": logp,
+                "reward": r, "pi": pi, "entropy": -(logp.exp() * logp).mean(), "r_mean": r.mean(),
+                "r_std": r.std(dim=1).mean() if G != 1 else r.new_zeros(()), "source_nodes": source_nodes,
+                "target_nodes": target_nodes, "first_action": first, "sample_seed": seed}
 
     def _rollout_chunked(self, x, src, tgt, first, n_aug, sample_seed=None):
         Bp = x.shape[0]

@@ -84,6 +84,18 @@ size_t htsp_encode_workspace_bytes(int Bp, int N, int mode);
 int htsp_encode(const void* blob, int n_layers, const float* x, int Bp, int N, int mode,
                 float* emb, void* workspace, size_t workspace_bytes, void* stream);
 
+/* MHAEncoder.forward with the BatchNorm1d layers in TRAIN mode (models.py:35,37 as PathSolver.training_step runs the
+ * encoder, rl4cop/train_path_solver.py:352-375): every norm layer normalises with the mean and biased variance of the
+ * batch (all Bp*N rows) and its own gamma / beta.  bn_gamma_beta: device [n_layers][4][128] f32 = norm1.weight |
+ * norm1.bias | norm2.weight | norm2.bias per layer; bn_batch_stats: device [n_layers][4][128] f32 out = batch mean |
+ * biased variance of norm1, then of norm2 (the caller updates running_mean / running_var with its momentum; the
+ * unbiased variance is var * M / (M - 1), M = Bp*N).  Tensor-core modes only (HTSP_MODE_TC_X3 / _FAST), else
+ * HTSP_ERR_UNSUPPORTED; deterministic (fixed-order fp64 reductions).  The running statistics inside `blob` are not used. */
+size_t htsp_encode_train_workspace_bytes(int Bp, int N, int mode);
+int htsp_encode_train(const void* blob, int n_layers, const float* bn_gamma_beta, const float* x, int Bp, int N,
+                      int mode, float* emb, float* bn_batch_stats, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
 /* ---- K3: POMO rollout ---------------------------------------------------------------
  * PathDecoder.reset/forward (models.py:360-446), GroupState/Env (train_path_solver.py:23-149)
  * and the decode loop + pi extraction (train_path_solver.py:252-288), greedy.

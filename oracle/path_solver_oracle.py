@@ -93,6 +93,36 @@ def encoder_layer(sd, i: int, x: Tensor) -> Tensor:
     return x
 
 
+def _bn_train(x: Tensor, sd, prefix: str, stats: dict) -> Tensor:
+    """torch.nn.BatchNorm1d in train() mode on x.view(-1, C) (models.py:35,37): batch statistics; `stats` receives
+    the updated running_mean / running_var (momentum 0.1, unbiased variance) under the state_dict keys."""
+    flat = x.reshape(-1, x.size(-1))
+    rm, rv = sd[prefix + ".running_mean"].clone(), sd[prefix + ".running_var"].clone()
+    y = F.batch_norm(flat, rm, rv, sd[prefix + ".weight"], sd[prefix + ".bias"], True, 0.1, 1e-5)
+    stats[prefix + ".running_mean"], stats[prefix + ".running_var"] = rm, rv
+    stats[prefix + ".batch_mean"] = flat.mean(dim=0)
+    stats[prefix + ".batch_var"] = flat.var(dim=0, unbiased=False)
+    return y.view(*x.size())
+
+
+def encode_train(sd, x: Tensor):
+    """MHAEncoder.forward with the module in train() mode (as PathSolver.training_step runs it,
+    train_path_solver.py:375): returns (embeddings, dict of updated running statistics + batch statistics)."""
+    stats = {}
+    h = F.linear(x, sd["encoder.init_projection_layer.weight"], sd["encoder.init_projection_layer.bias"])
+    for i in range(n_layers_of(sd)):
+        p = f"encoder.attn_layers.{i}."
+        q = split_heads(F.linear(h, sd[p + "Wq.weight"]))
+        k = split_heads(F.linear(h, sd[p + "Wk.weight"]))
+        v = split_heads(F.linear(h, sd[p + "Wv.weight"]))
+        h = h + F.linear(attention(q, k, v), sd[p + "multi_head_combine.weight"], sd[p + "multi_head_combine.bias"])
+        h = _bn_train(h, sd, p + "norm1", stats)
+        f = F.linear(h, sd[p + "feed_forward.0.weight"], sd[p + "feed_forward.0.bias"])
+        f = F.linear(F.relu(f), sd[p + "feed_forward.2.weight"], sd[p + "feed_forward.2.bias"])
+        h = _bn_train(h + f, sd, p + "norm2", stats)
+    return h, stats
+
+
 def encode(sd, x: Tensor) -> Tensor:
     """MHAEncoder.forward (models.py:55-60): coords [B',N,2] -> embeddings [B',N,H]."""
     h = F.linear(x, sd["encoder.init_projection_layer.weight"],

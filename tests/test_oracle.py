@@ -133,3 +133,24 @@ def test_oracle_is_bit_identical_to_reference(sd6):
         res = po.rollout(sd6, x, src.view(-1), tgt.view(-1), first, capture_logits=True)
     assert len(tap.logits) == N - 2
     assert all(torch.equal(a, b) for a, b in zip(tap.logits, res.logits))
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not mounted")
+def test_train_mode_encoder_oracle_is_bit_identical_to_reference(sd6):
+    """oracle.encode_train restates MHAEncoder.forward with the module in train() mode (batch statistics, the way
+    PathSolver.training_step runs the encoder, train_path_solver.py:375): embeddings and the updated running
+    statistics must equal the unmodified reference's bit for bit."""
+    model = ref_loader.build_reference_path_solver(sd6, n_layers=6)
+    model.train()
+    x = torch.rand(3, 30, 2, generator=torch.Generator().manual_seed(21))
+    with torch.no_grad():
+        want = model.encoder(x)
+        got, stats = po.encode_train(sd6, x)
+    assert torch.equal(got, want)
+    ref_sd = model.state_dict()
+    for i in range(6):
+        for n in ("norm1", "norm2"):
+            for k in ("running_mean", "running_var"):
+                key = f"encoder.attn_layers.{i}.{n}.{k}"
+                assert torch.equal(stats[key], ref_sd[key]), key
+    model.eval()

@@ -85,6 +85,77 @@ def test_fused_feed_forward_is_bit_identical(solvers, monkeypatch, Bp, N):
     assert torch.equal(s.encode(x), want)      # the default is the fused kernel
 
 
+@pytest.mark.parametrize("mode", ["x3", "fast"])
+@pytest.mark.parametrize("Bp,N", [(3, 50), (5, 137), (16, 200)])
+def test_train_mode_encoder_matches_oracle(sd6, built_lib, mode, Bp, N):
+    """htsp_encode_train: BatchNorm1d with batch statistics (the encoder inside PathSolver.training_step,
+    train_path_solver.py:375).  Embeddings within the x3 bound of the oracle (pinned bit-identical to the reference in
+    train() mode, tests/test_oracle.py), batch statistics and the updated running statistics within 1e-5 relative of
+    the largest value; repeated calls give the same bits (fixed-order reductions)."""
+    from htsp_b200 import B200PathSolver
+    s = B200PathSolver(state_dict=sd6, mode=mode, device="cuda")
+    s.train()
+    x = torch.rand(Bp, N, 2, generator=torch.Generator().manual_seed(Bp + N))
+    with torch.no_grad():
+        want, stats = po.encode_train(sd6, x)
+    got = s.encode(x.cuda(), train=True, update_running_stats=False)
+    again = s.encode(x.cuda(), train=True)
+    assert torch.equal(got, again)
+    assert float((got.cpu() - want).abs().max()) <= 1e-4
+    bs = s.last_bn_batch_stats.cpu()
+    for i in range(6):
+        for j, n in enumerate(("norm1", "norm2")):
+            p = f"encoder.attn_layers.{i}.{n}."
+            for got_t, want_t in ((bs[i, 2 * j], stats[p + "batch_mean"]), (bs[i, 2 * j + 1], stats[p + "batch_var"]),
+                                  (getattr(s.encoder.attn_layers[i], n).running_mean.cpu(), stats[p + "running_mean"]),
+                                  (getattr(s.encoder.attn_layers[i], n).running_var.cpu(), stats[p + "running_var"])):
+                assert float((got_t - want_t).abs().max()) <= 1e-5 * float(want_t.abs().max()) + 1e-6, p
+    assert int(s.encoder.attn_layers[0].norm1.num_batches_tracked) == 1
+    # eval mode afterwards uses the moved running statistics (the packed weights follow the buffers' versions)
+    s.eval()
+    sd_new = {k: v.detach().cpu() for k, v in s.state_dict().items()}
+    with torch.no_grad():
+        want_eval = po.encode(sd_new, x)
+    assert float((s.encode(x.cuda()).cpu() - want_eval).abs().max()) <= 1e-4
+
+
+def test_training_step_forward_matches_oracle(sd6, built_lib):
+    """B200PathSolver.training_step_forward = the forward half of PathSolver.training_step (train_path_solver.py:
+    352-434): train-mode encoder, sampling rollout, log-probabilities, advantage, loss.  The sampled tours are
+    teacher-forced through the oracle ON THE ORACLE'S train-mode embeddings: rewards <= 1e-5 relative, summed
+    log-probabilities within 5e-3 (sums of about -60), the loss recomputed from the oracle's quantities within 1e-3
+    relative."""
+    from htsp_b200 import B200PathSolver
+    s = B200PathSolver(state_dict=sd6, mode="fast", device="cuda", graph_size=60)
+    s.train()
+    torch.manual_seed(5)
+    B, N, G = 4, 60, 24
+    batch = torch.rand(B, N, 2)
+    out = s.training_step_forward(batch, group_size=G)
+    pi = out["pi"].cpu().long()
+    assert bool((pi.sort(dim=-1).values == torch.arange(N)).all())
+    src, tgt, first = out["source_nodes"].cpu(), out["target_nodes"].cpu(), out["first_action"].cpu().long()
+    with torch.no_grad():
+        emb, _ = po.encode_train(sd6, batch)
+        ref = po.rollout(sd6, batch, src, tgt, first, forced_pi=pi, capture_logits=True, emb=emb)
+    assert torch.equal(ref.pi, pi)
+    assert rel_err(out["reward"], ref.reward) <= 1e-5
+    # log p of the sampled tours under the oracle's policy
+    lp = torch.zeros(B, G, dtype=torch.float64)
+    count = torch.ones(B, G, dtype=torch.long) + ((pi[:, :, 0] == src.view(B, 1)) | (pi[:, :, 0] == tgt.view(B, 1))).long()
+    for t in range(N - 2):
+        a = pi.gather(2, count[..., None]).squeeze(2)
+        logits = ref.logits[t].double()
+        lp += logits.gather(2, a[..., None]).squeeze(2) - torch.logsumexp(logits, dim=2)
+        count = count + 1 + ((a == src.view(B, 1)) | (a == tgt.view(B, 1))).long()
+    got_lp = out["log_prob"].cpu().double()
+    assert float((got_lp - lp).abs().max()) <= 5e-3, float((got_lp - lp).abs().max())
+    r = ref.reward.double()
+    want_loss = float((-(r - r.mean(dim=1, keepdim=True)) * lp).mean())
+    assert abs(float(out["loss"]) - want_loss) <= 1e-3 * abs(want_loss) + 1e-4
+    assert abs(out["length"] - float(-ref.reward.max(dim=1).values.mean())) <= 1e-4
+
+
 def test_encoder_matches_golden(solvers, golden):
     x = T(golden["n200_x"]).cuda()
     got = solvers["fp32"].encode(x)[:, :8].cpu().numpy()
