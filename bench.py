@@ -293,6 +293,7 @@ def workload_config(args):
                         f"{args.batch} subproblems of {args.nodes} nodes per GPU, noAug_nTraj, greedy",
             "batch_per_gpu": args.batch, "nodes": args.nodes, "pomo_starts": args.group,
             "encoder_layers": args.layers, "val_type": "noAug_nTraj", "arith": args.mode,
+            "encoder_ff_fused": os.environ.get("HTSP_FF_FUSED", "1") != "0",
             "l2": "per-step working set (embeddings + decoder tables, >2 GB) exceeds the 126 MB L2; "
                   "a different input batch is used every step"}
 

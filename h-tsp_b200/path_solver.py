@@ -46,16 +46,21 @@ class _DecParams(torch.nn.Module):
 
 
 class _Workspace:
-    """Grow-only device scratch buffers keyed by name (the C ABI never allocates)."""
+    """Grow-only device scratch buffers keyed by (name, device, CUDA stream) -- the C ABI never allocates.  One buffer
+    per stream: two streams driving the same model do not share scratch memory (kernels of one stream are ordered, so
+    reuse within a stream is safe)."""
 
     def __init__(self):
-        self._bufs: Dict[str, torch.Tensor] = {}
+        self._bufs: Dict[tuple, torch.Tensor] = {}
 
     def get(self, name: str, nbytes: int, device) -> torch.Tensor:
-        buf = self._bufs.get(name)
-        if buf is None or buf.numel() < nbytes or buf.device != device:
+        device = torch.device(device)
+        stream = torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0
+        key = (name, str(device), stream)
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
             buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
-            self._bufs[name] = buf
+            self._bufs[key] = buf
         return buf
 
 
