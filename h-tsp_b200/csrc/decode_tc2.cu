@@ -52,6 +52,8 @@ constexpr int T2_THREADS_ONE = 512;
 constexpr int T2_SLOTS_ONE = 4;
 constexpr int T2_PER_STEP = 3 + 7 * 6 + 3 + 12;   // ring stages of one decode step
 constexpr int T2_SLOT = 12288;            // ring slot: one K_h^j (<= 5 KB), V_h^j (<= 12 KB) or K2_i^j (<= 10 KB) block
+constexpr int T2_SLOT_KB = 8192;          // key-block kernels: blocks of <= 192 keys have parts of <= 64 keys (K 4 KB, V 8 KB, K2 8 KB)
+constexpr int T2_KB_MAX_NPB = 192;
 constexpr int T2_TILE_STAGING = 65536;    // per row tile: [hi k0-63 | hi k64-127 | lo k0-63 | lo k64-127], 16 KB each
 constexpr int T2_OCOL = 416;              // O accumulator of tile t: columns 416 + 32 t .. + 31 ([P Vhi | P Vlo])
 constexpr int T2_XCOL = 480;              // exchange columns of tile t: 480 + 16 t: l[head & 1][part] (6), candidates (4), chosen (1)
@@ -60,6 +62,9 @@ constexpr int T2_XCOL = 480;              // exchange columns of tile t: 480 + 1
 #endif
 #ifndef T2_POLY
 #define T2_POLY 0                         // of every 16 exponentials, this many go through the FMA-pipe polynomial
+#endif
+#ifndef T2_KB_CTAS_PER_SM
+#define T2_KB_CTAS_PER_SM 2               // key-block kernels (N > 208): CTAs per SM the register budget is set for
 #endif
 constexpr float kT2InvSqrtH = 0.08838834764831845f;   // 1/sqrt(128)
 
@@ -97,34 +102,44 @@ __host__ __device__ inline size_t t2_voff(int NP, int j) {
   return b;
 }
 __host__ __device__ inline size_t t2_szk2(int NP) { return (size_t)NP * 128; }
-__host__ __device__ inline size_t t2_img_bytes(int NP) { return 8 * t2_szk(NP) + 8 * t2_szv(NP) + 4 * t2_szk2(NP); }
+// Key blocks (N > 208): the keys are processed in NKB blocks of NPB <= 208 keys (NPT = NKB * NPB padded keys in all);
+// K and K2 keep one [NPT keys x row] block per head / column block (a key block is a row range of it), V has its
+// part blocks per (head, key block).
+__host__ __device__ inline size_t t2_img_bytes(int NPB, int NKB = 1) {
+  return 8 * t2_szk(NPB * NKB) + 8 * (size_t)NKB * t2_szv(NPB) + 4 * t2_szk2(NPB * NKB);
+}
+__host__ __device__ constexpr int t2_per_step(int NKB) { return 3 + (8 * NKB - 1) * 6 + 3 + 12 * NKB; }
 
-// stage i of a decode step's operand stream: K_0^{0,1,2}; per head h: V_h^j, K_{h+1}^j (h < 7) for j = 0,1,2;
-// K2_i^j for i = 0..3, j = 0,1,2 -- (offset into the instance's image, bytes), looked up by the producer
-__host__ __device__ inline uint2 t2_stage_entry(int NP, int i) {
-  const T2Parts parts = t2_parts(NP);
-  const size_t szk = t2_szk(NP), szv = t2_szv(NP), szk2 = t2_szk2(NP);
+// stage i of a decode step's operand stream -- (offset into the instance's image, bytes), looked up by the producer.
+// With it = h * NKB + kb running over (head, key block): K_0^{0,1,2}; per it: V_it^j, K_{it+1}^j (it + 1 < 8 NKB) for
+// j = 0,1,2; then per key block kb: K2_i^j for i = 0..3, j = 0,1,2.
+__host__ __device__ inline uint2 t2_stage_entry(int NPB, int i, int NKB = 1) {
+  const T2Parts parts = t2_parts(NPB);
+  const int NPT = NPB * NKB, NIT = 8 * NKB;
+  const size_t szk = t2_szk(NPT), szvb = t2_szv(NPB), szk2 = t2_szk2(NPT);
   const int c1 = parts.cb[1], c2 = parts.cb[2], c3 = parts.cb[3];
   auto keys_of = [&](int j) { return (uint32_t)(16 * (j == 0 ? c1 : (j == 1 ? c2 - c1 : c3 - c2))); };
   auto krow_of = [&](int j) { return (uint32_t)(16 * (j == 0 ? 0 : (j == 1 ? c1 : c2))); };
   auto vbytes_of = [&](int j) { return (uint32_t)t2_vblocks((int)keys_of(j)) * 4096u; };
   auto voff_of = [&](int j) { return (size_t)((j > 0 ? vbytes_of(0) : 0u) + (j > 1 ? vbytes_of(1) : 0u)); };
+  auto k_of = [&](int it, int j) { return (size_t)(it / NKB) * szk + ((size_t)(it % NKB) * NPB + krow_of(j)) * 64; };
+  auto v_of = [&](int it, int j) { return 8 * szk + ((size_t)(it / NKB) * NKB + (size_t)(it % NKB)) * szvb + voff_of(j); };
   size_t off;
   uint32_t bytes;
   if (i < 3) {                                   // K_0^j
-    off = (size_t)krow_of(i) * 64;
+    off = k_of(0, i);
     bytes = keys_of(i) * 64u;
-  } else if (i < 3 + 42) {                       // heads 0..6: V_h^j, K_{h+1}^j
-    const int r = i - 3, h = r / 6, e = r - 6 * h, j = e >> 1;
-    if ((e & 1) == 0) { off = 8 * szk + (size_t)h * szv + voff_of(j); bytes = vbytes_of(j); }
-    else { off = (size_t)(h + 1) * szk + (size_t)krow_of(j) * 64; bytes = keys_of(j) * 64u; }
-  } else if (i < 48) {                           // head 7: V_7^j
-    const int j = i - 45;
-    off = 8 * szk + (size_t)7 * szv + voff_of(j);
+  } else if (i < 3 + 6 * (NIT - 1)) {            // it = 0 .. NIT-2: V_it^j, K_{it+1}^j
+    const int r = i - 3, it = r / 6, e = r - 6 * it, j = e >> 1;
+    if ((e & 1) == 0) { off = v_of(it, j); bytes = vbytes_of(j); }
+    else { off = k_of(it + 1, j); bytes = keys_of(j) * 64u; }
+  } else if (i < 6 + 6 * (NIT - 1)) {            // last (head, key block): V^j
+    const int j = i - (3 + 6 * (NIT - 1));
+    off = v_of(NIT - 1, j);
     bytes = vbytes_of(j);
-  } else {                                       // K2_i^j
-    const int r = i - 48, blk = r / 3, j = r - 3 * blk;
-    off = 8 * szk + 8 * szv + (size_t)blk * szk2 + (size_t)krow_of(j) * 128;
+  } else {                                       // K2_i^j of key block kb
+    const int r = i - (6 + 6 * (NIT - 1)), q = r / 3, j = r - 3 * q, kb = q >> 2, blk = q & 3;
+    off = 8 * szk + 8 * (size_t)NKB * szvb + (size_t)blk * szk2 + ((size_t)kb * NPB + krow_of(j)) * 128;
     bytes = keys_of(j) * 128u;
   }
   return make_uint2((uint32_t)off, bytes);
@@ -132,10 +147,11 @@ __host__ __device__ inline uint2 t2_stage_entry(int NP, int i) {
 
 // mean key of every head (the centring vector): kbar[b][c] = mean_n K[b, n, c]; block 0 also writes the stage table
 // that the producers of the single-tile CTAs read (they have no shared memory to spare for it)
-__global__ void __launch_bounds__(128) decode_tc2_kbar_kernel(const float* __restrict__ proj, int N, int NP,
+__global__ void __launch_bounds__(128) decode_tc2_kbar_kernel(const float* __restrict__ proj, int N, int NPB, int NKB,
                                                               float* __restrict__ kbar, uint2* __restrict__ stage_tab) {
   const int b = blockIdx.x, c = threadIdx.x;
-  if (b == 0 && c < T2_PER_STEP) stage_tab[c] = t2_stage_entry(NP, c);
+  if (b == 0)
+    for (int i = c; i < t2_per_step(NKB); i += 128) stage_tab[i] = t2_stage_entry(NPB, i, NKB);
   const float* pb = proj + (size_t)b * N * PROJ + c;
   float s = 0.f;
   for (int n = 0; n < N; ++n) s += __ldg(pb + (size_t)n * PROJ);
@@ -144,10 +160,11 @@ __global__ void __launch_bounds__(128) decode_tc2_kbar_kernel(const float* __res
 
 // proj fp32 [Bp*N, 640] (K | V | QL | QF | K2) -> operand image.  grid = (blocks per instance, Bp)
 __global__ void __launch_bounds__(256)
-decode_tc2_pack_kernel(const float* __restrict__ proj, const float* __restrict__ kbar, int Bp, int N, int NP,
+decode_tc2_pack_kernel(const float* __restrict__ proj, const float* __restrict__ kbar, int Bp, int N, int NPB, int NKB,
                        unsigned char* __restrict__ img) {
-  const size_t szk = t2_szk(NP), szv = t2_szv(NP), szk2 = t2_szk2(NP), per = t2_img_bytes(NP);
-  const T2Parts parts = t2_parts(NP);
+  const int NP = NPB * NKB;                 // all padded keys
+  const size_t szk = t2_szk(NP), szvb = t2_szv(NPB), szv = (size_t)NKB * szvb, szk2 = t2_szk2(NP), per = t2_img_bytes(NPB, NKB);
+  const T2Parts parts = t2_parts(NPB);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   for (int b = blockIdx.y; b < Bp; b += gridDim.y) {
     const float* pb = proj + (size_t)b * N * PROJ;
@@ -193,11 +210,12 @@ decode_tc2_pack_kernel(const float* __restrict__ proj, const float* __restrict__
         hi[k] = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
         lo[k] = v - hi[k];
       }
-      const int ch = r4 >> 2;                                   // 16-key chunk of these keys
+      const int kb = (r4 * 4) / NPB;                            // key block of these keys
+      const int ch = (r4 * 4 - kb * NPB) >> 4;                  // 16-key chunk inside the block
       const int j = ch >= parts.cb[2] ? 2 : (ch >= parts.cb[1] ? 1 : 0);
-      const int kl = r4 * 4 - 16 * parts.cb[j];                 // key index inside the part
+      const int kl = r4 * 4 - kb * NPB - 16 * parts.cb[j];      // key index inside the part
       const int h = c >> 4, d = c & 15;
-      unsigned char* blk = base + 8 * szk + (size_t)h * szv + t2_voff(NP, j) + (size_t)(kl >> 5) * 4096;
+      unsigned char* blk = base + 8 * szk + (size_t)h * szv + (size_t)kb * szvb + t2_voff(NPB, j) + (size_t)(kl >> 5) * 4096;
       *(float4*)(blk + tc::sw128_off(d, (kl & 31) >> 2)) = make_float4(hi[0], hi[1], hi[2], hi[3]);
       *(float4*)(blk + tc::sw128_off(16 + d, (kl & 31) >> 2)) = make_float4(lo[0], lo[1], lo[2], lo[3]);
     }
@@ -224,7 +242,7 @@ struct T2Args {
 };
 
 // barrier slots: per row tile, then the shared ring (T2B_FULL, T2B_EMPTY, T2B_TOTAL depend on the variant)
-enum { T2B_SFULL = 0, T2B_PFULL = 3, T2B_OFULL = 6, T2B_OREADY = 7, T2B_QFULL = 8, T2B_UFULL = 9, T2B_PER_TILE = 10 };
+enum { T2B_SFULL = 0, T2B_PFULL = 3, T2B_OFULL = 6, T2B_OREADY = 7, T2B_QFULL = 8, T2B_UFULL = 9, T2B_UDONE = 10, T2B_PER_TILE = 11 };
 constexpr int T2_FULL_BARS = 8;     // "landed" barriers: stage `it` signals barrier it % 8 (see land() in run_helper)
 __host__ __device__ constexpr int t2_bar_total(bool one) {
   return (one ? 1 : 2) * T2B_PER_TILE + T2_FULL_BARS + (one ? T2_SLOTS_ONE : T2_SLOTS);
@@ -236,11 +254,20 @@ __host__ __device__ constexpr int t2_bar_total(bool one) {
 // lock-step -- they share the operand ring -- so their softmax phases collide on the MUFU pipe and their serial tails
 // leave it idle together.  Two independent CTAs drift apart and fill each other's gaps; the price is that every
 // operand block is fetched from L2 once per tile instead of once per instance.
-template <bool LOGITS, bool DEBUG, bool SPLIT, bool SAMPLE, bool ONE>
-__global__ void __launch_bounds__(ONE ? T2_THREADS_ONE : T2_THREADS, ONE ? 2 : 1) decode_tc2_kernel(const T2Args A) {
+//
+// NKB > 1 (N > 208, single-tile CTAs only, one per SM): the keys of an instance are processed in NKB blocks of
+// A.NP <= 208 keys.  P = 2^S carries no shift, so the blocks of a head simply accumulate into the same O and the same
+// row sums: per head the chain is NKB x [S block -> softmax -> P V], the accumulator is drained after the last block;
+// the pointer logits are computed and scanned block by block (the score columns hold one block at a time), with the
+// running arg-max carried across the blocks.
+template <bool LOGITS, bool DEBUG, bool SPLIT, bool SAMPLE, bool ONE, int NKB = 1>
+__global__ void __launch_bounds__(ONE ? T2_THREADS_ONE : T2_THREADS, ONE ? (NKB == 1 ? 2 : T2_KB_CTAS_PER_SM) : 1) decode_tc2_kernel(const T2Args A) {
   static_assert(!ONE || (SPLIT && !DEBUG), "single-tile CTAs: SPLIT launches, no debug dump");
+  static_assert(NKB == 1 || (ONE && !SAMPLE), "key blocks: single-tile CTAs, greedy or teacher-forced");
+  constexpr int NIT = NH * NKB;             // (head, key block) iterations of the glimpse per decode step
   constexpr int T2_THREADS = ONE ? htsp::T2_THREADS_ONE : htsp::T2_THREADS;     // (shadow the two-tile constants)
   constexpr int T2_SLOTS = ONE ? htsp::T2_SLOTS_ONE : htsp::T2_SLOTS;
+  constexpr int T2_SLOT = NKB > 1 ? htsp::T2_SLOT_KB : htsp::T2_SLOT;     // (the smaller slots leave room for c0 of all keys with two CTAs per SM)
   constexpr int TILES = ONE ? 1 : 2;
   constexpr int T2B_FULL = TILES * T2B_PER_TILE, T2B_EMPTY = T2B_FULL + T2_FULL_BARS, T2B_TOTAL = T2B_EMPTY + T2_SLOTS;
   constexpr int T2_OCOL = ONE ? 208 : htsp::T2_OCOL, T2_XCOL = ONE ? 240 : htsp::T2_XCOL, TCOLS = ONE ? 256 : 512;
@@ -255,25 +282,27 @@ __global__ void __launch_bounds__(ONE ? T2_THREADS_ONE : T2_THREADS, ONE ? 2 : 1
   const int G = SPLIT ? min(A.rows_per_cta, GT - r0) : A.G;   // rows of this CTA, from row r0 of the instance
   const int n_steps = N - 2;
   const int n_tiles = (!ONE && G > 128) ? 2 : 1;
-  const T2Parts parts = t2_parts(NP);
-  constexpr int PER_STEP = T2_PER_STEP;
+  const T2Parts parts = t2_parts(NP);      // NP = keys per block (= all padded keys when NKB == 1)
+  const int NPT = NKB * NP;                // all padded keys
+  constexpr int PER_STEP = t2_per_step(NKB);
 
   unsigned char* staging = smem;                                         // TILES x 64 KB
   unsigned char* ring = smem + TILES * T2_TILE_STAGING;                  // T2_SLOTS x 12 KB
-  float* c0s = (float*)(ring + (size_t)T2_SLOTS * T2_SLOT);              // [NP]
-  uint64_t* bars = (uint64_t*)(c0s + NP);
+  float* c0s = (float*)(ring + (size_t)T2_SLOTS * T2_SLOT);              // [NPT]
+  uint64_t* bars = (uint64_t*)(c0s + NPT);
   uint32_t* tmem_slot = (uint32_t*)(bars + T2B_TOTAL);
-  uint2* stage_tab = (uint2*)(tmem_slot + 4);                            // [PER_STEP] (image offset, bytes) of a step's stages (not ONE)
-  const uint2* stage_tab_g = (const uint2*)(A.img - 1024);               // the same table in global memory (ONE)
+  uint2* stage_tab = (uint2*)(tmem_slot + 2);                            // [PER_STEP] (image offset, bytes) of a step's stages (not ONE)
+  const uint2* stage_tab_g = (const uint2*)(A.img - 2048);               // the same table in global memory (ONE)
   const uint32_t bar0 = tc::smem_u32(bars);
   auto TBAR = [&](int t, int i) { return bar0 + 8u * (uint32_t)(t * T2B_PER_TILE + i); };
   auto RBAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
 
-  const unsigned char* imgb = A.img + (size_t)b * t2_img_bytes(NP);
+  const unsigned char* imgb = A.img + (size_t)b * t2_img_bytes(NP, NKB);
   const float* projb = A.proj + (size_t)b * N * PROJ;
 
   if ((tc::smem_u32(smem) & 1023u) != 0u) __trap();   // swizzle atoms need 1024-byte alignment
   if (G > (ONE ? 128 : 224)) __trap();                 // tile 1 has three lane quarters (the host splits larger instances)
+  if (NKB > 1 && NP > T2_KB_MAX_NPB) __trap();         // key-block ring slots hold parts of at most 64 keys
   if (tid == 0) {
     for (int t = 0; t < TILES; ++t) {
       const int rows_t = min(128, G - 128 * t);
@@ -286,6 +315,7 @@ __global__ void __launch_bounds__(ONE ? T2_THREADS_ONE : T2_THREADS, ONE ? 2 : 1
       tc::mbar_init(TBAR(t, T2B_OREADY), warps_t);
       tc::mbar_init(TBAR(t, T2B_QFULL), T2_PARTS * warps_t);
       tc::mbar_init(TBAR(t, T2B_UFULL), T2_PARTS);           // one commit per key part (issuer + two helpers)
+      tc::mbar_init(TBAR(t, T2B_UDONE), T2_PARTS * warps_t); // (key blocks) the logits of a block have been scanned
     }
     for (int s = 0; s < T2_FULL_BARS; ++s) tc::mbar_init(RBAR(T2B_FULL + s), 1);
     for (int s = 0; s < T2_SLOTS; ++s) tc::mbar_init(RBAR(T2B_EMPTY + s), n_tiles);      // a slot is released by every tile's issuer
@@ -293,7 +323,7 @@ __global__ void __launch_bounds__(ONE ? T2_THREADS_ONE : T2_THREADS, ONE ? 2 : 1
   }
   // zero the A tiles (rows that never receive a query must hold finite values)
   for (int i = tid; i < TILES * T2_TILE_STAGING / 16; i += T2_THREADS) ((uint4*)staging)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < NP; i += T2_THREADS) c0s[i] = i < N ? __ldg(&A.c0[(size_t)b * N + i]) : 0.f;
+  for (int i = tid; i < NPT; i += T2_THREADS) c0s[i] = i < N ? __ldg(&A.c0[(size_t)b * N + i]) : 0.f;
   if (!ONE && tid < PER_STEP) stage_tab[tid] = t2_stage_entry(NP, tid);
   if (warp == 3) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)),
@@ -349,29 +379,36 @@ __global__ void __launch_bounds__(ONE ? T2_THREADS_ONE : T2_THREADS, ONE ? 2 : 1
         }
         __syncwarp();
       }
-      for (int i = 0; i < 4; ++i) {
-        const int half = i & 1;
-        const uint32_t o_hi = (stg >> 4) + half * 1024, o_lo = o_hi + 2048;
-        // (the parity of a ring barrier only tells the current use from the previous one: a stage may be waited for
-        // once the stage eight positions earlier has been consumed by this tile -- true after OREADY, not before)
-        if (i == 0) {
-          tc::mbar_wait(TBAR(t, T2B_OREADY), step & 1);
+#pragma unroll 1
+      for (int kb = 0; kb < NKB; ++kb) {
+        if (NKB > 1 && kb > 0) {      // the softmax warps have scanned the previous block's logits
+          tc::mbar_wait(TBAR(t, T2B_UDONE), (uint32_t)(step * NKB + kb - 1) & 1u);
           tc::fence_after();
         }
-        const uint32_t sk = land(base + (uint32_t)(48 + 3 * i + j));
-        const uint32_t kb = (ring0 + sk * T2_SLOT) >> 4;
-        if (tc::elect_one()) {
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            tc::mma_ss_lo(dSj, o_hi + kk * 2, kb + kk * 2, idK, (i | kk) != 0);
-            if (i < 2) tc::mma_ss_lo(dSj, o_lo + kk * 2, kb + kk * 2, idK, 1);
+        for (int i = 0; i < 4; ++i) {
+          const int half = i & 1;
+          const uint32_t o_hi = (stg >> 4) + half * 1024, o_lo = o_hi + 2048;
+          // (the parity of a ring barrier only tells the current use from the previous one: a stage may be waited for
+          // once the stage eight positions earlier has been consumed by this tile -- true after OREADY, not before)
+          if (i == 0 && kb == 0) {
+            tc::mbar_wait(TBAR(t, T2B_OREADY), step & 1);
+            tc::fence_after();
           }
-          tc::commit(RBAR(T2B_EMPTY + sk));
+          const uint32_t sk = land(base + (uint32_t)(6 + 6 * (NIT - 1) + 3 * (4 * kb + i) + j));
+          const uint32_t kb_ = (ring0 + sk * T2_SLOT) >> 4;
+          if (tc::elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              tc::mma_ss_lo(dSj, o_hi + kk * 2, kb_ + kk * 2, idK, (i | kk) != 0);
+              if (i < 2) tc::mma_ss_lo(dSj, o_lo + kk * 2, kb_ + kk * 2, idK, 1);
+            }
+            tc::commit(RBAR(T2B_EMPTY + sk));
+          }
+          __syncwarp();
         }
+        if (tc::elect_one()) tc::commit(TBAR(t, T2B_UFULL));
         __syncwarp();
       }
-      if (tc::elect_one()) tc::commit(TBAR(t, T2B_UFULL));
-      __syncwarp();
     }
   };
 
@@ -425,15 +462,17 @@ __global__ void __launch_bounds__(ONE ? T2_THREADS_ONE : T2_THREADS, ONE ? 2 : 1
         __syncwarp();
       };
       // O (+)= P_h^j [Vhi | Vlo]: A = fp32 words in the score columns of part j, B = V^T blocks of 32 keys in slot sv
-      auto issue_PV = [&](int j, uint32_t sv) {
+      // (first: the first part of the first key block of a head starts the accumulator; last: the last part of the
+      // last key block publishes it)
+      auto issue_PV = [&](int j, uint32_t sv, bool first, bool last) {
         const uint32_t vb = (ring0 + sv * T2_SLOT) >> 4;
         const uint32_t pa = dS + (uint32_t)(16 * parts.cb[j]);
         const int n8 = kk8[j];
         if (tc::elect_one()) {
 #pragma unroll 1
           for (int ks = 0; ks < n8; ++ks)
-            tc::mma_ts_tf32_lo(dO, pa + 8 * ks, vb + (ks >> 2) * 256 + (ks & 3) * 2, idO, (j | ks) != 0);
-          if (j == T2_PARTS - 1) tc::commit(TBAR(t, T2B_OFULL));
+            tc::mma_ts_tf32_lo(dO, pa + 8 * ks, vb + (ks >> 2) * 256 + (ks & 3) * 2, idO, !(first && ks == 0));
+          if (last) tc::commit(TBAR(t, T2B_OFULL));
         }
         __syncwarp();
       };
@@ -445,48 +484,56 @@ __global__ void __launch_bounds__(ONE ? T2_THREADS_ONE : T2_THREADS, ONE ? 2 : 1
         tick(3);
         issue_S(0, 0, k0);
         release(k0);
-        for (int h = 0; h < NH; ++h) {
-          const uint32_t par = (uint32_t)(step * NH + h) & 1u;
+        for (int it = 0; it < NIT; ++it) {               // (head, key block)
+          const uint32_t par = (uint32_t)(step * NIT + it) & 1u;
+          const int kb = NKB == 1 ? 0 : it % NKB;
 #pragma unroll
           for (int j = 0; j < T2_PARTS; ++j) {
-            const uint32_t nv = base + (h + 1 < NH ? (uint32_t)(3 + 6 * h + 2 * j) : (uint32_t)(45 + j));
-            const uint32_t sv = land(nv);                               // V_h^j
-            const uint32_t sk = (h + 1 < NH) ? land(nv + 1) : 0u;       // K_{h+1}^j
+            const uint32_t nv = base + (it + 1 < NIT ? (uint32_t)(3 + 6 * it + 2 * j) : (uint32_t)(3 + 6 * (NIT - 1) + j));
+            const uint32_t sv = land(nv);                               // V of (head, block), part j
+            const uint32_t sk = (it + 1 < NIT) ? land(nv + 1) : 0u;     // K of the next (head, block), part j
             tick(2);
             tc::mbar_wait(TBAR(t, T2B_PFULL + j), par);
             tc::fence_after();
             tick(1);
-            issue_PV(j, sv);
+            issue_PV(j, sv, kb == 0 && j == 0, kb == NKB - 1 && j == T2_PARTS - 1);
             release(sv);
-            if (h + 1 < NH) {
-              issue_S(h + 1, j, sk);
+            if (it + 1 < NIT) {
+              issue_S((it + 1) / NKB, j, sk);
               release(sk);
             }
           }
         }
-        // pointer logits U = O K2^T into the (consumed) score columns of part 0 (parts 1, 2: helpers)
-        for (int i = 0; i < 4; ++i) {
-          const int half = i & 1;                    // O / K2 columns 64*half .. +63
-          const uint32_t o_hi = (stg >> 4) + half * 1024, o_lo = o_hi + 2048;
-          const uint32_t sk = land(base + (uint32_t)(48 + 3 * i));
-          if (i == 0) {
-            tc::mbar_wait(TBAR(t, T2B_OREADY), step & 1);
+        // pointer logits U = O K2^T into the (consumed) score columns of part 0 (parts 1, 2: helpers), key block by key block
+#pragma unroll 1
+        for (int kb = 0; kb < NKB; ++kb) {
+          if (NKB > 1 && kb > 0) {
+            tc::mbar_wait(TBAR(t, T2B_UDONE), (uint32_t)(step * NKB + kb - 1) & 1u);
             tc::fence_after();
-            tick(4);
           }
-          const uint32_t kb = (ring0 + sk * T2_SLOT) >> 4;
-          if (tc::elect_one()) {
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              tc::mma_ss_lo(dS, o_hi + kk * 2, kb + kk * 2, idK[0], (i | kk) != 0);
-              if (i < 2) tc::mma_ss_lo(dS, o_lo + kk * 2, kb + kk * 2, idK[0], 1);
+          for (int i = 0; i < 4; ++i) {
+            const int half = i & 1;                    // O / K2 columns 64*half .. +63
+            const uint32_t o_hi = (stg >> 4) + half * 1024, o_lo = o_hi + 2048;
+            const uint32_t sk = land(base + (uint32_t)(6 + 6 * (NIT - 1) + 3 * (4 * kb + i)));
+            if (i == 0 && kb == 0) {
+              tc::mbar_wait(TBAR(t, T2B_OREADY), step & 1);
+              tc::fence_after();
+              tick(4);
             }
-            tc::commit(RBAR(T2B_EMPTY + sk));
+            const uint32_t kb_ = (ring0 + sk * T2_SLOT) >> 4;
+            if (tc::elect_one()) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                tc::mma_ss_lo(dS, o_hi + kk * 2, kb_ + kk * 2, idK[0], (i | kk) != 0);
+                if (i < 2) tc::mma_ss_lo(dS, o_lo + kk * 2, kb_ + kk * 2, idK[0], 1);
+              }
+              tc::commit(RBAR(T2B_EMPTY + sk));
+            }
+            __syncwarp();
           }
+          if (tc::elect_one()) tc::commit(TBAR(t, T2B_UFULL));
           __syncwarp();
         }
-        if (tc::elect_one()) tc::commit(TBAR(t, T2B_UFULL));
-        __syncwarp();
         tick(5);
       }
       if (DEBUG && b == 0 && lane == 0) {
@@ -536,21 +583,28 @@ __global__ void __launch_bounds__(ONE ? T2_THREADS_ONE : T2_THREADS, ONE ? 2 : 1
       bool bad = false;                              // softmax sum left the fp32 range (part 0 only)
       float logp_acc = 0.f;                          // SAMPLE, part 0: sum of log p(sampled node) over the steps
 
-      // visited flags of THIS warp's keys only (bit k = key 16 c_lo + k; at most 96 keys per part); padded keys
-      // (>= N) are permanently visited
+      // visited flags of THIS warp's keys only (per key block kb: bit k = key kb NP + 16 c_lo + k; at most 96 keys per
+      // part and block); padded keys (>= N) are permanently visited.  (A key of another part or block sets, at most,
+      // a bit beyond this warp's chunks, which nothing reads.)
       const int nc = c_hi - c_lo;
-      unsigned pv[3];
+      unsigned pv[NKB][3];
 #pragma unroll
-      for (int w = 0; w < 3; ++w) {
-        const int lo = 16 * c_lo + 32 * w;
-        pv[w] = (lo + 32 <= N) ? 0u : ((N <= lo) ? 0xffffffffu : (0xffffffffu << (N - lo)));
+      for (int kb = 0; kb < NKB; ++kb) {
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+          const int lo = kb * NP + 16 * c_lo + 32 * w;
+          pv[kb][w] = (lo + 32 <= N) ? 0u : ((N <= lo) ? 0xffffffffu : (0xffffffffu << (N - lo)));
+        }
       }
       int cur = 0, cnt = 0;
       auto mark = [&](int a) {
-        const unsigned rel = (unsigned)(a - 16 * c_lo);
-        const unsigned bit = rel < 96u ? (1u << (rel & 31u)) : 0u;
 #pragma unroll
-        for (int w = 0; w < 3; ++w) pv[w] |= ((rel >> 5) == (unsigned)w) ? bit : 0u;
+        for (int kb = 0; kb < NKB; ++kb) {
+          const unsigned rel = (unsigned)(a - kb * NP - 16 * c_lo);
+          const unsigned bit = rel < 96u ? (1u << (rel & 31u)) : 0u;
+#pragma unroll
+          for (int w = 0; w < 3; ++w) pv[kb][w] |= ((rel >> 5) == (unsigned)w) ? bit : 0u;
+        }
       };
       // visit(a) with source<->target coupling (train_path_solver.py:45-66); only part 0 records pi
       auto visit = [&](int a) {
@@ -578,7 +632,7 @@ __global__ void __launch_bounds__(ONE ? T2_THREADS_ONE : T2_THREADS, ONE ? 2 : 1
 
       // ---- P = 2^S of this warp's key chunks of head h, in place; returns the row sum of what the tensor core
       // will read (the top 19 bits of every word)
-      auto softmax_pass = [&](int step, int h) {
+      auto softmax_pass = [&](int step, int h, const unsigned (&pvb)[3]) {
         float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
@@ -586,7 +640,7 @@ __global__ void __launch_bounds__(ONE ? T2_THREADS_ONE : T2_THREADS, ONE ? 2 : 1
             const int c = c_lo + i;
             uint32_t s[32];
             tld<16>(tS + 16 * c, s);
-            const unsigned bits = (pv[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
+            const unsigned bits = (pvb[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
             tld_wait16(s);
             if (DEBUG && b == 0 && step == A.dbg_step) {
               float* dSd = A.dbg + ((size_t)(t * 8 + h) * 128 + row) * NP + 16 * c;
@@ -617,9 +671,10 @@ __global__ void __launch_bounds__(ONE ? T2_THREADS_ONE : T2_THREADS, ONE ? 2 : 1
         return acc.x + acc.y;
       };
       // publish the row sum of this part, then P itself
-      auto publish = [&](int h, float l) {
-        asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tX + (h & 1) * 3 + part), "r"(__float_as_uint(l))
-                     : "memory");
+      auto publish = [&](int h, float l, bool with_sum) {
+        if (with_sum)
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tX + (h & 1) * 3 + part), "r"(__float_as_uint(l))
+                       : "memory");
         tc::st_wait();
         tc::fence_before();
         __syncwarp();
@@ -732,18 +787,22 @@ __global__ void __launch_bounds__(ONE ? T2_THREADS_ONE : T2_THREADS, ONE ? 2 : 1
         // ------------------------------------------------------------ glimpse, one head at a time
 #pragma unroll 1
         for (int h = 0; h < NH; ++h) {
-          tc::mbar_wait(TBAR(t, T2B_SFULL + part), (step * NH + h) & 1);
-          tc::fence_after();
-          tick(0);
-          const float l = softmax_pass(step, h);
-          tick(1);
-          // the previous head's accumulator must be drained before this head's first P V (part 0, which the
-          // issuer serves first) overwrites it
-          if (part == 0 && h > 0) {
-            drain_o(step, h - 1);
-            tick(2);
+          float l = 0.f;                 // row sum of this part over the key blocks of the head
+#pragma unroll
+          for (int kb = 0; kb < NKB; ++kb) {
+            tc::mbar_wait(TBAR(t, T2B_SFULL + part), (uint32_t)((step * NH + h) * NKB + kb) & 1u);
+            tc::fence_after();
+            tick(0);
+            l += softmax_pass(step, h, pv[kb]);
+            tick(1);
+            // the previous head's accumulator must be drained before this head's first P V (part 0 of key block 0,
+            // which the issuer serves first) overwrites it
+            if (part == 0 && h > 0 && kb == 0) {
+              drain_o(step, h - 1);
+              tick(2);
+            }
+            publish(h, l, kb == NKB - 1);
           }
-          publish(h, l);
         }
         if (part == 0) {
           drain_o(step, NH - 1);
@@ -757,20 +816,20 @@ __global__ void __launch_bounds__(ONE ? T2_THREADS_ONE : T2_THREADS, ONE ? 2 : 1
         // ------------------------------------------------------------ pointer logits + arg-max
         // Each warp of the trio scans its own key chunks and reduces them to one candidate (clipped logit, key);
         // part 0 merges the three (ties -> lower key = the lower part).
-        tc::mbar_wait(TBAR(t, T2B_UFULL), step & 1);
-        tc::fence_after();
-        tick(3);
         float best = -INFINITY;
         int idx = 0x7fffffff;
         float zbest = 0.f, sumexp = 0.f;       // SAMPLE with log-probabilities (train_path_solver.py:394-414)
         float* lo_out = nullptr;
         if (LOGITS && A.logits_out != nullptr)
           lo_out = A.logits_out + (((size_t)b * GT + r0 + gc) * n_steps + step) * N;
+        // candidates of one key block (koff = its first key, pvb = its visited words)
+        float bk, zk, sek;
+        int ik;
         // pass(EXACT): EXACT compares the clipped logits 10*tanh(.) themselves (models.py:438-440); otherwise the
         // monotone pre-activation is compared, which picks the same key except when two clipped logits round to
         // the same float (handled by re-running EXACT near the clip).  Four independent running maxima (column
         // slot mod 4), merged with the lowest key winning ties (torch.argmax returns the first maximum).
-        auto pass = [&](auto exact_tag) {
+        auto pass = [&](auto exact_tag, const int koff, const unsigned (&pvb)[3]) {
           constexpr bool EXACT = decltype(exact_tag)::value;
           float bj[4];
           int kj[4];
@@ -784,14 +843,14 @@ __global__ void __launch_bounds__(ONE ? T2_THREADS_ONE : T2_THREADS, ONE ? 2 : 1
             if (i >= nc) continue;
             const int c = c_lo + i;
             tld<16>(tS + 16 * c, u);
-            const unsigned bits = (pv[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
+            const unsigned bits = (pvb[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
             tld_wait16(u);
             if (DEBUG && b == 0 && step == A.dbg_step) {
               float* dU = A.dbg + (size_t)2 * 8 * 128 * NP + (size_t)256 * 128 + (size_t)(t * 128 + row) * NP + 16 * c;
 #pragma unroll
               for (int j = 0; j < 16; ++j) dU[j] = __uint_as_float(u[j]);
             }
-            const float4* cc4 = (const float4*)(c0s + 16 * c);
+            const float4* cc4 = (const float4*)(c0s + koff + 16 * c);
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
               const float4 cc = cc4[j4];
@@ -812,28 +871,42 @@ __global__ void __launch_bounds__(ONE ? T2_THREADS_ONE : T2_THREADS, ONE ? 2 : 1
                   z += tcd_gumbel(ra[jj]);
                 }
                 if ((bits >> j) & 1u) z = -INFINITY;
-                if (LOGITS && lo_out != nullptr && valid && 16 * c + j < N) lo_out[16 * c + j] = z;
-                if (z > bj[jj]) { bj[jj] = z; kj[jj] = 16 * c + j; if (SAMPLE) zj[jj] = zc; }
+                if (LOGITS && lo_out != nullptr && valid && koff + 16 * c + j < N) lo_out[koff + 16 * c + j] = z;
+                if (z > bj[jj]) { bj[jj] = z; kj[jj] = koff + 16 * c + j; if (SAMPLE) zj[jj] = zc; }
               }
             }
           }
-          best = bj[0];
-          idx = kj[0];
-          zbest = zj[0];
-          sumexp = se;
+          bk = bj[0];
+          ik = kj[0];
+          zk = zj[0];
+          sek = se;
 #pragma unroll
           for (int j = 1; j < 4; ++j)
-            if (bj[j] > best || (bj[j] == best && kj[j] < idx)) { best = bj[j]; idx = kj[j]; zbest = zj[j]; }
+            if (bj[j] > bk || (bj[j] == bk && kj[j] < ik)) { bk = bj[j]; ik = kj[j]; zk = zj[j]; }
         };
-        if (LOGITS || SAMPLE) {
-          pass(std::true_type{});
-        } else {
-          pass(std::false_type{});
-          if (__any_sync(0xffffffffu, valid && best * kT2InvSqrtH > 3.0f)) {
-            pass(std::true_type{});
+#pragma unroll
+        for (int kb = 0; kb < NKB; ++kb) {
+          // (key blocks: the score columns hold the logits of one block at a time)
+          tc::mbar_wait(TBAR(t, T2B_UFULL), (uint32_t)(step * NKB + kb) & 1u);
+          tc::fence_after();
+          tick(3);
+          if (LOGITS || SAMPLE) {
+            pass(std::true_type{}, kb * NP, pv[kb]);
           } else {
-            best = (best == -INFINITY) ? best : clip_tanh10(best * kT2InvSqrtH);   // candidates are exchanged as clipped logits
+            pass(std::false_type{}, kb * NP, pv[kb]);
+            if (__any_sync(0xffffffffu, valid && bk * kT2InvSqrtH > 3.0f)) {
+              pass(std::true_type{}, kb * NP, pv[kb]);
+            } else {
+              bk = (bk == -INFINITY) ? bk : clip_tanh10(bk * kT2InvSqrtH);   // candidates are exchanged as clipped logits
+            }
           }
+          if (NKB > 1) {               // this warp has read the block's logits: the issuers may overwrite them
+            tc::fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(TBAR(t, T2B_UDONE));
+          }
+          if (kb == 0 || bk > best) { best = bk; idx = ik; zbest = zk; }     // ties keep the lower block's key
+          sumexp += sek;
         }
         tick(4);
         int a;
@@ -864,8 +937,9 @@ __global__ void __launch_bounds__(ONE ? T2_THREADS_ONE : T2_THREADS, ONE ? 2 : 1
                        : "memory");
           asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(z1), "+r"(i1), "+r"(z2), "+r"(i2)::"memory");
           int win = 0;
-          if (__uint_as_float(z1) > best) { best = __uint_as_float(z1); idx = (int)i1; win = 1; }     // ties keep the lower part's key
-          if (__uint_as_float(z2) > best) { best = __uint_as_float(z2); idx = (int)i2; win = 2; }
+          // ties keep the lower key (one key block: that of the lower part)
+          if (__uint_as_float(z1) > best || (NKB > 1 && __uint_as_float(z1) == best && (int)i1 < idx)) { best = __uint_as_float(z1); idx = (int)i1; win = 1; }
+          if (__uint_as_float(z2) > best || (NKB > 1 && __uint_as_float(z2) == best && (int)i2 < idx)) { best = __uint_as_float(z2); idx = (int)i2; win = 2; }
           if (SAMPLE) {
             // log p(sampled node) = z - logsumexp(z over the unvisited keys) (softmax of the masked clipped logits,
             // models.py:442; train_path_solver.py:394-414 sums the logarithms over the decode steps)
@@ -954,11 +1028,30 @@ __global__ void __launch_bounds__(ONE ? T2_THREADS_ONE : T2_THREADS, ONE ? 2 : 1
 // host side
 // ------------------------------------------------------------------------------------------
 static int t2_np_of(int N) { return (N + 15) / 16 * 16; }
+// key blocks: one block of all (padded) keys up to 208 keys, else NKB equal blocks of NPB <= 208 keys
+static void t2_blocks_of(int N, int& NPB, int& NKB) {
+  if (t2_np_of(N) <= 208) {
+    NKB = 1;
+    NPB = t2_np_of(N);
+  } else {
+    NKB = (t2_np_of(N) + T2_KB_MAX_NPB - 1) / T2_KB_MAX_NPB;
+    NPB = t2_np_of((N + NKB - 1) / NKB);
+  }
+}
+constexpr int T2_MAX_NKB = 3;
+constexpr size_t T2_TAB_BYTES = 2048;     // stage table in front of the operand images (<= 180 entries of 8 bytes)
 
-bool decode_tc2_supported(int N, int G) { return t2_np_of(N) <= 208 && t2_np_of(N) >= 48 && G <= 256; }
+bool decode_tc2_supported(int N, int G) {
+  int NPB, NKB;
+  t2_blocks_of(N, NPB, NKB);
+  if (NKB == 1) return NPB >= 48 && G <= 256;
+  return NKB <= T2_MAX_NKB && G >= 1;        // key blocks: single-tile CTAs of 128 rows, any number per instance
+}
 size_t decode_tc2_pack_bytes(int Bp, int N) {
-  // [slack to a 1024-byte boundary | stage table, 1 KB | operand images | mean keys]
-  return 1024 + 1024 + align_up((size_t)Bp * t2_img_bytes(t2_np_of(N)), 256) + align_up((size_t)Bp * H * 4, 256);
+  // [slack to a 1024-byte boundary | stage table, 2 KB | operand images | mean keys]
+  int NPB, NKB;
+  t2_blocks_of(N, NPB, NKB);
+  return 1024 + T2_TAB_BYTES + align_up((size_t)Bp * t2_img_bytes(NPB, NKB), 256) + align_up((size_t)Bp * H * 4, 256);
 }
 size_t decode_tc2_dbg_floats(int N) {
   const int NP = t2_np_of(N);
@@ -996,19 +1089,19 @@ static void t2_choose_split(int Bp, int G, bool debug, int& split, int& rows_per
 }
 
 // dynamic shared memory of a CTA: A tiles, ring, c0, barriers, TMEM slot (+ the stage table of the two-tile variant)
-static size_t t2_smem_bytes(int NP, bool one) {
-  return (size_t)(one ? 1 : 2) * T2_TILE_STAGING + (size_t)(one ? T2_SLOTS_ONE : T2_SLOTS) * T2_SLOT + (size_t)NP * 4 +
+static size_t t2_smem_bytes(int NP, bool one, bool key_blocks = false) {
+  return (size_t)(one ? 1 : 2) * T2_TILE_STAGING + (size_t)(one ? T2_SLOTS_ONE : T2_SLOTS) * (key_blocks ? T2_SLOT_KB : T2_SLOT) + (size_t)NP * 4 +
          (size_t)t2_bar_total(one) * 8 + 16 + (one ? 0 : T2_PER_STEP * 8);
 }
 
-template <bool LOGITS, bool DEBUG, bool SPLIT, bool SAMPLE = false, bool ONE = false>
+template <bool LOGITS, bool DEBUG, bool SPLIT, bool SAMPLE = false, bool ONE = false, int NKB = 1>
 static int launch_t2(const T2Args& a, int Bp, cudaStream_t s) {
-  const size_t smem = t2_smem_bytes(a.NP, ONE);
+  const size_t smem = t2_smem_bytes(a.NP * NKB, ONE, NKB > 1);
   if (smem > 227 * 1024) {
     set_error("decode_tc2: N=%d needs %zu bytes of shared memory", a.N, smem);
     return HTSP_ERR_UNSUPPORTED;
   }
-  auto kern = decode_tc2_kernel<LOGITS, DEBUG, SPLIT, SAMPLE, ONE>;
+  auto kern = decode_tc2_kernel<LOGITS, DEBUG, SPLIT, SAMPLE, ONE, NKB>;
   HTSP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (ONE) HTSP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   kernel_timer_begin(s);
@@ -1063,7 +1156,9 @@ static bool t2_use_one(int Bp, int G, int NP, bool debug) {
 
 // CTAs of the rollout kernel that share an SM for such a call: 2 = single-tile CTAs, 1 = two-tile (or row-split) CTAs
 int decode_tc2_ctas_per_sm(int Bp, int N, int G) {
-  return (decode_tc2_supported(N, G) && t2_use_one(Bp, G, t2_np_of(N), false)) ? 2 : 1;
+  if (!decode_tc2_supported(N, G)) return 1;
+  if (t2_np_of(N) > 208) return T2_KB_CTAS_PER_SM;
+  return t2_use_one(Bp, G, t2_np_of(N), false) ? 2 : 1;
 }
 
 int launch_decode_tc2(const float* x, const float* proj, const float* qfix, const float* c0,
@@ -1076,14 +1171,17 @@ int launch_decode_tc2(const float* x, const float* proj, const float* qfix, cons
   HTSP_REQUIRE(sample_seed == nullptr || (dbg == nullptr && logits_out == nullptr && forced_pi == nullptr),
                "sampling rollouts take no teacher forcing, logit capture or debug dump");
   HTSP_REQUIRE(dbg == nullptr || G <= 224, "debug dump: at most 224 rows");
-  const int NP = t2_np_of(N);
-  unsigned char* img = (unsigned char*)(((uintptr_t)pack_ws + 1023) & ~(uintptr_t)1023) + 1024;   // (the stage table sits in the KB before)
-  float* kbar = (float*)(img + align_up((size_t)Bp * t2_img_bytes(NP), 256));
-  decode_tc2_kbar_kernel<<<Bp, 128, 0, s>>>(proj, N, NP, kbar, (uint2*)(img - 1024));
+  int NP, NKB;                            // keys per block (all padded keys when NKB == 1), key blocks
+  t2_blocks_of(N, NP, NKB);
+  HTSP_REQUIRE(NKB == 1 || (sample_seed == nullptr && dbg == nullptr),
+               "decode_tc2 with key blocks (N > 208): greedy and teacher-forced rollouts only");
+  unsigned char* img = (unsigned char*)(((uintptr_t)pack_ws + 1023) & ~(uintptr_t)1023) + T2_TAB_BYTES;   // (the stage table sits in front)
+  float* kbar = (float*)(img + align_up((size_t)Bp * t2_img_bytes(NP, NKB), 256));
+  decode_tc2_kbar_kernel<<<Bp, 128, 0, s>>>(proj, N, NP, NKB, kbar, (uint2*)(img - T2_TAB_BYTES));
   HTSP_CHECK_LAUNCH();
   {
-    const int items = max(NP * 32, (NP >> 2) * 128);
-    decode_tc2_pack_kernel<<<dim3((items + 255) / 256, min(Bp, 65535)), 256, 0, s>>>(proj, kbar, Bp, N, NP, img);
+    const int items = max(NP * NKB * 32, (NP * NKB >> 2) * 128);
+    decode_tc2_pack_kernel<<<dim3((items + 255) / 256, min(Bp, 65535)), 256, 0, s>>>(proj, kbar, Bp, N, NP, NKB, img);
     HTSP_CHECK_LAUNCH();
   }
   T2Args a;
@@ -1093,6 +1191,15 @@ int launch_decode_tc2(const float* x, const float* proj, const float* qfix, cons
   a.seed = sample_seed ? *sample_seed : 0ull;
   a.N = N; a.NP = NP; a.G = G; a.dbg_step = dbg_step;
   a.tile1_delay = getenv("HTSP_TILE1_DELAY") ? atoi(getenv("HTSP_TILE1_DELAY")) : 0;
+  if (NKB > 1) {
+    // key blocks: single-tile CTAs of up to 128 rows, as many per instance as its rows need (rows spread evenly in
+    // multiples of 32)
+    const int n_ctas = (G + 127) / 128;
+    a.rows_per_cta = min(128, ((G + n_ctas - 1) / n_ctas + 31) / 32 * 32);
+    const bool lg = logits_out != nullptr || forced_pi != nullptr;
+    if (NKB == 2) return lg ? launch_t2<true, false, true, false, true, 2>(a, Bp, s) : launch_t2<false, false, true, false, true, 2>(a, Bp, s);
+    return lg ? launch_t2<true, false, true, false, true, 3>(a, Bp, s) : launch_t2<false, false, true, false, true, 3>(a, Bp, s);
+  }
   int n_split = 1, rows_per_cta = G;
   if (t2_use_one(Bp, G, NP, dbg != nullptr)) {
     // two-CTA instances: 128 rows + the rest (a multiple of 32 rows in the first CTA keeps the number of lane quarters

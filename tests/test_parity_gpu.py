@@ -194,7 +194,10 @@ def test_teacher_forced_logits_match_golden_n200(solvers, golden, mode):
                                     # odd chunk counts (NP = 144), smallest NP (32), one row, G = 129
                                     (1, 208, 208), (2, 130, 130), (3, 17, 17), (2, 64, 1), (1, 150, 129),
                                     # the benchmark's own shape (config 2: N = G = 200), two instances
-                                    (2, 200, 200)])
+                                    (2, 200, 200),
+                                    # key blocks of the second tcgen05 kernel (mode fast, N > 208): two blocks of 192
+                                    # and of 112 keys, several CTAs per instance, three blocks up to the largest N
+                                    (1, 384, 33), (1, 416, 33), (1, 209, 40), (2, 300, 150), (1, 576, 8)])
 def test_teacher_forced_logits_match_oracle(solvers, sd6, mode, Bp, N, G):
     s = solvers[mode]
     g = torch.Generator().manual_seed(N + G)
@@ -218,7 +221,7 @@ def test_teacher_forced_logits_match_oracle(solvers, sd6, mode, Bp, N, G):
 
 # ---------------------------------------------------------------- K3 decode: free-running greedy
 @pytest.mark.parametrize("mode", MODES)
-@pytest.mark.parametrize("Bp,N,G", [(4, 50, 50), (2, 200, 16), (16, 30, 5), (1, 500, 20)])
+@pytest.mark.parametrize("Bp,N,G", [(4, 50, 50), (2, 200, 16), (16, 30, 5), (1, 500, 20), (2, 300, 140)])
 def test_greedy_rollout_is_tie_aware_identical(solvers, sd6, mode, Bp, N, G):
     s = solvers[mode]
     g = torch.Generator().manual_seed(1000 + N)
