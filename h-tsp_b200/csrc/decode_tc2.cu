@@ -1091,7 +1091,7 @@ static void t2_choose_split(int Bp, int G, bool debug, int& split, int& rows_per
 // dynamic shared memory of a CTA: A tiles, ring, c0, barriers, TMEM slot (+ the stage table of the two-tile variant)
 static size_t t2_smem_bytes(int NP, bool one, bool key_blocks = false) {
   return (size_t)(one ? 1 : 2) * T2_TILE_STAGING + (size_t)(one ? T2_SLOTS_ONE : T2_SLOTS) * (key_blocks ? T2_SLOT_KB : T2_SLOT) + (size_t)NP * 4 +
-         (size_t)t2_bar_total(one) * 8 + 16 + (one ? 0 : T2_PER_STEP * 8);
+         (size_t)t2_bar_total(one) * 8 + 8 + (one ? 0 : T2_PER_STEP * 8);   // (single-tile CTAs, 208 keys: 115712 bytes -- two per SM with not a byte to spare)
 }
 
 template <bool LOGITS, bool DEBUG, bool SPLIT, bool SAMPLE = false, bool ONE = false, int NKB = 1>
