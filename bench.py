@@ -308,7 +308,7 @@ def secondary_workloads(args, model, dev, world, rank, barrier):
     (tests/test_e2e_pipeline.py), not as a quality claim."""
     import torch
     import torch.distributed as dist
-    from htsp_b200 import B200RLSolver
+    from htsp_b200 import B200PathSolver, B200RLSolver
     from htsp_b200.evaluate import construct_tours
     from htsp_b200.upper_policy import B200UpperPolicy, synthetic_policy_state_dict
     out = {}
@@ -359,6 +359,36 @@ def secondary_workloads(args, model, dev, world, rank, barrier):
                         "scaling": "weak: 16 independent instances per GPU, no data-path collective",
                         "config": {"k": 40, "frag_len": 200, "max_new_nodes": 190, "val_type": "x8Aug_2Traj",
                                    "pomo_starts": 200, "arith": args.mode}}
+        # (3) BASELINE config 5: the other subproblem sizes of the sweep, one batch each (tools/sweep_sizes.py runs the
+        # whole grid; N = 500 runs the rollout in key blocks on tcgen05, csrc/decode_tc2.cu)
+        from htsp_b200.weights import synthetic_state_dict
+        sweep = []
+        for n_nodes, n_batch in ((100, 4096), (500, 1024)):
+            m = B200PathSolver(state_dict=synthetic_state_dict(1234, args.layers), mode=args.mode, device=dev,
+                               graph_size=n_nodes)
+            m.first_action_override = torch.randperm(n_nodes, generator=torch.Generator().manual_seed(7)).to(dev)
+            xs = [torch.rand(n_batch, n_nodes, 2, generator=torch.Generator().manual_seed(55 + i + 97 * rank)).to(dev)
+                  for i in range(2)]
+            s0 = torch.zeros(n_batch, 1, dtype=torch.long, device=dev)
+            t0 = torch.full((n_batch, 1), n_nodes - 1, dtype=torch.long, device=dev)
+            m(xs[0], s0, t0, val_type="noAug_nTraj", return_pi=True, group_size=n_nodes)       # warm-up
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            length, pi = m(xs[1], s0, t0, val_type="noAug_nTraj", return_pi=True, group_size=n_nodes)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            ok = torch.tensor([int(bool((pi.sort(dim=-1).values == torch.arange(n_nodes, device=dev)).all()))], device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            sweep.append({"nodes": n_nodes, "pomo_starts": n_nodes, "batch_per_gpu": n_batch,
+                          "value": n_batch * world / (float(ms) * 1e-3), "unit": "solves/s", "ms_per_step": float(ms),
+                          "tours_are_permutations": bool(int(ok)), "arith": args.mode})
+            del m, xs, length, pi
+            torch.cuda.empty_cache()
+        out["size_sweep"] = sweep
     finally:
         model.first_action_override = saved
     return out

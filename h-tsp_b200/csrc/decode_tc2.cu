@@ -1030,9 +1030,14 @@ __global__ void __launch_bounds__(ONE ? T2_THREADS_ONE : T2_THREADS, ONE ? (NKB 
 static int t2_np_of(int N) { return (N + 15) / 16 * 16; }
 // key blocks: one block of all (padded) keys up to 208 keys, else NKB equal blocks of NPB <= 208 keys
 static void t2_blocks_of(int N, int& NPB, int& NKB) {
-  if (t2_np_of(N) <= 208) {
+  const char* env = getenv("HTSP_T2_NKB");       // (A/B experiments: key blocks for a subproblem that fits one block)
+  const int forced = env ? atoi(env) : 0;
+  if (t2_np_of(N) <= 208 && !((forced == 2 || forced == 3) && N >= 48 * forced)) {
     NKB = 1;
     NPB = t2_np_of(N);
+  } else if (t2_np_of(N) <= 208) {
+    NKB = forced;
+    NPB = t2_np_of((N + NKB - 1) / NKB);
   } else {
     NKB = (t2_np_of(N) + T2_KB_MAX_NPB - 1) / T2_KB_MAX_NPB;
     NPB = t2_np_of((N + NKB - 1) / NKB);

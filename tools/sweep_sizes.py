@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """BASELINE config 5: subproblem-size sweep N = G in {100, 200, 500} x batch 1K ... 64K at 1 / 2 / 4 / 8 GPUs
 (device-resident inputs, noAug_nTraj, greedy, L = 6).  One JSON line per (N, batch): whole-job solves/s, ms per
-step, which rollout kernel served it (tcgen05 for N <= 208, mma.sync above) and the algorithmic TFLOP/s of the whole
+step, which rollout kernel served it (tcgen05 for N <= 208 and, in mode fast, in key blocks up to N = 576; mma.sync above) and the algorithmic TFLOP/s of the whole
 step (SURVEY 8d count).  Under torchrun (one rank per GPU) the batch is PER GPU (weak scaling, as bench.py): every
 rank solves its own subproblems, the selected tours are all-gathered over NCCL each step, the time is the maximum
 over ranks (CUDA events between barriers).
@@ -87,7 +87,7 @@ def main():
             print(json.dumps({"metric": f"{N}-node subpath solves/sec (POMO {N} starts, greedy)", "nodes": N, "batch_per_gpu": B,
                               "n_gpus": world, "scaling": "weak",
                               "value": B_total / (ms * 1e-3), "unit": "solves/s", "ms_per_step": ms, "arith": a.mode,
-                              "rollout_kernel": "tcgen05" if N <= 208 else "mma.sync",
+                              "rollout_kernel": "tcgen05" if (N <= 208 or (a.mode == "fast" and N <= 576)) else "mma.sync",
                               "algorithmic_tflops": flops(N, N, 6) * B_total / (ms * 1e-3) / 1e12,
                               "tours_are_permutations": ok, "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}),
                   flush=True)
