@@ -1,6 +1,7 @@
 // Encoder self-attention on tensor cores (utils.multi_head_attention, rl4cop/utils/utils.py:12-29, as
 // used by MHAEncoderLayer.forward, models.py:30-34): softmax(q k^T / 4) v per (instance, head), no
-// mask.  One CTA per (instance, head): K_h / V_h (fp16 hi/lo, ldmatrix-swizzled) are staged once in
+// mask.  One CTA per (instance, head, block of 208 query rows -- one block up to N = 208): K_h / V_h of ALL keys
+// (fp16 hi/lo, ldmatrix-swizzled, 128 bytes per key: N <= 1024) are staged once per CTA in
 // shared memory, every warp owns 16 query rows and runs the same flash-style register pipeline as
 // the rollout kernel (mma.sync m16n8k16, split-fp16 x3, lazy online softmax).  Inputs and outputs
 // are the fp16 hi/lo activations the tcgen05 GEMMs produce/consume: qkv [M,384], out [M,128].
@@ -17,15 +18,15 @@ __global__ void __launch_bounds__(416, ATT_MIN_CTAS)
 enc_attention_mma_kernel(const __half* __restrict__ qkv_hi, const __half* __restrict__ qkv_lo,
                          __half* __restrict__ out_hi, __half* __restrict__ out_lo, int N, int NP) {
   extern __shared__ __align__(128) unsigned char att_smem[];
-  const int h = blockIdx.x, b = blockIdx.y;
+  const int h = blockIdx.x, b = blockIdx.y, q0 = blockIdx.z * 208;     // first query row of this CTA
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int NCHUNK = NCHUNK_T > 0 ? NCHUNK_T : NP / 16;
   const size_t row0 = (size_t)b * N;
   // tiles: K hi | K lo | V hi | V lo, each NP x 16 halves (32 B rows), 16B chunk c of row r stored at
   // c ^ ((r>>2)&1): conflict-free for ldmatrix.  Thread tid stages 16-byte chunk (tid & 1) of key tid >> 1
-  // of all four tiles (2 NP <= 416 threads)
-  if (tid < 2 * NP) {
-    const int key = tid >> 1, chunk = tid & 1;
+  // of all four tiles (2 NP <= 416 threads up to N = 208)
+  for (int it = tid; it < 2 * NP; it += 416) {
+    const int key = it >> 1, chunk = it & 1;
     uint4 v[4];
 #pragma unroll
     for (int mat = 0; mat < 4; ++mat) {
@@ -42,11 +43,11 @@ enc_attention_mma_kernel(const __half* __restrict__ qkv_hi, const __half* __rest
   }
   const uint32_t khi = smem_u32(att_smem), klo = khi + NP * 32, vhi = khi + 2 * NP * 32, vlo = khi + 3 * NP * 32;
   const int q4 = lane & 3, rr = lane >> 2, mi = lane >> 3, l7 = lane & 7;
-  const int rA = warp * 16 + rr, rB = rA + 8;
+  const int rA = q0 + warp * 16 + rr, rB = rA + 8;
   const bool okA = rA < N, okB = rB < N;
   // query A fragments: q = hi + lo (exact in fp32), scaled by 1/sqrt(dk)*log2(e), re-split
   uint32_t qh[4], ql[4];
-  if (warp * 16 < N) {
+  if (q0 + warp * 16 < N) {
     auto load2 = [&](int row, int col) -> float2 {
       const size_t off = (row0 + min(row, N - 1)) * (3 * H) + h * DK + col;
       const float2 a = __half22float2(*(const __half2*)(qkv_hi + off));
@@ -61,7 +62,7 @@ enc_attention_mma_kernel(const __half* __restrict__ qkv_hi, const __half* __rest
     split2p(b1.x, b1.y, qh[3], ql[3]);
   }
   __syncthreads();
-  if (warp * 16 >= N) return;
+  if (q0 + warp * 16 >= N) return;
   float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
   float mA = -1e30f, mB = -1e30f, lA = 0.f, lB = 0.f;
   // two 16-key chunks per iteration: one lazy-rescale vote per 32 keys, and the two chunks' MMA / MUFU
@@ -168,13 +169,16 @@ enc_attention_mma_kernel(const __half* __restrict__ qkv_hi, const __half* __rest
 int launch_enc_attention_mma(const __half* qkv_hi, const __half* qkv_lo, __half* out_hi, __half* out_lo,
                              int Bp, int N, cudaStream_t s) {
   const int NP = (N + 15) / 16 * 16;
-  HTSP_REQUIRE(N >= 1 && NP <= 208, "enc_attention_mma supports N <= 208");
+  HTSP_REQUIRE(N >= 1 && NP <= 1024, "enc_attention_mma supports N <= 1024");
   const size_t smem = (size_t)4 * NP * 32;
-  dim3 grid(NH, Bp);
-  if (NP == 208)
+  dim3 grid(NH, Bp, (NP + 207) / 208);
+  if (NP == 208) {
     enc_attention_mma_kernel<13><<<grid, 416, smem, s>>>(qkv_hi, qkv_lo, out_hi, out_lo, N, NP);
-  else
+  } else {
+    if (smem > 48 * 1024)
+      HTSP_CHECK_CUDA(cudaFuncSetAttribute(enc_attention_mma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     enc_attention_mma_kernel<0><<<grid, 416, smem, s>>>(qkv_hi, qkv_lo, out_hi, out_lo, N, NP);
+  }
   HTSP_CHECK_LAUNCH();
   return HTSP_OK;
 }

@@ -1,7 +1,7 @@
 // K2 (tensor-core variant): MHAEncoder.forward (rl4cop/models/models.py:30-60) with every Linear on
 // tcgen05 (gemm_tc.cu, split-fp16 x3) and the bias / ReLU / residual / eval-BatchNorm epilogues fused.
 // Activations travel between layers as fp32 (residual stream) plus the fp16 hi/lo split the next
-// GEMM's TMA loads consume.  The [N x N] self-attention runs on mma.sync tensor cores (enc_attention_mma.cu) for N <= 208.
+// GEMM's TMA loads consume.  The [N x N] self-attention runs on mma.sync tensor cores (enc_attention_mma.cu) for N <= 1024.
 #include <stdlib.h>
 #include "common.cuh"
 
@@ -56,7 +56,7 @@ int launch_encode_tc(const void* blob, int n_layers, const float* x, int Bp, int
     const EncLayerOff o = enc_layer_off(l);
     const EncLayerOffH oh = enc_layer_off_h(l);
     // q,k,v projections (models.py:31-33), no bias
-    const bool tc_att = N <= 208;     // tensor-core attention kernel stages one head's K/V tile
+    const bool tc_att = N <= 1024;    // tensor-core attention kernel stages one head's K/V tile (128 bytes per key)
     if ((rc = launch_linear_tc(h_hi, h_lo, hb + oh.wqkv_hi, hb + oh.wqkv_lo, nullptr, nullptr, nullptr,
                                nullptr, false, tc_att ? nullptr : qkv, tc_att ? q_hi : nullptr,
                                tc_att ? q_lo : nullptr, (int)M, 3 * H, H, s))) return rc;
