@@ -53,19 +53,25 @@ env_knn_kernel(const float2* __restrict__ x, int Ntot, int k, long long* __restr
   const float2* xy = x + (size_t)e * Ntot;
   const float2 pc = xy[c];
   const double bx = (double)pc.x * 1000.0, by = (double)pc.y * 1000.0;
+  // every thread owns the entries tid, tid + 256, ... of the row and is the only one that reads or retires them
+  // (no barrier guards drow); it keeps the minimum of its entries in registers and rescans them only after one of
+  // them has won a round -- a round costs the other threads the block arg-min alone
+  auto scan_mine = [&]() {
+    DistIdx m = {INFINITY, 0x7fffffff};
+    for (int j = tid; j < Ntot; j += FRAG_THREADS) m = di_min(m, DistIdx{drow[j], j});
+    return m;
+  };
   for (int j = tid; j < Ntot; j += FRAG_THREADS) drow[j] = (j == c) ? INFINITY : dist32(xy[j], bx, by, 1000.0);
-  __syncthreads();
+  DistIdx mine = scan_mine();
   long long* out = knn + ((size_t)e * Ntot + c) * k;
   for (int r = 0; r < k; ++r) {          // k selection rounds (k = 40): block arg-min, then retire the winner
-    DistIdx best = {INFINITY, 0x7fffffff};
-    for (int j = tid; j < Ntot; j += FRAG_THREADS) best = di_min(best, DistIdx{drow[j], j});
-    best = block_min(best, red);
-    if (tid == 0) {
-      out[r] = best.i;
+    const DistIdx best = block_min(mine, red);
+    if (tid == 0) out[r] = best.i;
+    if ((unsigned)best.i < (unsigned)Ntot && best.i % FRAG_THREADS == tid) {
       // a retired entry must lose against every remaining one, including other infinities (the diagonal)
       drow[best.i] = __int_as_float(0x7fc00000);     // NaN: never '<' and never '==' anything
+      mine = scan_mine();
     }
-    __syncthreads();
   }
 }
 
