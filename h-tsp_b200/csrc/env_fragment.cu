@@ -22,21 +22,22 @@ struct DistIdx {
 __device__ __forceinline__ DistIdx di_min(DistIdx a, DistIdx b) {
   return (b.d < a.d || (b.d == a.d && b.i < a.i)) ? b : a;
 }
+// warp arg-min by two redux instructions: the distances are non-negative floats (or +inf, or the NaN 0x7fc00000 of a
+// retired entry), whose bit patterns order like the numbers (NaN last)
+__device__ __forceinline__ DistIdx warp_min(unsigned dbits, int i) {
+  const unsigned m = __reduce_min_sync(0xffffffffu, dbits);
+  const unsigned mi = __reduce_min_sync(0xffffffffu, dbits == m ? (unsigned)i : 0xffffffffu);
+  return DistIdx{__uint_as_float(m), (int)mi};
+}
 __device__ __forceinline__ DistIdx block_min(DistIdx v, DistIdx* red) {
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    DistIdx o;
-    o.d = __shfl_xor_sync(0xffffffffu, v.d, off);
-    o.i = __shfl_xor_sync(0xffffffffu, v.i, off);
-    v = di_min(v, o);
-  }
-  const int tid = threadIdx.x;
+  v = warp_min(__float_as_uint(v.d), v.i);
+  const int tid = threadIdx.x, lane = tid & 31;
   __syncthreads();                       // red may still be read from a previous call
-  if ((tid & 31) == 0) red[tid >> 5] = v;
+  if (lane == 0) red[tid >> 5] = v;
   __syncthreads();
-  DistIdx r = red[0];
-  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = di_min(r, red[w]);
-  return r;
+  const bool have = lane < (int)(blockDim.x >> 5);
+  const DistIdx r = have ? red[lane] : DistIdx{0.f, 0x7fffffff};
+  return warp_min(have ? __float_as_uint(r.d) : 0xffffffffu, r.i);
 }
 // float32( |a - b| in float64 ) with a scale applied in float64 first (x1000 for the k-NN matrix, h_tsp.py:449-452)
 __device__ __forceinline__ float dist32(float2 a, double bx, double by, double scale) {
@@ -123,7 +124,12 @@ __global__ void __launch_bounds__(FRAG_THREADS) env_fragment_kernel(const FragAr
   const int nwords = (Ntot + 31) / 32;
   unsigned* seen = frag_smem;                    // [nwords] bitmap of the FIFO's selected_set
   int* queue = (int*)(frag_smem + nwords);       // [qcap]
-  for (int i = tid; i < nwords; i += FRAG_THREADS) seen[i] = 0u;
+  // the bitmap starts as the selected flags: "not yet seen and not selected" (h_tsp.py:472-480) is one bit test
+  for (int i0 = (tid >> 5) * 32; i0 < Ntot; i0 += FRAG_THREADS) {
+    const int i = i0 + lane;
+    const unsigned m = __ballot_sync(0xffffffffu, i < Ntot && sel[i] != 0);
+    if (lane == 0) seen[i0 >> 5] = m;
+  }
   for (int i = tid; i < FL; i += FRAG_THREADS) newc[i] = -1;
   int start_city = -1, n_new = 0;
   const float2 act = A.action[e];
@@ -138,23 +144,35 @@ __global__ void __launch_bounds__(FRAG_THREADS) env_fragment_kernel(const FragAr
     const int max_cities = max(A.max_new_nodes, FL - T);
     __syncthreads();
     // FIFO expansion over the k-NN lists by one warp (h_tsp.py:512-524): pop, record, append the
-    // not-yet-seen unselected neighbours in list order (ballot + prefix count keeps the order)
+    // not-yet-seen unselected neighbours in list order (ballot + prefix count keeps the order).  The pops form a
+    // chain of dependent L2 reads (190 of them per step): the k-NN rows of the next two queue entries are requested
+    // while the current one is processed (k <= 64: a row is two registers per lane).
     if (tid < 32) {
       int head = 0, tail = 1;
       if (lane == 0) { queue[0] = new_start; seen[new_start >> 5] |= 1u << (new_start & 31); }
       __syncwarp();
+      int ra[3], rb[3];
+      bool have[3] = {false, false, false};
+      auto request = [&](int slot, int qpos) {          // row of queue[qpos] -> registers of `slot` (if it is queued yet)
+        if (have[slot] || qpos >= tail || k > 64) return;
+        const long long* row = nn + (size_t)queue[qpos] * k;
+        ra[slot] = lane < k ? (int)row[lane] : -1;
+        rb[slot] = 32 + lane < k ? (int)row[32 + lane] : -1;
+        have[slot] = true;
+      };
       while (head < tail && n_new < max_cities && n_new < FL) {
-        const int node = queue[head++];
+        const int node = queue[head];
+        request(0, head);
+        request(1, head + 1);
+        request(2, head + 2);
+        ++head;
         if (lane == 0) newc[n_new] = node;
         ++n_new;
         for (int j0 = 0; j0 < k; j0 += 32) {
           const int j = j0 + lane;
           int nb = -1;
-          bool ok = false;
-          if (j < k) {
-            nb = (int)nn[(size_t)node * k + j];
-            ok = !((seen[nb >> 5] >> (nb & 31)) & 1u) && sel[nb] == 0;
-          }
+          if (j < k) nb = have[0] ? (j0 == 0 ? ra[0] : (j0 == 32 ? rb[0] : (int)nn[(size_t)node * k + j])) : (int)nn[(size_t)node * k + j];
+          const bool ok = nb >= 0 && !((seen[nb >> 5] >> (nb & 31)) & 1u);
           const unsigned m = __ballot_sync(0xffffffffu, ok);
           if (ok) {
             const int slot = tail + __popc(m & ((1u << lane) - 1u));
@@ -164,6 +182,9 @@ __global__ void __launch_bounds__(FRAG_THREADS) env_fragment_kernel(const FragAr
           tail = min(tail + __popc(m), A.qcap);
           __syncwarp();
         }
+        ra[0] = ra[1]; rb[0] = rb[1]; have[0] = have[1];
+        ra[1] = ra[2]; rb[1] = rb[2]; have[1] = have[2];
+        have[2] = false;
       }
       if (lane == 0) s_nnew = n_new;
     }
