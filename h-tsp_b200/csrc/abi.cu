@@ -254,12 +254,12 @@ static int decode_dispatch(const void* blob, int n_layers, const float* x, const
                            cudaStream_t s) {
   if (logp != nullptr && !use_tc2_kernel(N, G, mode)) {
     set_error("htsp_decode_sample_logp: log-probabilities are returned by the second tcgen05 kernel only (mode fast, "
-              "33 <= N <= 208, G <= 256); got mode %d, N %d, G %d", mode, N, G);
+              "33 <= N <= 208 and G <= 256, or 208 < N <= 576 in key blocks); got mode %d, N %d, G %d", mode, N, G);
     return HTSP_ERR_UNSUPPORTED;
   }
-  if (sample_seed != nullptr && (mode == HTSP_MODE_FP32 || !use_tc_kernel(N, G))) {
-    set_error("htsp_decode_sample: sampling rollouts are served by the tcgen05 kernel only (tensor-core mode, "
-              "17 <= N <= 208, G <= 256); got mode %d, N %d, G %d", mode, N, G);
+  if (sample_seed != nullptr && (mode == HTSP_MODE_FP32 || !(use_tc_kernel(N, G) || use_tc2_kernel(N, G, mode)))) {
+    set_error("htsp_decode_sample: sampling rollouts are served by the tcgen05 kernels only (tensor-core mode, "
+              "17 <= N <= 208, G <= 256; mode fast: up to N = 576 in key blocks); got mode %d, N %d, G %d", mode, N, G);
     return HTSP_ERR_UNSUPPORTED;
   }
   if (mode == HTSP_MODE_FP32)

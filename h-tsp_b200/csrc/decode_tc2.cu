@@ -259,11 +259,11 @@ __host__ __device__ constexpr int t2_bar_total(bool one) {
 // A.NP <= 208 keys.  P = 2^S carries no shift, so the blocks of a head simply accumulate into the same O and the same
 // row sums: per head the chain is NKB x [S block -> softmax -> P V], the accumulator is drained after the last block;
 // the pointer logits are computed and scanned block by block (the score columns hold one block at a time), with the
-// running arg-max carried across the blocks.
+// running arg-max (and, when sampling, the sum of exponentials of the log-probability) carried across the blocks.
 template <bool LOGITS, bool DEBUG, bool SPLIT, bool SAMPLE, bool ONE, int NKB = 1>
 __global__ void __launch_bounds__(ONE ? T2_THREADS_ONE : T2_THREADS, ONE ? (NKB == 1 ? 2 : T2_KB_CTAS_PER_SM) : 1) decode_tc2_kernel(const T2Args A) {
   static_assert(!ONE || (SPLIT && !DEBUG), "single-tile CTAs: SPLIT launches, no debug dump");
-  static_assert(NKB == 1 || (ONE && !SAMPLE), "key blocks: single-tile CTAs, greedy or teacher-forced");
+  static_assert(NKB == 1 || ONE, "key blocks: single-tile CTAs");
   constexpr int NIT = NH * NKB;             // (head, key block) iterations of the glimpse per decode step
   constexpr int T2_THREADS = ONE ? htsp::T2_THREADS_ONE : htsp::T2_THREADS;     // (shadow the two-tile constants)
   constexpr int T2_SLOTS = ONE ? htsp::T2_SLOTS_ONE : htsp::T2_SLOTS;
@@ -857,7 +857,7 @@ __global__ void __launch_bounds__(ONE ? T2_THREADS_ONE : T2_THREADS, ONE ? (NKB 
               const float ca[4] = {cc.x, cc.y, cc.z, cc.w};
               uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
               if (SAMPLE)
-                rnd = tcd_philox(make_uint4((uint32_t)(4 * c + j4), (uint32_t)step, (uint32_t)(r0 + gc), (uint32_t)b),
+                rnd = tcd_philox(make_uint4((uint32_t)((koff >> 2) + 4 * c + j4), (uint32_t)step, (uint32_t)(r0 + gc), (uint32_t)b),
                                  make_uint2((uint32_t)A.seed, (uint32_t)(A.seed >> 32)));
               const uint32_t ra[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
@@ -1178,8 +1178,7 @@ int launch_decode_tc2(const float* x, const float* proj, const float* qfix, cons
   HTSP_REQUIRE(dbg == nullptr || G <= 224, "debug dump: at most 224 rows");
   int NP, NKB;                            // keys per block (all padded keys when NKB == 1), key blocks
   t2_blocks_of(N, NP, NKB);
-  HTSP_REQUIRE(NKB == 1 || (sample_seed == nullptr && dbg == nullptr),
-               "decode_tc2 with key blocks (N > 208): greedy and teacher-forced rollouts only");
+  HTSP_REQUIRE(NKB == 1 || dbg == nullptr, "decode_tc2 with key blocks (N > 208): no debug dump");
   unsigned char* img = (unsigned char*)(((uintptr_t)pack_ws + 1023) & ~(uintptr_t)1023) + T2_TAB_BYTES;   // (the stage table sits in front)
   float* kbar = (float*)(img + align_up((size_t)Bp * t2_img_bytes(NP, NKB), 256));
   decode_tc2_kbar_kernel<<<Bp, 128, 0, s>>>(proj, N, NP, NKB, kbar, (uint2*)(img - T2_TAB_BYTES));
@@ -1202,6 +1201,8 @@ int launch_decode_tc2(const float* x, const float* proj, const float* qfix, cons
     const int n_ctas = (G + 127) / 128;
     a.rows_per_cta = min(128, ((G + n_ctas - 1) / n_ctas + 31) / 32 * 32);
     const bool lg = logits_out != nullptr || forced_pi != nullptr;
+    if (sample_seed != nullptr)
+      return NKB == 2 ? launch_t2<false, false, true, true, true, 2>(a, Bp, s) : launch_t2<false, false, true, true, true, 3>(a, Bp, s);
     if (NKB == 2) return lg ? launch_t2<true, false, true, false, true, 2>(a, Bp, s) : launch_t2<false, false, true, false, true, 2>(a, Bp, s);
     return lg ? launch_t2<true, false, true, false, true, 3>(a, Bp, s) : launch_t2<false, false, true, false, true, 3>(a, Bp, s);
   }

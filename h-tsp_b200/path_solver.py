@@ -303,9 +303,11 @@ class B200PathSolver(torch.nn.Module):
         # greedy=False (train_path_solver.py:266-271): rows sample their next node in the kernel; the seed
         # is drawn from torch's global generator, so torch.manual_seed controls it (the reference consumes the
         # same generator through multinomial: equal in distribution, not bit-wise)
-        if not greedy and (self.mode == "fp32" or not 17 <= batch.shape[1] <= 208 or int(group_size) > 256):
-            raise NotImplementedError("sampling rollouts (greedy=False) are served by the tcgen05 kernel only: "
-                                      "tensor-core mode, 17 <= N <= 208, group_size <= 256")
+        n_nodes = batch.shape[1]
+        key_blocks = self.mode == "fast" and 208 < n_nodes <= 576          # csrc/decode_tc2.cu, NKB = 2 | 3
+        if not greedy and (self.mode == "fp32" or not (key_blocks or (17 <= n_nodes <= 208 and int(group_size) <= 256))):
+            raise NotImplementedError("sampling rollouts (greedy=False) are served by the tcgen05 kernels only: "
+                                      "tensor-core mode, 17 <= N <= 208, group_size <= 256 (mode fast: N <= 576)")
         sample_seed = None if greedy else int(torch.randint(0, 2**62, (1,)).item())
         lib = _abi.lib()
         val_type = val_type or self.cfg.val_type

@@ -371,7 +371,8 @@ def test_sampling_rollout_validity_and_distribution(built_lib, monkeypatch, mode
     assert stat_u >= df_u + 50 * (2 * df_u) ** 0.5
 
 
-def test_sampling_rollout_log_probabilities(built_lib):
+@pytest.mark.parametrize("Bp,N,G", [(3, 40, 33), (1, 300, 40)])       # (N = 300: two key blocks of 160 keys)
+def test_sampling_rollout_log_probabilities(built_lib, Bp, N, G):
     """SURVEY 8f-4, forward half of the training step (train_path_solver.py:394-414): htsp_decode_sample_logp returns,
     for every sampled tour, the sum over the decode steps of log p(sampled node) with p = softmax(masked clipped
     logits).  Parity: the sampled tours are teacher-forced through the ORACLE (fp32, CPU), whose per-step logits give
@@ -383,7 +384,6 @@ def test_sampling_rollout_log_probabilities(built_lib):
     sd = synthetic_state_dict(4321, 6)                      # peaked policy: log-probabilities far from -log(n)
     s = B200PathSolver(state_dict=sd, mode="fast", device="cuda")
     g = torch.Generator().manual_seed(11)
-    Bp, N, G = 3, 40, 33
     x = torch.rand(Bp, N, 2, generator=g)
     src = torch.randint(0, N, (Bp,), generator=g)
     tgt = (src + 1 + torch.randint(0, N - 1, (Bp,), generator=g)) % N
@@ -412,8 +412,9 @@ def test_sampling_rollout_log_probabilities(built_lib):
     err = (got - want).abs()
     print(f"[fast] sum of log p over {N - 2} steps: mean {float(want.mean()):.3f}, max |d| {float(err.max()):.2e}, "
           f"|d mean| {float((got.mean() - want.mean()).abs()):.2e}")
-    assert float(want.abs().min()) > 1.0 and float(err.max()) <= 5e-3
-    assert float((got.mean() - want.mean()).abs()) <= 1e-3
+    scale = max(1.0, (N - 2) / 38.0)          # the bounds are per 38 summed terms
+    assert float(want.abs().min()) > 1.0 and float(err.max()) <= 5e-3 * scale
+    assert float((got.mean() - want.mean()).abs()) <= 1e-3 * scale
     # x3 has no log-probability path yet: the call must refuse, not fall back
     s3 = B200PathSolver(state_dict=sd, mode="x3", device="cuda")
     with pytest.raises(_abi.HtspError):
