@@ -37,6 +37,8 @@ SIGNATURES = {
     "htsp_decode_sample_logp": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, C.c_uint64, _vp, _vp, _vp, _vp,
                                      _sz, _vp]),
     "htsp_decode_ctas_per_sm": (_i, [_i, _i, _i, _i]),
+    "htsp_decode_key_blocks": (_i, [_i, _vp]),
+    "htsp_decode_key_block_stage": (_i, [_i, _i, _vp]),
     "htsp_decode_debug_floats": (_sz, [_i]),
     "htsp_decode_debug": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp,
                                _vp, _sz, _vp, _i, _vp]),

@@ -306,6 +306,22 @@ extern "C" int htsp_decode_ctas_per_sm(int Bp, int N, int G, int mode) {
   if (Bp <= 0 || N < 3 || G < 1) return 0;
   return use_tc2_kernel(N, G, mode) ? decode_tc2_ctas_per_sm(Bp, N, G) : 1;
 }
+extern "C" int htsp_decode_key_blocks(int N, int32_t* out5) {
+  HTSP_REQUIRE(out5 != nullptr, "null pointer");
+  if (!decode_tc2_geometry(N, out5)) {
+    set_error("htsp_decode_key_blocks: N=%d is not served by the second tcgen05 kernel (33 <= N <= 576)", N);
+    return HTSP_ERR_UNSUPPORTED;
+  }
+  return HTSP_OK;
+}
+extern "C" int htsp_decode_key_block_stage(int N, int i, uint32_t* out2) {
+  HTSP_REQUIRE(out2 != nullptr, "null pointer");
+  if (!decode_tc2_stage(N, i, out2)) {
+    set_error("htsp_decode_key_block_stage: no stage %d for N=%d", i, N);
+    return HTSP_ERR_UNSUPPORTED;
+  }
+  return HTSP_OK;
+}
 extern "C" size_t htsp_decode_debug_floats(int N) { return std::max(decode_tc_dbg_floats(N), decode_tc2_dbg_floats(N)); }
 extern "C" int htsp_decode_debug(const void* blob, int n_layers, const float* x, const float* emb,
                                  const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp,

@@ -191,6 +191,8 @@ bool decode_tc2_supported(int N, int G);
 size_t decode_tc2_pack_bytes(int Bp, int N);
 size_t decode_tc2_dbg_floats(int N);
 int decode_tc2_ctas_per_sm(int Bp, int N, int G);
+bool decode_tc2_geometry(int N, int32_t out[5]);
+bool decode_tc2_stage(int N, int i, uint32_t out[2]);
 int launch_decode_tc2(const float* x, const float* proj, const float* qfix, const float* c0,
                       const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp, int N,
                       int G, const int32_t* forced_pi, int32_t* pi, float* reward,

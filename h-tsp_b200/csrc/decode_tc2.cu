@@ -1,4 +1,5 @@
-// K3, second tcgen05 rollout kernel (HTSP_MODE_TC_FAST, 33 <= N <= 208): the glimpse probabilities stay in TMEM as the
+// K3, second tcgen05 rollout kernel (HTSP_MODE_TC_FAST, 33 <= N <= 208, and 208 < N <= 576 in key blocks -- see the
+// template parameter NKB of the kernel): the glimpse probabilities stay in TMEM as the
 // fp32 words they were computed in and feed a kind::tf32 MMA in place, and every row quarter is served by THREE
 // softmax warps.
 //
@@ -1061,6 +1062,28 @@ size_t decode_tc2_pack_bytes(int Bp, int N) {
 size_t decode_tc2_dbg_floats(int N) {
   const int NP = t2_np_of(N);
   return (size_t)2 * 8 * 128 * NP + (size_t)256 * 128 + (size_t)256 * NP + 256;
+}
+
+// geometry of the operand stream for N nodes (host logic, checked on the CPU by tests/test_abi.py): keys per block,
+// key blocks, ring stages per decode step, operand-image bytes per instance, ring-slot bytes
+bool decode_tc2_geometry(int N, int32_t out[5]) {
+  if (N < 3 || !decode_tc2_supported(N, 1)) return false;
+  int NPB, NKB;
+  t2_blocks_of(N, NPB, NKB);
+  out[0] = NPB;
+  out[1] = NKB;
+  out[2] = t2_per_step(NKB);
+  out[3] = (int32_t)t2_img_bytes(NPB, NKB);
+  out[4] = NKB > 1 ? T2_SLOT_KB : T2_SLOT;
+  return true;
+}
+bool decode_tc2_stage(int N, int i, uint32_t out[2]) {
+  int32_t g[5];
+  if (!decode_tc2_geometry(N, g) || i < 0 || i >= g[2]) return false;
+  const uint2 e = t2_stage_entry(g[0], i, g[1]);
+  out[0] = e.x;
+  out[1] = e.y;
+  return true;
 }
 
 // CTAs per instance: 1 unless the launch would leave most SMs idle (then the rows are cut into 128-, 64- or 32-row

@@ -123,7 +123,8 @@ int htsp_decode_sample(const void* blob, int n_layers, const float* x, const flo
 /* As htsp_decode_sample, additionally returning logp [Bp,G] f32 = sum over the N-2 decode steps of
  * log p(sampled node), p = softmax(masked 10*tanh logits): the `group_prob_list.log().sum(dim=2)` of the
  * reference's training step (train_path_solver.py:394-414), forward only.
- * Served by the second tcgen05 kernel (HTSP_MODE_TC_FAST, 33 <= N <= 208, G <= 256), else HTSP_ERR_UNSUPPORTED. */
+ * Served by the second tcgen05 kernel (HTSP_MODE_TC_FAST; 33 <= N <= 208 with G <= 256, or 208 < N <= 576 in key
+ * blocks), else HTSP_ERR_UNSUPPORTED. */
 int htsp_decode_sample_logp(const void* blob, int n_layers, const float* x, const float* emb,
                             const int32_t* src, const int32_t* tgt, const int32_t* first, int Bp, int N,
                             int G, int mode, uint64_t seed, int32_t* pi, float* reward, float* logp,
@@ -133,6 +134,15 @@ int htsp_decode_sample_logp(const void* blob, int n_layers, const float* x, cons
  * mode HTSP_MODE_TC_FAST runs its single-tile CTAs (more CTAs than SMs; HTSP_T2_ONE = 0 | 1 overrides), else 1; 0 for
  * an invalid shape.  The result does not depend on it (bit-identical); bench.py and the tests report it.          */
 int htsp_decode_ctas_per_sm(int Bp, int N, int G, int mode);
+
+/* Operand-stream geometry of the HTSP_MODE_TC_FAST rollout kernel for subproblems of N nodes (host logic, no CUDA call;
+ * tests/test_abi.py checks it on the CPU): out5 = { keys per key block (a multiple of 16; <= 208 with one block, <= 192
+ * with several), key blocks (1 up to N = 208, 2 or 3 up to N = 576), ring stages per decode step, bytes of the operand
+ * image of one instance, bytes of a ring slot }.  HTSP_ERR_UNSUPPORTED outside 33 <= N <= 576.                      */
+int htsp_decode_key_blocks(int N, int32_t* out5);
+/* Stage i (0 <= i < stages per decode step) of that stream: out2 = { byte offset into the instance's operand image,
+ * bytes }.  The stages of a step tile the image exactly once and each fits a ring slot.                            */
+int htsp_decode_key_block_stage(int N, int i, uint32_t* out2);
 
 /* Test hook (tests/test_parity_gpu.py): as htsp_decode in a tensor-core mode on the tcgen05 kernel
  * (N <= 224, G <= 256), additionally dumping the intermediates of instance 0 at decode step

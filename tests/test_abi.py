@@ -58,3 +58,35 @@ def test_argument_validation_without_gpu(built_lib):
     assert b"null pointer" in lib.htsp_last_error()
     assert lib.htsp_encode_workspace_bytes(0, 200, 0) == 0
     assert lib.htsp_decode_workspace_bytes(4, 200, 200, 0) > 4 * 200 * 640 * 4
+
+
+def test_rollout_operand_stream_geometry(built_lib, monkeypatch):
+    """Host logic of the HTSP_MODE_TC_FAST rollout kernel (csrc/decode_tc2.cu), no GPU: for every supported subproblem
+    size the keys are cut into 1 - 3 equal blocks that cover them without an empty block, and the ring stages of one
+    decode step tile the operand image of an instance exactly once, each within a ring slot."""
+    import ctypes as C
+    from htsp_b200 import _abi
+    monkeypatch.delenv("HTSP_T2_NKB", raising=False)
+    lib = _abi.lib()
+    g, st = (C.c_int32 * 5)(), (C.c_uint32 * 2)()
+    for bad in (2, 32, 577, 1000):
+        assert lib.htsp_decode_key_blocks(bad, g) != 0
+    for N in list(range(33, 577, 7)) + [48, 49, 192, 200, 208, 209, 384, 385, 500, 576]:
+        assert lib.htsp_decode_key_blocks(N, g) == 0, N
+        npb, nkb, stages, img, slot = list(g)
+        assert npb % 16 == 0 and npb >= 48
+        assert (nkb == 1 and npb <= 208 and N <= 208) or (nkb in (2, 3) and npb <= 192 and N > 208)
+        assert nkb * npb >= N > (nkb - 1) * npb                       # every block holds real keys
+        assert stages == 3 + 6 * (8 * nkb - 1) + 3 + 12 * nkb
+        spans = []
+        for i in range(stages):
+            assert lib.htsp_decode_key_block_stage(N, i, st) == 0
+            assert 0 < st[1] <= slot and st[0] % 1024 == 0 and st[1] % 1024 == 0    # swizzle atoms stay aligned
+            spans.append((st[0], st[1]))
+        assert lib.htsp_decode_key_block_stage(N, stages, st) != 0
+        spans.sort()
+        pos = 0
+        for off, nbytes in spans:
+            assert off == pos, (N, off, pos)
+            pos += nbytes
+        assert pos == img
