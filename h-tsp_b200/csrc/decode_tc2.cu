@@ -256,13 +256,13 @@ __host__ __device__ constexpr int t2_bar_total(bool one) {
 // leave it idle together.  Two independent CTAs drift apart and fill each other's gaps; the price is that every
 // operand block is fetched from L2 once per tile instead of once per instance.
 //
-// NKB > 1 (N > 208, single-tile CTAs only, one per SM): the keys of an instance are processed in NKB blocks of
-// A.NP <= 208 keys.  P = 2^S carries no shift, so the blocks of a head simply accumulate into the same O and the same
+// NKB > 1 (N > 208, single-tile CTAs only, two per SM -- one when sampling, whose key-block loops do not fit 64
+// registers): the keys of an instance are processed in NKB blocks of A.NP <= 192 keys.  P = 2^S carries no shift, so the blocks of a head simply accumulate into the same O and the same
 // row sums: per head the chain is NKB x [S block -> softmax -> P V], the accumulator is drained after the last block;
 // the pointer logits are computed and scanned block by block (the score columns hold one block at a time), with the
 // running arg-max (and, when sampling, the sum of exponentials of the log-probability) carried across the blocks.
 template <bool LOGITS, bool DEBUG, bool SPLIT, bool SAMPLE, bool ONE, int NKB = 1>
-__global__ void __launch_bounds__(ONE ? T2_THREADS_ONE : T2_THREADS, ONE ? (NKB == 1 ? 2 : T2_KB_CTAS_PER_SM) : 1) decode_tc2_kernel(const T2Args A) {
+__global__ void __launch_bounds__(ONE ? T2_THREADS_ONE : T2_THREADS, ONE ? (NKB == 1 ? 2 : (SAMPLE ? 1 : T2_KB_CTAS_PER_SM)) : 1) decode_tc2_kernel(const T2Args A) {
   static_assert(!ONE || (SPLIT && !DEBUG), "single-tile CTAs: SPLIT launches, no debug dump");
   static_assert(NKB == 1 || ONE, "key blocks: single-tile CTAs");
   constexpr int NIT = NH * NKB;             // (head, key block) iterations of the glimpse per decode step
