@@ -117,18 +117,29 @@ class B200RLSolver(LowLevelSolver):
 
     def solve(self, data: torch.Tensor, fragment: torch.Tensor,
               frag_buffer=None) -> Tuple[List[List[int]], np.ndarray]:
-        paths, lengths, status, _ = self.solve_device(data, fragment, frag_buffer)
+        paths, lengths, status, x_new = self.solve_device(data, fragment, frag_buffer)
         host = torch.cat([paths.reshape(-1), status.to(torch.int64)]).cpu()
         B, N = paths.shape
         st = host[B * N:]
-        # the reference asserts these per path (h_tsp.py:218-224)
         lens = lengths.cpu().numpy()
-        if np.isnan(lens).any():
-            # the kernels clamp every caller-supplied index and flag the call instead of faulting (the reference's
-            # torch.gather raises IndexError for the same input, h_tsp.py:176-182)
-            raise IndexError("fragment ids outside [0, Ntot) (or POMO starts outside [0, N)) in subproblem(s) "
-                             f"{np.nonzero(np.isnan(lens))[0].tolist()}")
-        assert bool((st == 0).all()), f"invalid path(s) returned by the rollout, status={st.tolist()}"
+        if np.isnan(lens).any() or bool((st != 0).any()):
+            bad = np.nonzero(np.isnan(lens) | (st.numpy() != 0))[0].tolist()
+            first = self._solver_model.first_action_override
+            starts_ok = first is None or bool(((first >= 0) & (first < N)).all())
+            if bool(torch.isnan(x_new).any()) or not starts_ok:
+                # the kernels clamp every caller-supplied index and flag the call instead of faulting (the reference's
+                # torch.gather raises IndexError for the same input, h_tsp.py:176-182)
+                raise IndexError(f"fragment ids outside [0, Ntot) (or POMO starts outside [0, N)) in subproblem(s) {bad}")
+            if np.isnan(lens).any() or bool(((st & 4) != 0).any()):
+                # the indices were fine and yet a row has no finite reward or visited a node twice: its logits were not
+                # finite -- with the split-fp16 operands of the tensor-core modes that is an activation beyond the fp16
+                # range (|v| >= 65504) or a softmax sum beyond fp32
+                raise FloatingPointError(
+                    f"no valid tour for subproblem(s) {bad} in mode '{self._solver_model.mode}' (status {st.tolist()}): the "
+                    "activations left the range of the tensor-core arithmetic (split-fp16 operands, |v| < 65504); "
+                    "use B200PathSolver(mode='fp32') for these weights")
+            # the reference asserts these per path (h_tsp.py:218-224)
+            raise AssertionError(f"invalid path(s) returned by the rollout, status={st.tolist()}")
         return host[:B * N].reshape(B, N).tolist(), lens
 
 

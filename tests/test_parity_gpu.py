@@ -656,6 +656,23 @@ def test_out_of_range_indices_do_not_fault(solvers):
         s(x, torch.tensor([[0], [40]]), tgt.reshape(2, 1), val_type="noAug_nTraj", group_size=4)
 
 
+def test_activations_beyond_the_fp16_range_are_reported(built_lib):
+    """the tensor-core modes split every operand into fp16 hi + lo, so an activation with
+    |v| >= 65504 has no representation.  Nothing may pass silently: the rollout's rewards are NaN and the hook raises
+    FloatingPointError naming mode='fp32' (an IndexError is reserved for bad indices)."""
+    from htsp_b200 import B200PathSolver, B200RLSolver
+    from htsp_b200.weights import synthetic_state_dict
+    sd = synthetic_state_dict(1234, 2)
+    sd["encoder.init_projection_layer.weight"] = sd["encoder.init_projection_layer.weight"] * 1e7     # embeddings ~1e7
+    g = torch.Generator().manual_seed(5)
+    data = torch.rand(2, 300, 2, generator=g).cuda()
+    frag = torch.stack([torch.randperm(300, generator=g)[:40] for _ in range(2)]).cuda()
+    for mode in ("x3", "fast"):
+        hook = B200RLSolver(B200PathSolver(state_dict=sd, mode=mode, device="cuda"), sample_size=4)
+        with pytest.raises(FloatingPointError, match="fp32"):
+            hook.solve(data, frag, None)
+
+
 def test_packed_weights_follow_in_place_parameter_updates(built_lib):
     """The library works on a packed copy of the weights; in-place updates of the module's parameters (optimizer.step
     during joint training, `copy_`) must invalidate it (only load_state_dict / _apply did)."""
