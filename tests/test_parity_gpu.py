@@ -197,7 +197,9 @@ def test_teacher_forced_logits_match_golden_n200(solvers, golden, mode):
                                     (2, 200, 200),
                                     # key blocks of the second tcgen05 kernel (mode fast, N > 208): two blocks of 192
                                     # and of 112 keys, several CTAs per instance, three blocks up to the largest N
-                                    (1, 384, 33), (1, 416, 33), (1, 209, 40), (2, 300, 150), (1, 576, 8)])
+                                    (1, 384, 33), (1, 416, 33), (1, 209, 40), (2, 300, 150), (1, 576, 8),
+                                    # ... with one POMO row, and with 129 (a second CTA of one row)
+                                    (1, 240, 1), (2, 250, 129)])
 def test_teacher_forced_logits_match_oracle(solvers, sd6, mode, Bp, N, G):
     s = solvers[mode]
     g = torch.Generator().manual_seed(N + G)
