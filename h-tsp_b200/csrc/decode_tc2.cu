@@ -51,6 +51,10 @@ constexpr int T2_SLOTS = 8;
 // single-tile CTAs (template parameter ONE): one 128-row tile per CTA, TWO CTAs per SM -- half of everything
 constexpr int T2_THREADS_ONE = 512;
 constexpr int T2_SLOTS_ONE = 4;
+#ifndef T2_SLOTS_KB
+#define T2_SLOTS_KB 4                     // key-block kernels: ring slots of 8 KB (five would fit with two CTAs per SM:
+                                          // N = 500 +2 %, N = 300 -1 %, both inside the run-to-run spread)
+#endif
 constexpr int T2_PER_STEP = 3 + 7 * 6 + 3 + 12;   // ring stages of one decode step
 constexpr int T2_SLOT = 12288;            // ring slot: one K_h^j (<= 5 KB), V_h^j (<= 12 KB) or K2_i^j (<= 10 KB) block
 constexpr int T2_SLOT_KB = 8192;          // key-block kernels: blocks of <= 192 keys have parts of <= 64 keys (K 4 KB, V 8 KB, K2 8 KB)
@@ -245,8 +249,8 @@ struct T2Args {
 // barrier slots: per row tile, then the shared ring (T2B_FULL, T2B_EMPTY, T2B_TOTAL depend on the variant)
 enum { T2B_SFULL = 0, T2B_PFULL = 3, T2B_OFULL = 6, T2B_OREADY = 7, T2B_QFULL = 8, T2B_UFULL = 9, T2B_UDONE = 10, T2B_PER_TILE = 11 };
 constexpr int T2_FULL_BARS = 8;     // "landed" barriers: stage `it` signals barrier it % 8 (see land() in run_helper)
-__host__ __device__ constexpr int t2_bar_total(bool one) {
-  return (one ? 1 : 2) * T2B_PER_TILE + T2_FULL_BARS + (one ? T2_SLOTS_ONE : T2_SLOTS);
+__host__ __device__ constexpr int t2_bar_total(bool one, bool key_blocks = false) {
+  return (one ? 1 : 2) * T2B_PER_TILE + T2_FULL_BARS + (one ? (key_blocks ? T2_SLOTS_KB : T2_SLOTS_ONE) : T2_SLOTS);
 }
 
 // ONE: the CTA owns ONE row tile (at most 128 rows, SPLIT launches only) with 512 threads, 256 TMEM columns, a
@@ -267,12 +271,13 @@ __global__ void __launch_bounds__(ONE ? T2_THREADS_ONE : T2_THREADS, ONE ? (NKB 
   static_assert(NKB == 1 || ONE, "key blocks: single-tile CTAs");
   constexpr int NIT = NH * NKB;             // (head, key block) iterations of the glimpse per decode step
   constexpr int T2_THREADS = ONE ? htsp::T2_THREADS_ONE : htsp::T2_THREADS;     // (shadow the two-tile constants)
-  constexpr int T2_SLOTS = ONE ? htsp::T2_SLOTS_ONE : htsp::T2_SLOTS;
+  constexpr int T2_SLOTS = ONE ? (NKB > 1 ? T2_SLOTS_KB : htsp::T2_SLOTS_ONE) : htsp::T2_SLOTS;
   constexpr int T2_SLOT = NKB > 1 ? htsp::T2_SLOT_KB : htsp::T2_SLOT;     // (the smaller slots leave room for c0 of all keys with two CTAs per SM)
   constexpr int TILES = ONE ? 1 : 2;
   constexpr int T2B_FULL = TILES * T2B_PER_TILE, T2B_EMPTY = T2B_FULL + T2_FULL_BARS, T2B_TOTAL = T2B_EMPTY + T2_SLOTS;
   constexpr int T2_OCOL = ONE ? 208 : htsp::T2_OCOL, T2_XCOL = ONE ? 240 : htsp::T2_XCOL, TCOLS = ONE ? 256 : 512;
-  static_assert(T2B_TOTAL == t2_bar_total(ONE), "barrier count");
+  static_assert(T2B_TOTAL == t2_bar_total(ONE, NKB > 1), "barrier count");
+  static_assert(T2_SLOTS <= T2_FULL_BARS, "a landed-barrier is reused only after its stage's slot has been released");
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler too
@@ -1118,8 +1123,9 @@ static void t2_choose_split(int Bp, int G, bool debug, int& split, int& rows_per
 
 // dynamic shared memory of a CTA: A tiles, ring, c0, barriers, TMEM slot (+ the stage table of the two-tile variant)
 static size_t t2_smem_bytes(int NP, bool one, bool key_blocks = false) {
-  return (size_t)(one ? 1 : 2) * T2_TILE_STAGING + (size_t)(one ? T2_SLOTS_ONE : T2_SLOTS) * (key_blocks ? T2_SLOT_KB : T2_SLOT) + (size_t)NP * 4 +
-         (size_t)t2_bar_total(one) * 8 + 8 + (one ? 0 : T2_PER_STEP * 8);   // (single-tile CTAs, 208 keys: 115712 bytes -- two per SM with not a byte to spare)
+  return (size_t)(one ? 1 : 2) * T2_TILE_STAGING +
+         (size_t)(one ? (key_blocks ? T2_SLOTS_KB : T2_SLOTS_ONE) : T2_SLOTS) * (key_blocks ? T2_SLOT_KB : T2_SLOT) + (size_t)NP * 4 +
+         (size_t)t2_bar_total(one, key_blocks) * 8 + 8 + (one ? 0 : T2_PER_STEP * 8);   // (single-tile CTAs, 208 keys: 115712 bytes -- two per SM with not a byte to spare)
 }
 
 template <bool LOGITS, bool DEBUG, bool SPLIT, bool SAMPLE = false, bool ONE = false, int NKB = 1>
