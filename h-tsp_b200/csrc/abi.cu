@@ -235,7 +235,7 @@ static int decode_impl(const void* blob, int n_layers, const float* x, const flo
   // src / tgt / first / forced_pi are used as indices: the kernels clamp them, this flags the call (NaN rewards)
   int rc = launch_decode_validate(src, tgt, first, forced_pi, Bp, N, G, idx_flag, s);
   if (rc) return rc;
-  rc = launch_decode_prep(blob, n_layers, emb, src, tgt, Bp, N, proj, qfix, c0, tc, prep_ws, s);
+  rc = launch_decode_prep(blob, n_layers, emb, src, tgt, Bp, N, proj, qfix, c0, tc, prep_ws, idx_flag, s);
   if (rc) return rc;
   rc = decode_dispatch(blob, n_layers, x, emb, proj, qfix, c0, src, tgt, first, Bp, N, G, mode, forced_pi, pi, reward,
                        logits_out, pack_ws, dbg, dbg_step, sample_seed, logp, s);

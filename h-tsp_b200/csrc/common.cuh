@@ -158,7 +158,7 @@ int launch_enc_attention_mma(const __half* qkv_hi, const __half* qkv_lo, __half*
 size_t decode_prep_tc_ws_bytes(int Bp, int N);
 int launch_decode_prep(const void* blob, int n_layers, const float* emb, const int32_t* src,
                        const int32_t* tgt, int Bp, int N, float* proj, float* qfix, float* c0,
-                       bool tensor_cores, void* tc_ws, cudaStream_t s);
+                       bool tensor_cores, void* tc_ws, int32_t* flag, cudaStream_t s);
 // flag[0] |= 1 if any src / tgt / first / forced_pi entry is outside [0, N); poison: reward := NaN when flagged
 int launch_decode_validate(const int32_t* src, const int32_t* tgt, const int32_t* first, const int32_t* forced_pi,
                            int Bp, int N, int G, int32_t* flag, cudaStream_t s);

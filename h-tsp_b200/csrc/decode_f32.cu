@@ -39,6 +39,7 @@ decode_f32_kernel(const float* __restrict__ x, const float* __restrict__ emb,
   unsigned* vis = (unsigned*)(tour + RB * N);  // [RB][NW]
   int* cur = (int*)(vis + RB * NW);          // [RB]
   int* cnt = cur + RB;                       // [RB]
+  int* nocand = cnt + RB;                    // [RB] a decode step found no finite logit: NaN reward
 
   const int src = clamp_index(src_a[b], N), tgt = clamp_index(tgt_a[b], N);
   const float* projb = proj + (size_t)b * N * PROJ;
@@ -57,7 +58,7 @@ decode_f32_kernel(const float* __restrict__ x, const float* __restrict__ emb,
       if (a == src) { tour[r * N + n++] = tgt; vis[r * NW + (tgt >> 5)] |= 1u << (tgt & 31); c = tgt; }
       else if (a == tgt) { tour[r * N + n++] = src; vis[r * NW + (src >> 5)] |= 1u << (src & 31); c = src; }
     }
-    cur[r] = c; cnt[r] = n;
+    cur[r] = c; cnt[r] = n; nocand[r] = 0;
   }
   for (int i = tid; i < RB * H; i += DF_THREADS) {
     const int r = i / H, c = i % H, g = min(g0 + r, G - 1);
@@ -187,6 +188,10 @@ decode_f32_kernel(const float* __restrict__ x, const float* __restrict__ emb,
       if (lane == 0) {
         int n = cnt[r];
         int a = (forced_pi != nullptr) ? clamp_index(forced_pi[((size_t)b * G + g) * N + min(n, N - 1)], N) : bi;
+        if ((unsigned)a >= (unsigned)N) {          // no finite logit (non-finite embeddings): stay in range, flag the row
+          a = cur[r];
+          nocand[r] = 1;
+        }
         int c = a;
         // (n < N always holds for a valid tour; a flagged forced tour that repeats nodes must not write past the row)
         if (n < N) tour[r * N + n++] = a;
@@ -202,6 +207,9 @@ decode_f32_kernel(const float* __restrict__ x, const float* __restrict__ emb,
   for (int r = warp; r < RB; r += DF_THREADS / 32) {
     const int g = g0 + r;
     if (g >= G) continue;
+    // (a flagged row, or a forced tour that repeats nodes, may have recorded fewer than N nodes: every entry must be a node)
+    for (int i = cnt[r] + lane; i < N; i += 32) tour[r * N + i] = cur[r];
+    __syncwarp();
     float len = 0.f;
     for (int i = lane; i < N; i += 32) {
       const int a = tour[r * N + i], c = tour[r * N + (i + 1 == N ? 0 : i + 1)];
@@ -214,7 +222,7 @@ decode_f32_kernel(const float* __restrict__ x, const float* __restrict__ emb,
     if (lane == 0) {
       const float dx = xs[src].x - xs[tgt].x, dy = xs[src].y - xs[tgt].y;
       const float fixed = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
-      reward[(size_t)b * G + g] = -(len - fixed);
+      reward[(size_t)b * G + g] = nocand[r] ? __int_as_float(0x7fc00000) : -(len - fixed);
     }
   }
 }
@@ -223,7 +231,7 @@ template <int RB>
 static size_t decode_f32_smem(int N) {
   const int NW = (N + 31) / 32;
   return (size_t)4 * RB * H * 4 + (size_t)RB * NH * N * 4 + (size_t)RB * N * 4 + (size_t)N * 8 +
-         (size_t)RB * N * 4 + (size_t)RB * NW * 4 + 2 * RB * 4;
+         (size_t)RB * N * 4 + (size_t)RB * NW * 4 + 3 * RB * 4;
 }
 
 template <int RB>

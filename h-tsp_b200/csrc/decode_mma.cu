@@ -216,19 +216,20 @@ __global__ void __launch_bounds__((NWARPS + 1) * 32, 1) decode_mma_kernel(const 
   unsigned* visA = vis + rA * VSTRIDE;
   unsigned* visB = vis + rB * VSTRIDE;
   int curA = 0, curB = 0, cntA = 0, cntB = 0;
+  bool badA = false, badB = false;
   int32_t* piA = A.pi + ((size_t)b * G + min(gA, G - 1)) * N;
   int32_t* piB = A.pi + ((size_t)b * G + min(gB, G - 1)) * N;
 
   // visit(a) with source<->target coupling (train_path_solver.py:45-66); all four lanes of a quad
   // execute it redundantly with identical values (same-value smem writes are benign)
   auto visit = [&](unsigned* v, int32_t* p, int& cur, int& cnt, int a) {
-    if (q4 == 0) p[cnt] = a;
+    if (q4 == 0 && cnt < A.N) p[cnt] = a;          // (a row without finite logits repeats a node: never write past the row)
     v[a >> 5] |= 1u << (a & 31);
     cnt++;
     cur = a;
     const int partner = (a == src) ? tgt : ((a == tgt) ? src : -1);
     if (partner >= 0) {
-      if (q4 == 0) p[cnt] = partner;
+      if (q4 == 0 && cnt < A.N) p[cnt] = partner;
       v[partner >> 5] |= 1u << (partner & 31);
       cnt++;
       cur = partner;
@@ -483,9 +484,17 @@ __global__ void __launch_bounds__((NWARPS + 1) * 32, 1) decode_mma_kernel(const 
     }
     // ---- state update (train_path_solver.py:45-72); all quad lanes hold identical values
     __syncwarp();
+    if ((unsigned)idxA >= (unsigned)N) { idxA = curA; badA = true; }     // a row without finite logits has no candidate:
+    if ((unsigned)idxB >= (unsigned)N) { idxB = curB; badB = true; }     // stay in range, flag the row (NaN reward)
     if (okA) visit(visA, piA, curA, cntA, A.forced_pi ? clamp_index(A.forced_pi[((size_t)b * G + gA) * N + min(cntA, N - 1)], N) : idxA);
     if (okB) visit(visB, piB, curB, cntB, A.forced_pi ? clamp_index(A.forced_pi[((size_t)b * G + gB) * N + min(cntB, N - 1)], N) : idxB);
     __syncwarp();
+  }
+  // (a flagged row, or a forced tour that repeats nodes, may have recorded fewer than N nodes: every entry of its tour
+  // must still be a node, the tour is read as indices below and by the callers)
+  if (q4 == 0) {
+    if (okA) for (; cntA < N; ++cntA) piA[cntA] = curA;
+    if (okB) for (; cntB < N; ++cntB) piB[cntB] = curB;
   }
   // ---- reward = -(closed tour length - fixed edge)   (train_path_solver.py:109-149)
   __syncwarp();
@@ -509,8 +518,8 @@ __global__ void __launch_bounds__((NWARPS + 1) * 32, 1) decode_mma_kernel(const 
     const float dx = xs[src].x - xs[tgt].x, dy = xs[src].y - xs[tgt].y;
     const float fixed = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
     if (q4 == 0) {
-      if (okA) A.reward[(size_t)b * G + gA] = -(lenA - fixed);
-      if (okB) A.reward[(size_t)b * G + gB] = -(lenB - fixed);
+      if (okA) A.reward[(size_t)b * G + gA] = badA ? __int_as_float(0x7fc00000) : -(lenA - fixed);
+      if (okB) A.reward[(size_t)b * G + gB] = badB ? __int_as_float(0x7fc00000) : -(lenB - fixed);
     }
   }
 }

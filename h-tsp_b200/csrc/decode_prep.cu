@@ -21,17 +21,19 @@ decode_prep_kernel(const float* __restrict__ emb, const float* __restrict__ Wg,
                    const float* __restrict__ Ws, const float* __restrict__ Wt,
                    const float* __restrict__ bc, const int32_t* __restrict__ src,
                    const int32_t* __restrict__ tgt, int N, float* __restrict__ qfix,
-                   float* __restrict__ c0) {
+                   float* __restrict__ c0, float amax_limit, int32_t* __restrict__ flag) {
   __shared__ __align__(16) float part[4][H];
   __shared__ __align__(16) float mean[H], es[H], et[H];
   const int b = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const float* e = emb + (size_t)b * N * H;
   const float4 bc4 = __ldg((const float4*)bc + lane);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float amax = 0.f;                      // largest |embedding| this lane has seen (NaNs show up in the sums instead)
 #pragma unroll 4
   for (int n = warp; n < N; n += 4) {
     const float4 v = __ldg((const float4*)(e + (size_t)n * H) + lane);
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    amax = fmaxf(fmaxf(amax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
     float d = fmaf(v.w, bc4.w, fmaf(v.z, bc4.z, fmaf(v.y, bc4.y, v.x * bc4.x)));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
@@ -42,7 +44,11 @@ decode_prep_kernel(const float* __restrict__ emb, const float* __restrict__ Wg,
   et[t] = __ldg(&e[(size_t)clamp_index(tgt[b], N) * H + t]);
   __syncthreads();
   mean[t] = ((part[0][t] + part[1][t]) + (part[2][t] + part[3][t])) / (float)N;
-  __syncthreads();
+  // Embeddings the arithmetic of this call cannot represent -- non-finite ones (an overflow upstream), or, in the
+  // tensor-core modes, |v| >= 65504 (the operands are split into fp16 hi + lo) -- flag the call: its rewards come
+  // back NaN (decode_poison_kernel) instead of tours decided by garbage logits.
+  const bool unrepresentable = !(fabsf(mean[t]) <= 3.0e38f) || !(amax < amax_limit);
+  if (__syncthreads_or(unrepresentable) && t == 0) atomicOr(flag, 2);
   const float4* wg = (const float4*)(Wg + (size_t)t * H);
   const float4* ws = (const float4*)(Ws + (size_t)t * H);
   const float4* wt = (const float4*)(Wt + (size_t)t * H);
@@ -64,7 +70,7 @@ size_t decode_prep_tc_ws_bytes(int Bp, int N) {
 
 int launch_decode_prep(const void* blobv, int n_layers, const float* emb, const int32_t* src,
                        const int32_t* tgt, int Bp, int N, float* proj, float* qfix, float* c0,
-                       bool tensor_cores, void* tc_ws, cudaStream_t s) {
+                       bool tensor_cores, void* tc_ws, int32_t* flag, cudaStream_t s) {
   const float* blob = (const float*)blobv;
   DecOff d = dec_off(n_layers);
   int rc;
@@ -83,7 +89,7 @@ int launch_decode_prep(const void* blobv, int n_layers, const float* emb, const 
   }
   if (rc) return rc;
   decode_prep_kernel<<<Bp, 128, 0, s>>>(emb, blob + d.wg, blob + d.ws, blob + d.wt, blob + d.bc,
-                                        src, tgt, N, qfix, c0);
+                                        src, tgt, N, qfix, c0, tensor_cores ? 65504.f : 3.0e38f, flag);
   HTSP_CHECK_LAUNCH();
   return HTSP_OK;
 }

@@ -452,19 +452,20 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
         vis[w] = (lo + 32 <= N) ? 0u : ((N <= lo) ? 0xffffffffu : (0xffffffffu << (N - lo)));
       }
       int cur = 0, cnt = 0;
+      bool nocand = false;                           // a decode step found no finite logit: the reward is NaN
       auto mark = [&](int a) {
 #pragma unroll
         for (int w = 0; w < 7; ++w) vis[w] |= ((a >> 5) == w) ? (1u << (a & 31)) : 0u;
       };
       // visit(a) with source<->target coupling (train_path_solver.py:45-66); only the primary records pi
       auto visit = [&](int a) {
-        if (valid && half == 0 && (!(LOGITS || DEBUG) || cnt < N)) pirow[cnt] = a;     // (a forced tour may repeat nodes)
+        if (valid && half == 0 && cnt < N) pirow[cnt] = a;     // (a forced tour, or a row without finite logits, may repeat nodes)
         mark(a);
         cnt++;
         cur = a;
         const int partner = (a == src) ? tgt : ((a == tgt) ? src : -1);
         if (partner >= 0) {
-          if (valid && half == 0 && (!(LOGITS || DEBUG) || cnt < N)) pirow[cnt] = partner;
+          if (valid && half == 0 && cnt < N) pirow[cnt] = partner;
           mark(partner);
           cnt++;
           cur = partner;
@@ -829,6 +830,10 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
           if (__uint_as_float(bz) > best) idx = (int)bi;     // ties keep the primary's (lower) key
           // ---- state update (train_path_solver.py:45-72); the chosen node goes to the secondary warp
           a = ((LOGITS || DEBUG) && A.forced_pi) ? clamp_index(A.forced_pi[((size_t)b * GT + r0 + gc) * N + min(cnt, N - 1)], N) : idx;   // teacher forcing: LOGITS / DEBUG kernels only
+          if ((unsigned)a >= (unsigned)N) {            // a row without finite logits has no candidate: stay in range, flag the row
+            a = cur;
+            nocand = true;
+          }
           asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tX + 8), "r"((uint32_t)a) : "memory");
           tc::st_wait();
           tc::fence_before();
@@ -839,6 +844,10 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
         if (step + 1 < n_steps) gather_q();
         tick(5);
       }
+      // (a flagged row, or a forced tour that repeats nodes, may have recorded fewer than N nodes: every entry of its
+      // tour must still be a node, the tour is read as indices below and by the callers)
+      if (valid && half == 0)
+        for (; cnt < N; ++cnt) pirow[cnt] = cur;
       // ---- reward = -(closed tour length - fixed edge)   (train_path_solver.py:109-149)
       if (valid && half == 0) {
         const float2* xb = (const float2*)A.x + (size_t)b * N;
@@ -854,7 +863,7 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) decode_tc_kernel(const TcdArgs
         const float2 ps = __ldg(&xb[src]), pt = __ldg(&xb[tgt]);
         const float dx = ps.x - pt.x, dy = ps.y - pt.y;
         const float fixed = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
-        A.reward[(size_t)b * GT + r0 + g] = -(len - fixed);
+        A.reward[(size_t)b * GT + r0 + g] = nocand ? __int_as_float(0x7fc00000) : -(len - fixed);
       }
       if (DEBUG && b == 0 && lane == 0) {
         float* dT = A.dbg + (size_t)2 * 8 * 128 * NP + (size_t)256 * 128 + (size_t)256 * NP + sw * 8;

@@ -614,13 +614,13 @@ __global__ void __launch_bounds__(ONE ? T2_THREADS_ONE : T2_THREADS, ONE ? (NKB 
       };
       // visit(a) with source<->target coupling (train_path_solver.py:45-66); only part 0 records pi
       auto visit = [&](int a) {
-        if (valid && part == 0 && (!(LOGITS || DEBUG) || cnt < N)) pirow[cnt] = a;     // (a forced tour may repeat nodes)
+        if (valid && part == 0 && cnt < N) pirow[cnt] = a;     // (a forced tour, or a row without finite logits, may repeat nodes)
         mark(a);
         cnt++;
         cur = a;
         const int partner = (a == src) ? tgt : ((a == tgt) ? src : -1);
         if (partner >= 0) {
-          if (valid && part == 0 && (!(LOGITS || DEBUG) || cnt < N)) pirow[cnt] = partner;
+          if (valid && part == 0 && cnt < N) pirow[cnt] = partner;
           mark(partner);
           cnt++;
           cur = partner;
@@ -972,6 +972,10 @@ __global__ void __launch_bounds__(ONE ? T2_THREADS_ONE : T2_THREADS, ONE ? (NKB 
         if (step + 1 < n_steps) gather_q();
         tick(5);
       }
+      // (a flagged row -- no finite logits, or a forced tour that repeats nodes -- may have recorded fewer than N nodes:
+      // every entry of its tour must still be a node, the tour is read as indices below and by the callers)
+      if (valid && part == 0)
+        for (; cnt < N; ++cnt) pirow[cnt] = cur;
       // ---- reward = -(closed tour length - fixed edge)   (train_path_solver.py:109-149)
       if (valid && part == 0) {
         const float2* xb = (const float2*)A.x + (size_t)b * N;

@@ -669,10 +669,21 @@ def test_activations_beyond_the_fp16_range_are_reported(built_lib):
     g = torch.Generator().manual_seed(5)
     data = torch.rand(2, 300, 2, generator=g).cuda()
     frag = torch.stack([torch.randperm(300, generator=g)[:40] for _ in range(2)]).cuda()
+    x = torch.rand(3, 230, 2, generator=g).cuda()                  # (230 nodes: the key-block / mma.sync kernels)
+    src, tgt, first = torch.zeros(3, dtype=torch.long), torch.full((3,), 229), torch.arange(5)
     for mode in ("x3", "fast"):
-        hook = B200RLSolver(B200PathSolver(state_dict=sd, mode=mode, device="cuda"), sample_size=4)
+        m = B200PathSolver(state_dict=sd, mode=mode, device="cuda")
+        hook = B200RLSolver(m, sample_size=4)
         with pytest.raises(FloatingPointError, match="fp32"):
             hook.solve(data, frag, None)
+        # the raw rollout: NaN rewards, and tours whose every entry is still a node (a row without finite logits
+        # records fewer than N nodes; its tour used to keep uninitialised entries that were then read as indices)
+        for xx, s_, t_, f_ in ((x, src, tgt, first), (x[:, :40].contiguous(), src, torch.full((3,), 39), first)):
+            pi, rew, _ = m.rollout(xx, m.encode(xx), s_, t_, f_)
+            assert bool(torch.isnan(rew).all()) and int(pi.min()) >= 0 and int(pi.max()) < xx.shape[1]
+    ok = B200RLSolver(B200PathSolver(state_dict=synthetic_state_dict(1234, 2), mode="fast", device="cuda"), sample_size=4)
+    paths, lens = ok.solve(data, frag, None)                      # the CUDA context is still usable
+    assert np.isfinite(lens).all() and sorted(paths[0]) == sorted(frag[0].tolist())
 
 
 def test_packed_weights_follow_in_place_parameter_updates(built_lib):
