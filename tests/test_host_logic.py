@@ -80,3 +80,43 @@ def test_make_reference_subclass_is_a_reference_rlsolver():
     assert type(solver).solve is rl_solver.B200RLSolver.solve
     assert type(solver).solve is not h_tsp.RLSolver.solve
     assert solver._sample_size == 2 and solver._solver_model is model      # max(sample_size, 2), h_tsp.py:168
+
+
+def test_hook_reports_a_failed_rollout_by_cause():
+    """B200RLSolver.solve turns what the device returned into the reference's contract (h_tsp.py:206-228) and names
+    the cause of a failure: bad indices -> IndexError (torch.gather's error in the reference),
+    non-finite rewards or a repeated node with good indices -> FloatingPointError naming mode='fp32', any other failed
+    path check -> the reference's AssertionError.  Host logic only: solve_device is replaced by canned tensors."""
+    import numpy as np
+    from htsp_b200 import rl_solver
+    from htsp_b200.path_solver import B200PathSolver
+
+    model = B200PathSolver.__new__(B200PathSolver)      # no device work
+    torch.nn.Module.__init__(model)
+    model.mode = "fast"
+    model.first_action_override = None
+    hook = rl_solver.B200RLSolver(model, sample_size=4)
+    B, N = 2, 5
+    paths = torch.arange(N).repeat(B, 1) + 10
+    x_ok = torch.rand(B, N, 2)
+
+    def canned(lengths, status, x_new):
+        hook.solve_device = lambda data, fragment, frag_buffer=None: (paths, torch.tensor(lengths), torch.tensor(status, dtype=torch.int32), x_new)
+        return hook.solve(None, None, None)
+
+    got_paths, got_lens = canned([1.5, 2.5], [0, 0], x_ok)
+    assert got_paths == paths.tolist() and np.allclose(got_lens, [1.5, 2.5])
+    x_nan = x_ok.clone()
+    x_nan[1] = float("nan")
+    with pytest.raises(IndexError, match=r"\[1\]"):
+        canned([1.5, float("nan")], [0, 0], x_nan)                   # htsp_extract_normalize flagged fragment ids
+    model.first_action_override = torch.tensor([0, 1, 2, N])          # a POMO start outside [0, N)
+    with pytest.raises(IndexError):
+        canned([float("nan"), float("nan")], [0, 0], x_ok)
+    model.first_action_override = None
+    with pytest.raises(FloatingPointError, match="mode='fp32'"):
+        canned([float("nan"), 2.5], [0, 0], x_ok)                    # indices fine, no finite reward
+    with pytest.raises(FloatingPointError, match="fp32"):
+        canned([1.5, 2.5], [0, 4], x_ok)                             # ... or a tour that repeats a node
+    with pytest.raises(AssertionError, match="status"):
+        canned([1.5, 2.5], [2, 0], x_ok)                             # the reference's own path asserts
